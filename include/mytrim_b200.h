@@ -279,6 +279,9 @@ int mtb_tally_device_views(mtb_handle * h, void ** u64_dev, size_t * n_u64, void
 /* Single-process multi-GPU reduction of the additive tallies into handles[0] (NCCL all-reduce). */
 int mtb_allreduce(mtb_handle ** handles, int n_handles);
 
+/* Measures the FP32 FMA issue rate of `device` (the roofline denominator of this path). */
+int mtb_measure_fp32_peak(int device, double * tflops, float * ms);
+
 /* Replaces one TrimBase::trim(pka, recoils) call for arbitrary subclasses: follows ONE ion,
  * never follows recoils, and reports every collision so the host can run the virtual hooks
  * and fill its own std::queue.  `ion` is updated in place (final pos/dir/E/state). */

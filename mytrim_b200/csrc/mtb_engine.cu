@@ -1,0 +1,1005 @@
+// mtb_engine.cu — CUDA kernels (sm_100a) and the extern "C" layer of include/mytrim_b200.h.
+//
+// Kernels:
+//   transport_kernel      persistent lanes, one cascade per lane at a time (mtb_transport.cuh)
+//   trim_one_kernel       single-ion event mode behind mtb_trim_one
+//   stopping_kernel       batched MaterialBase::getrstop
+// The host part flattens the caller's configuration into device tables, owns all device
+// buffers, launches, and reads tallies back.  No torch types, no exceptions across the ABI.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "mtb_tables.h"
+#include "mtb_transport.cuh"
+
+using namespace mtb;
+
+namespace
+{
+thread_local std::string g_last_error;
+
+int
+fail(int code, const std::string & msg)
+{
+  g_last_error = msg;
+  return code;
+}
+
+#define MTB_CUDA(call)                                                                                   \
+  do                                                                                                     \
+  {                                                                                                      \
+    cudaError_t err__ = (call);                                                                          \
+    if (err__ != cudaSuccess)                                                                            \
+      return fail(MTB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(err__));                     \
+  } while (0)
+
+constexpr int kBlock = 128;
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+struct SmemLayout
+{
+  size_t elements, materials, ionz, layer_cum, layer_mat, hist_vac, hist_repl, blk_u64, blk_f64, total;
+};
+
+__host__ __device__ inline size_t
+align_up(size_t v, size_t a)
+{
+  return (v + a - 1) / a * a;
+}
+
+__host__ __device__ inline SmemLayout
+smem_layout(const LaunchParams & P)
+{
+  SmemLayout L;
+  size_t o = 0;
+  L.blk_u64 = o;
+  o += CNT_COUNT * sizeof(unsigned long long);
+  L.blk_f64 = o;
+  o += 2 * sizeof(double);
+  L.layer_cum = o;
+  o += (size_t)P.n_layers * sizeof(double);
+  L.elements = o = align_up(o, 16);
+  o += (size_t)P.n_elements * sizeof(DevElement);
+  L.materials = o = align_up(o, 16);
+  o += (size_t)P.n_materials * sizeof(DevMaterial);
+  L.ionz = o = align_up(o, 16);
+  o += (MTB_NZ + 1) * sizeof(DevIonZ);
+  L.layer_mat = o;
+  o += (size_t)P.n_layers * sizeof(int32_t);
+  L.hist_vac = o = align_up(o, 16);
+  o += (size_t)P.smem_hist_bins * sizeof(unsigned int);
+  L.hist_repl = o;
+  o += (size_t)P.smem_hist_bins * sizeof(unsigned int);
+  L.total = align_up(o, 16);
+  return L;
+}
+
+template <class T>
+__device__ inline void
+block_copy(T * dst, const T * src, size_t n)
+{
+  const uint32_t * s = reinterpret_cast<const uint32_t *>(src);
+  uint32_t * d = reinterpret_cast<uint32_t *>(dst);
+  const size_t words = n * sizeof(T) / 4;
+  for (size_t i = threadIdx.x; i < words; i += blockDim.x)
+    d[i] = s[i];
+}
+
+__device__ inline BlockCtx
+stage_block(const LaunchParams & P, unsigned char * smem)
+{
+  const SmemLayout L = smem_layout(P);
+  BlockCtx S;
+  DevElement * el = reinterpret_cast<DevElement *>(smem + L.elements);
+  DevMaterial * mat = reinterpret_cast<DevMaterial *>(smem + L.materials);
+  DevIonZ * iz = reinterpret_cast<DevIonZ *>(smem + L.ionz);
+  double * lc = reinterpret_cast<double *>(smem + L.layer_cum);
+  int32_t * lm = reinterpret_cast<int32_t *>(smem + L.layer_mat);
+  unsigned int * hv = reinterpret_cast<unsigned int *>(smem + L.hist_vac);
+  unsigned int * hr = reinterpret_cast<unsigned int *>(smem + L.hist_repl);
+  unsigned long long * bu = reinterpret_cast<unsigned long long *>(smem + L.blk_u64);
+  double * bf = reinterpret_cast<double *>(smem + L.blk_f64);
+  block_copy(el, P.elements, (size_t)P.n_elements);
+  block_copy(mat, P.materials, (size_t)P.n_materials);
+  block_copy(iz, P.ionz, (size_t)MTB_NZ + 1);
+  if (P.n_layers > 0)
+  {
+    block_copy(lc, P.layer_cum, (size_t)P.n_layers);
+    block_copy(lm, P.layer_mat, (size_t)P.n_layers);
+  }
+  for (int i = threadIdx.x; i < 2 * P.smem_hist_bins; i += blockDim.x)
+    hv[i] = 0u; // hist_repl follows hist_vac
+  if (threadIdx.x < CNT_COUNT)
+    bu[threadIdx.x] = 0ull;
+  if (threadIdx.x < 2)
+    bf[threadIdx.x] = 0.0;
+  __syncthreads();
+  S.elements = el;
+  S.materials = mat;
+  S.ionz = iz;
+  S.layer_cum = lc;
+  S.layer_mat = lm;
+  S.hist_vac = hv;
+  S.hist_repl = hr;
+  S.blk_u64 = bu;
+  S.blk_f64 = bf;
+  return S;
+}
+
+__device__ inline void
+flush_block(const LaunchParams & P, const BlockCtx & S)
+{
+  __syncthreads();
+  for (int i = threadIdx.x; i < P.smem_hist_bins; i += blockDim.x)
+  {
+    const unsigned int v = S.hist_vac[i], r = S.hist_repl[i];
+    if (v)
+      atomicAdd(&P.u64[off_vac(P) + i], (unsigned long long)v);
+    if (r)
+      atomicAdd(&P.u64[off_repl(P) + i], (unsigned long long)r);
+  }
+  if (threadIdx.x < CNT_STACKMAX)
+  {
+    const unsigned long long v = S.blk_u64[threadIdx.x];
+    if (v)
+      atomicAdd(&P.u64[threadIdx.x], v);
+  }
+  if (threadIdx.x == CNT_STACKMAX)
+    atomicMax(&P.u64[CNT_STACKMAX], S.blk_u64[CNT_STACKMAX]);
+  if (threadIdx.x < 2 && S.blk_f64[threadIdx.x] != 0.0)
+    atomicAdd(&P.f64[threadIdx.x], S.blk_f64[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(kBlock)
+transport_kernel(const __grid_constant__ LaunchParams P)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const BlockCtx S = stage_block(P, smem);
+  lane_loop<false>(P, S, blockIdx.x * blockDim.x + threadIdx.x);
+  flush_block(P, S);
+}
+
+__global__ void __launch_bounds__(32)
+trim_one_kernel(const __grid_constant__ LaunchParams P)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const BlockCtx S = stage_block(P, smem);
+  if (threadIdx.x == 0)
+    lane_loop<true>(P, S, 0);
+  flush_block(P, S);
+}
+
+__global__ void
+stopping_kernel(const __grid_constant__ LaunchParams P, int material, size_t n, const int32_t * Z1,
+                const double * m1, const double * E, double * out)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const BlockCtx S = stage_block(P, smem);
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+  {
+    Projectile pr;
+    const DevIonZ & iz = S.ionz[Z1[i]];
+    pr.Z = Z1[i];
+    pr.fz = (float)Z1[i];
+    pr.m = m1[i] == 0.0 ? iz.mm1 : (float)m1[i];
+    pr.z023 = iz.z023;
+    pr.cbrt = iz.cbrt;
+    pr.lfctr = iz.lfctr;
+    out[i] = (double)material_stopping(pr, S.materials[material], S.elements, (float)E[i]);
+  }
+}
+
+// FP32 FMA issue-rate probe: the roofline denominator of this path is the FP32
+// pipe, and MEASURED_PEAKS.json only carries HBM and tensor numbers.  8 independent FMA chains per
+// thread, 2 flops per FMA.
+__global__ void __launch_bounds__(256)
+fp32_peak_kernel(float * out, int iters, float a, float b)
+{
+  float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f,
+        x7 = x0 + 7.f;
+  for (int i = 0; i < iters; ++i)
+  {
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+    {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 12345.678f)
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <class T>
+struct DevBuf
+{
+  T * p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release()
+  {
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t ensure(size_t count)
+  {
+    if (count <= n)
+      return cudaSuccess;
+    release();
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess)
+      n = count;
+    return e;
+  }
+  cudaError_t upload(const T * src, size_t count, cudaStream_t s)
+  {
+    cudaError_t e = ensure(count);
+    if (e != cudaSuccess || !count)
+      return e;
+    return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+};
+} // namespace
+
+struct mtb_handle
+{
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 0, blocks_per_sm = 0;
+
+  HostConfig host; // host copies of the configuration
+  bool dirty = true, have_materials = false;
+
+  // device tables
+  DevBuf<DevElement> d_elements;
+  DevBuf<DevMaterial> d_materials;
+  DevBuf<DevIonZ> d_ionz;
+  DevBuf<double> d_layer_cum, d_cl_xyzr;
+  DevBuf<int32_t> d_layer_mat, d_cl_hash, d_cl_next;
+  // outputs
+  DevBuf<unsigned long long> d_u64;
+  DevBuf<double> d_f64;
+  DevBuf<mtb_record> d_records;
+  DevBuf<mtb_ion_log> d_ionlog;
+  DevBuf<RangeEntry> d_range;
+  DevBuf<StackEntry> d_stacks;
+  DevBuf<mtb_ion> d_primaries;
+  DevBuf<mtb_event> d_events;
+  uint64_t n_resident = 0;
+  uint64_t last_n = 0;
+  bool records_valid = false;
+
+  LaunchParams P;
+  size_t u64_size = 0;
+  size_t smem_bytes = 0;
+  float last_ms = 0.f;
+  bool timing_pending = false;
+};
+
+namespace
+{
+int
+build_tables(mtb_handle * h)
+{
+  if (!h->have_materials)
+    return fail(MTB_EINVAL, "mtb_set_materials has not been called");
+  const mtb_config & c = h->host.cfg;
+  LaunchParams & P = h->P;
+  HostTables T;
+  std::string err;
+  if (int rc = build_host_tables(h->host, T, P, err))
+    return fail(rc, err);
+
+  MTB_CUDA(h->d_elements.upload(T.elements.data(), T.elements.size(), h->stream));
+  MTB_CUDA(h->d_materials.upload(T.materials.data(), T.materials.size(), h->stream));
+  MTB_CUDA(h->d_ionz.upload(T.ionz.data(), T.ionz.size(), h->stream));
+  P.elements = h->d_elements.p;
+  P.materials = h->d_materials.p;
+  P.ionz = h->d_ionz.p;
+  if (P.n_layers)
+  {
+    MTB_CUDA(h->d_layer_cum.upload(T.layer_cum.data(), T.layer_cum.size(), h->stream));
+    MTB_CUDA(h->d_layer_mat.upload(T.layer_mat.data(), T.layer_mat.size(), h->stream));
+    P.layer_cum = h->d_layer_cum.p;
+    P.layer_mat = h->d_layer_mat.p;
+  }
+  if (P.geom_kind == MTB_GEOM_CLUSTERS)
+  {
+    MTB_CUDA(h->d_cl_hash.upload(T.cl_hash.data(), T.cl_hash.size(), h->stream));
+    MTB_CUDA(h->d_cl_next.upload(T.cl_next.data(), T.cl_next.size(), h->stream));
+    MTB_CUDA(h->d_cl_xyzr.upload(h->host.cluster_xyzr.data(), h->host.cluster_xyzr.size(), h->stream));
+    P.cl_hash = h->d_cl_hash.p;
+    P.cl_next = h->d_cl_next.p;
+    P.cl_xyzr = h->d_cl_xyzr.p;
+  }
+  MTB_CUDA(cudaStreamSynchronize(h->stream)); // T goes out of scope
+
+  const size_t nu64 = u64_block_size(P);
+  if (nu64 != h->u64_size)
+  {
+    h->d_u64.release();
+    MTB_CUDA(h->d_u64.ensure(nu64));
+    MTB_CUDA(cudaMemsetAsync(h->d_u64.p, 0, nu64 * sizeof(unsigned long long), h->stream));
+    h->u64_size = nu64;
+  }
+  if (!h->d_f64.p)
+  {
+    MTB_CUDA(h->d_f64.ensure(2));
+    MTB_CUDA(cudaMemsetAsync(h->d_f64.p, 0, 2 * sizeof(double), h->stream));
+  }
+  P.u64 = h->d_u64.p;
+  P.f64 = h->d_f64.p;
+  if (c.tally_mask & MTB_TALLY_IONLOG)
+  {
+    MTB_CUDA(h->d_ionlog.ensure(P.ionlog_cap));
+    P.ionlog = h->d_ionlog.p;
+  }
+  if (c.tally_mask & MTB_TALLY_RANGE)
+  {
+    MTB_CUDA(h->d_range.ensure(P.range_cap));
+    P.range = h->d_range.p;
+  }
+
+  h->smem_bytes = smem_layout(P).total;
+  if (h->smem_bytes > 200 * 1024)
+    return fail(MTB_EINVAL, "configuration tables do not fit in shared memory");
+  MTB_CUDA(cudaFuncSetAttribute(transport_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  MTB_CUDA(cudaFuncSetAttribute(trim_one_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  MTB_CUDA(cudaFuncSetAttribute(stopping_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  int bps = 0;
+  MTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, transport_kernel, kBlock, h->smem_bytes));
+  h->blocks_per_sm = std::max(bps, 1);
+  h->dirty = false;
+  return MTB_OK;
+}
+
+int
+ensure_ready(mtb_handle * h)
+{
+  if (!h)
+    return fail(MTB_EINVAL, "null handle");
+  MTB_CUDA(cudaSetDevice(h->device));
+  if (h->dirty)
+    return build_tables(h);
+  return MTB_OK;
+}
+
+int
+launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, const mtb_ion * beam, uint64_t seed,
+                 uint64_t first_index, bool want_records)
+{
+  LaunchParams & P = h->P;
+  P.primaries = primaries_dev;
+  if (beam)
+    P.beam = *beam;
+  P.n_primaries = n;
+  P.first_index = first_index;
+  P.key0 = (uint32_t)seed;
+  P.key1 = (uint32_t)(seed >> 32);
+  P.records = nullptr;
+  if (want_records)
+  {
+    MTB_CUDA(h->d_records.ensure(n));
+    P.records = h->d_records.p;
+  }
+  h->records_valid = want_records;
+  h->last_n = n;
+  if (!n)
+    return MTB_OK;
+  const uint64_t max_blocks = (uint64_t)h->sm_count * h->blocks_per_sm;
+  const uint64_t want_blocks = (n + kBlock - 1) / kBlock;
+  const unsigned blocks = (unsigned)std::min(max_blocks, want_blocks);
+  MTB_CUDA(h->d_stacks.ensure((size_t)blocks * kBlock * MTB_STACK_DEPTH));
+  P.stacks = h->d_stacks.p;
+  MTB_CUDA(cudaMemsetAsync(&P.u64[CNT_NEXT_PRIMARY], 0, sizeof(unsigned long long), h->stream));
+  MTB_CUDA(cudaEventRecord(h->ev0, h->stream));
+  transport_kernel<<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+  MTB_CUDA(cudaGetLastError());
+  MTB_CUDA(cudaEventRecord(h->ev1, h->stream));
+  h->timing_pending = true;
+  return MTB_OK;
+}
+
+int
+sync_and_check(mtb_handle * h)
+{
+  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->timing_pending)
+  {
+    MTB_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    h->timing_pending = false;
+  }
+  unsigned long long err = 0;
+  MTB_CUDA(cudaMemcpy(&err, h->d_u64.p + CNT_ERROR, sizeof(err), cudaMemcpyDeviceToHost));
+  if (err)
+    return fail(MTB_ESTACK, "recoil stack overflow in " + std::to_string(err) + " collision(s)");
+  return MTB_OK;
+}
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// extern "C"
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *
+mtb_version(void)
+{
+  return "mytrim_b200 0.1 (sm_100a)";
+}
+
+const char *
+mtb_last_error(void)
+{
+  return g_last_error.c_str();
+}
+
+int
+mtb_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess)
+    return 0;
+  return n;
+}
+
+void
+mtb_default_config(mtb_config * cfg)
+{
+  default_config(cfg);
+}
+
+int
+mtb_create(const mtb_config * cfg, mtb_handle ** out)
+{
+  if (!cfg || !out)
+    return fail(MTB_EINVAL, "null argument");
+  if (!(cfg->length_scale > 0.0) || cfg->potential < 0 || cfg->potential > 2)
+    return fail(MTB_EINVAL, "bad configuration");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(MTB_ENODEV, "no CUDA device: the transport engine has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev)
+    return fail(MTB_EINVAL, "device ordinal out of range");
+  MTB_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  MTB_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major < 10)
+    return fail(MTB_ENODEV, std::string("device ") + prop.name + " is not sm_100 class");
+  mtb_handle * h = new (std::nothrow) mtb_handle();
+  if (!h)
+    return fail(MTB_ENOMEM, "out of memory");
+  h->host.cfg = *cfg;
+  h->device = cfg->device;
+  h->sm_count = prop.multiProcessorCount;
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess)
+    e = cudaEventCreate(&h->ev0);
+  if (e == cudaSuccess)
+    e = cudaEventCreate(&h->ev1);
+  if (e != cudaSuccess)
+  {
+    delete h;
+    return fail(MTB_ECUDA, cudaGetErrorString(e));
+  }
+  *out = h;
+  return MTB_OK;
+}
+
+int
+mtb_destroy(mtb_handle * h)
+{
+  if (!h)
+    return MTB_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  cudaEventDestroy(h->ev0);
+  cudaEventDestroy(h->ev1);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return MTB_OK;
+}
+
+int
+mtb_get_tables(double * pcoef, double * vfermi, double * lfctr, double * mm1)
+{
+  for (int z = 0; z < MTB_NZ; ++z)
+  {
+    if (pcoef)
+      std::memcpy(pcoef + 8 * z, builtin_zbl()[z].pcoef, 8 * sizeof(double));
+    if (vfermi)
+      vfermi[z] = builtin_zbl()[z].vfermi;
+    if (lfctr)
+      lfctr[z] = builtin_zbl()[z].lfctr;
+    if (mm1)
+      mm1[z] = builtin_zbl()[z].mm1;
+  }
+  return MTB_OK;
+}
+
+int
+mtb_set_tables(mtb_handle * h, const double * pcoef, const double * vfermi, const double * lfctr, const double * mm1)
+{
+  if (!h)
+    return fail(MTB_EINVAL, "null handle");
+  for (int z = 0; z < MTB_NZ; ++z)
+  {
+    if (pcoef)
+      std::memcpy(h->host.zbl[z].pcoef, pcoef + 8 * z, 8 * sizeof(double));
+    if (vfermi)
+      h->host.zbl[z].vfermi = vfermi[z];
+    if (lfctr)
+      h->host.zbl[z].lfctr = lfctr[z];
+    if (mm1)
+      h->host.zbl[z].mm1 = mm1[z];
+  }
+  h->dirty = true;
+  return MTB_OK;
+}
+
+int
+mtb_set_materials(mtb_handle * h, int n_materials, const mtb_material * materials, int n_elements,
+                  const mtb_element * elements)
+{
+  if (!h)
+    return fail(MTB_EINVAL, "null handle");
+  std::string err;
+  if (int rc = check_materials(n_materials, materials, n_elements, elements, err))
+    return fail(rc, err);
+  h->host.materials.assign(materials, materials + n_materials);
+  h->host.elements.assign(elements, elements + n_elements);
+  h->have_materials = true;
+  h->dirty = true;
+  return MTB_OK;
+}
+
+int
+mtb_set_geometry(mtb_handle * h, const mtb_geometry * g)
+{
+  if (!h)
+    return fail(MTB_EINVAL, "null handle");
+  std::string err;
+  if (int rc = check_geometry(g, err))
+    return fail(rc, err);
+  h->host.layer_thickness.clear();
+  h->host.cluster_xyzr.clear();
+  if (g->kind == MTB_GEOM_LAYERS)
+    h->host.layer_thickness.assign(g->layer_thickness, g->layer_thickness + g->n_layers);
+  if (g->kind == MTB_GEOM_CLUSTERS && g->n_clusters)
+    h->host.cluster_xyzr.assign(g->cluster_xyzr, g->cluster_xyzr + 4 * (size_t)g->n_clusters);
+  h->host.geom = *g;
+  h->host.geom.layer_thickness = nullptr;
+  h->host.geom.cluster_xyzr = nullptr;
+  h->dirty = true;
+  return MTB_OK;
+}
+
+int
+mtb_upload_primaries(mtb_handle * h, uint64_t n, const mtb_ion * primaries)
+{
+  if (int rc = ensure_ready(h))
+    return rc;
+  if (n && !primaries)
+    return fail(MTB_EINVAL, "null primaries");
+  MTB_CUDA(h->d_primaries.upload(primaries, n, h->stream));
+  h->n_resident = n;
+  return MTB_OK;
+}
+
+int
+mtb_launch_resident(mtb_handle * h, uint64_t seed, uint64_t first_index)
+{
+  if (int rc = ensure_ready(h))
+    return rc;
+  return launch_transport(h, h->n_resident, h->d_primaries.p, nullptr, seed, first_index,
+                          (h->host.cfg.tally_mask & MTB_TALLY_RECORDS) != 0);
+}
+
+int
+mtb_synchronize(mtb_handle * h)
+{
+  if (!h)
+    return fail(MTB_EINVAL, "null handle");
+  MTB_CUDA(cudaSetDevice(h->device));
+  return sync_and_check(h);
+}
+
+int
+mtb_last_kernel_ms(mtb_handle * h, float * ms)
+{
+  if (!h || !ms)
+    return fail(MTB_EINVAL, "null argument");
+  if (h->timing_pending)
+    if (int rc = mtb_synchronize(h))
+      return rc;
+  *ms = h->last_ms;
+  return MTB_OK;
+}
+
+int
+mtb_fetch_records(mtb_handle * h, uint64_t n, mtb_record * records)
+{
+  if (!h || !records)
+    return fail(MTB_EINVAL, "null argument");
+  if (!h->records_valid || n > h->last_n)
+    return fail(MTB_EINVAL, "no records: enable MTB_TALLY_RECORDS");
+  MTB_CUDA(cudaSetDevice(h->device));
+  MTB_CUDA(cudaMemcpyAsync(records, h->d_records.p, n * sizeof(mtb_record), cudaMemcpyDeviceToHost, h->stream));
+  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  return MTB_OK;
+}
+
+int
+mtb_run(mtb_handle * h, uint64_t n, const mtb_ion * primaries, uint64_t seed, uint64_t first_index,
+        mtb_record * records)
+{
+  if (int rc = mtb_upload_primaries(h, n, primaries))
+    return rc;
+  if (int rc = launch_transport(h, n, h->d_primaries.p, nullptr, seed, first_index, records != nullptr))
+    return rc;
+  if (int rc = sync_and_check(h))
+    return rc;
+  if (records && n)
+    return mtb_fetch_records(h, n, records);
+  return MTB_OK;
+}
+
+int
+mtb_run_beam(mtb_handle * h, uint64_t n, const mtb_ion * ion, uint64_t seed, uint64_t first_index,
+             mtb_record * records)
+{
+  if (int rc = ensure_ready(h))
+    return rc;
+  if (!ion)
+    return fail(MTB_EINVAL, "null ion");
+  if (int rc = launch_transport(h, n, nullptr, ion, seed, first_index, records != nullptr))
+    return rc;
+  if (int rc = sync_and_check(h))
+    return rc;
+  if (records && n)
+    return mtb_fetch_records(h, n, records);
+  return MTB_OK;
+}
+
+int
+mtb_reset_tallies(mtb_handle * h)
+{
+  if (int rc = ensure_ready(h))
+    return rc;
+  MTB_CUDA(cudaMemsetAsync(h->d_u64.p, 0, h->u64_size * sizeof(unsigned long long), h->stream));
+  MTB_CUDA(cudaMemsetAsync(h->d_f64.p, 0, 2 * sizeof(double), h->stream));
+  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  return MTB_OK;
+}
+
+int
+mtb_get_counters(mtb_handle * h, mtb_counters * out)
+{
+  if (int rc = ensure_ready(h))
+    return rc;
+  if (!out)
+    return fail(MTB_EINVAL, "null argument");
+  unsigned long long c[CNT_COUNT];
+  double f[2];
+  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  MTB_CUDA(cudaMemcpy(c, h->d_u64.p, sizeof(c), cudaMemcpyDeviceToHost));
+  MTB_CUDA(cudaMemcpy(f, h->d_f64.p, sizeof(f), cudaMemcpyDeviceToHost));
+  out->vacancies_created = c[CNT_VAC];
+  out->replacements = c[CNT_REPL];
+  out->steps = c[CNT_STEPS];
+  out->ions = c[CNT_IONS];
+  out->primaries = c[CNT_PRIMARIES];
+  out->recoils_queued = c[CNT_QUEUED];
+  out->lost = c[CNT_LOST];
+  out->left_sample = c[CNT_LEFT];
+  out->hist_clamped = c[CNT_CLAMPED];
+  out->stack_max = c[CNT_STACKMAX];
+  out->EelTotal = f[0];
+  out->EnucTotal = f[1];
+  return MTB_OK;
+}
+
+int
+mtb_hist_bins(mtb_handle * h, size_t * bins, size_t * evac_rows)
+{
+  if (int rc = ensure_ready(h))
+    return rc;
+  if (bins)
+    *bins = (size_t)h->P.hist_bins;
+  if (evac_rows)
+    *evac_rows = (size_t)h->P.evac_rows;
+  return MTB_OK;
+}
+
+int
+mtb_get_vac_depth(mtb_handle * h, uint64_t * vac, uint64_t * repl, size_t capacity, size_t * n_bins)
+{
+  if (int rc = ensure_ready(h))
+    return rc;
+  const size_t B = (size_t)h->P.hist_bins;
+  std::vector<unsigned long long> buf(2 * B);
+  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  MTB_CUDA(cudaMemcpy(buf.data(), h->d_u64.p + off_vac(h->P), 2 * B * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  size_t last = 0;
+  for (size_t i = 0; i < B; ++i)
+    if (buf[i] || buf[B + i])
+      last = i + 1;
+  if (n_bins)
+    *n_bins = last;
+  for (size_t i = 0; i < capacity; ++i)
+  {
+    if (vac)
+      vac[i] = i < B ? buf[i] : 0;
+    if (repl)
+      repl[i] = i < B ? buf[B + i] : 0;
+  }
+  return last > capacity ? fail(MTB_ECAPACITY, "histogram longer than the output buffer") : MTB_OK;
+}
+
+int
+mtb_get_vac_energy(mtb_handle * h, uint64_t * evac, size_t rows, size_t bins)
+{
+  if (int rc = ensure_ready(h))
+    return rc;
+  if (!(h->host.cfg.tally_mask & MTB_TALLY_VAC_ENERGY) || !evac)
+    return fail(MTB_EINVAL, "MTB_TALLY_VAC_ENERGY not enabled");
+  const size_t B = (size_t)h->P.hist_bins, R = (size_t)h->P.evac_rows;
+  std::vector<unsigned long long> buf(R * B);
+  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  MTB_CUDA(cudaMemcpy(buf.data(), h->d_u64.p + off_evac(h->P), R * B * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  std::memset(evac, 0, rows * bins * sizeof(uint64_t));
+  for (size_t r = 0; r < std::min(R, rows); ++r)
+    for (size_t x = 0; x < std::min(B, bins); ++x)
+      evac[r * bins + x] = buf[r * B + x];
+  return MTB_OK;
+}
+
+int
+mtb_get_vacmap(mtb_handle * h, uint64_t * vmap)
+{
+  if (int rc = ensure_ready(h))
+    return rc;
+  if (!vmap)
+    return fail(MTB_EINVAL, "null argument");
+  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  MTB_CUDA(cudaMemcpy(vmap, h->d_u64.p + off_vmap(h->P), MTB_VMAP_NX * MTB_VMAP_NY * 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return MTB_OK;
+}
+
+int
+mtb_get_range_list(mtb_handle * h, float * x, int32_t * Z, size_t capacity, size_t * n)
+{
+  if (int rc = ensure_ready(h))
+    return rc;
+  if (!(h->host.cfg.tally_mask & MTB_TALLY_RANGE))
+    return fail(MTB_EINVAL, "MTB_TALLY_RANGE not enabled");
+  unsigned long long cnt = 0;
+  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  MTB_CUDA(cudaMemcpy(&cnt, h->d_u64.p + CNT_RANGE_N, sizeof(cnt), cudaMemcpyDeviceToHost));
+  if (n)
+    *n = (size_t)cnt;
+  const size_t have = (size_t)std::min<unsigned long long>(cnt, h->P.range_cap);
+  const size_t take = std::min(have, capacity);
+  std::vector<RangeEntry> buf(take);
+  if (take)
+    MTB_CUDA(cudaMemcpy(buf.data(), h->d_range.p, take * sizeof(RangeEntry), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < take; ++i)
+  {
+    if (x)
+      x[i] = buf[i].x;
+    if (Z)
+      Z[i] = buf[i].Z;
+  }
+  if (cnt > h->P.range_cap)
+    return fail(MTB_ECAPACITY, "range list overflowed range_capacity");
+  return cnt > capacity ? fail(MTB_ECAPACITY, "range list longer than the output buffer") : MTB_OK;
+}
+
+int
+mtb_get_ion_log(mtb_handle * h, mtb_ion_log * out, size_t capacity, size_t * n)
+{
+  if (int rc = ensure_ready(h))
+    return rc;
+  if (!(h->host.cfg.tally_mask & MTB_TALLY_IONLOG))
+    return fail(MTB_EINVAL, "MTB_TALLY_IONLOG not enabled");
+  unsigned long long cnt = 0;
+  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  MTB_CUDA(cudaMemcpy(&cnt, h->d_u64.p + CNT_IONLOG_N, sizeof(cnt), cudaMemcpyDeviceToHost));
+  const size_t have = (size_t)std::min<unsigned long long>(cnt, h->P.ionlog_cap);
+  std::vector<mtb_ion_log> raw(have);
+  if (have)
+    MTB_CUDA(cudaMemcpy(raw.data(), h->d_ionlog.p, have * sizeof(mtb_ion_log), cudaMemcpyDeviceToHost));
+  // join birth halves (state == -1) with death halves by stream id
+  std::unordered_map<uint64_t, size_t> birth;
+  birth.reserve(have);
+  for (size_t i = 0; i < have; ++i)
+    if (raw[i].state == -1)
+      birth[raw[i].uid] = i;
+  size_t m = 0;
+  for (size_t i = 0; i < have; ++i)
+  {
+    if (raw[i].state == -1)
+      continue;
+    auto it = birth.find(raw[i].uid);
+    if (it == birth.end())
+      continue;
+    if (m < capacity && out)
+    {
+      mtb_ion_log e = raw[i];
+      std::memcpy(e.pos0, raw[it->second].pos0, sizeof(e.pos0));
+      e.E0 = raw[it->second].E0;
+      out[m] = e;
+    }
+    ++m;
+  }
+  if (n)
+    *n = m;
+  if (cnt > h->P.ionlog_cap)
+    return fail(MTB_ECAPACITY, "ion log overflowed ionlog_capacity");
+  return m > capacity ? fail(MTB_ECAPACITY, "ion log longer than the output buffer") : MTB_OK;
+}
+
+int
+mtb_tally_device_views(mtb_handle * h, void ** u64_dev, size_t * n_u64, void ** f64_dev, size_t * n_f64)
+{
+  if (int rc = ensure_ready(h))
+    return rc;
+  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  if (u64_dev)
+    *u64_dev = h->d_u64.p;
+  if (n_u64)
+    *n_u64 = h->u64_size;
+  if (f64_dev)
+    *f64_dev = h->d_f64.p;
+  if (n_f64)
+    *n_f64 = 2;
+  return MTB_OK;
+}
+
+int
+mtb_trim_one(mtb_handle * h, mtb_ion * ion, uint64_t seed, uint64_t uid, int32_t * final_state,
+             mtb_event * events, size_t capacity, size_t * n_events)
+{
+  if (int rc = ensure_ready(h))
+    return rc;
+  if (!ion)
+    return fail(MTB_EINVAL, "null ion");
+  const size_t cap = std::max<size_t>(capacity, 1);
+  MTB_CUDA(h->d_events.ensure(cap));
+  LaunchParams P = h->P;
+  P.primaries = nullptr;
+  P.beam = *ion;
+  P.n_primaries = 1;
+  P.first_index = 0;
+  P.single_uid = uid;
+  P.key0 = (uint32_t)seed;
+  P.key1 = (uint32_t)(seed >> 32);
+  P.records = nullptr;
+  P.events = h->d_events.p;
+  P.events_cap = events ? capacity : 0;
+  P.tally_mask = 0; // hooks run on the host in this mode
+  MTB_CUDA(cudaMemsetAsync(&P.u64[CNT_EVENTS_N], 0, sizeof(unsigned long long), h->stream));
+  trim_one_kernel<<<1, 32, h->smem_bytes, h->stream>>>(P);
+  MTB_CUDA(cudaGetLastError());
+  unsigned long long cnt = 0;
+  MTB_CUDA(cudaMemcpyAsync(&cnt, h->d_u64.p + CNT_EVENTS_N, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
+  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  const size_t take = (size_t)std::min<unsigned long long>(cnt, P.events_cap);
+  mtb_event last;
+  bool have_last = false;
+  if (take)
+  {
+    MTB_CUDA(cudaMemcpy(events, h->d_events.p, take * sizeof(mtb_event), cudaMemcpyDeviceToHost));
+    if (take == cnt)
+    {
+      last = events[take - 1];
+      have_last = true;
+    }
+  }
+  if (n_events)
+    *n_events = (size_t)cnt;
+  if (cnt > P.events_cap)
+    return fail(MTB_ECAPACITY, "event buffer too small");
+  if (have_last)
+  {
+    std::memcpy(ion->pos, last.pka_pos, sizeof(ion->pos));
+    std::memcpy(ion->dir, last.pka_dir, sizeof(ion->dir));
+    ion->E = last.pka_E;
+    if (final_state)
+      *final_state = last.pka_state;
+  }
+  else if (final_state)
+    *final_state = MTB_MOVING;
+  return MTB_OK;
+}
+
+int
+mtb_stopping(mtb_handle * h, int material, size_t n, const int32_t * Z1, const double * m1, const double * E,
+             double * out)
+{
+  if (int rc = ensure_ready(h))
+    return rc;
+  if (material < 0 || material >= h->P.n_materials || !Z1 || !m1 || !E || !out)
+    return fail(MTB_EINVAL, "bad argument");
+  for (size_t i = 0; i < n; ++i)
+    if (Z1[i] < 1 || Z1[i] > MTB_NZ)
+      return fail(MTB_EINVAL, "projectile Z out of range");
+  if (!n)
+    return MTB_OK;
+  DevBuf<int32_t> dZ;
+  DevBuf<double> dm, dE, dout;
+  MTB_CUDA(dZ.upload(Z1, n, h->stream));
+  MTB_CUDA(dm.upload(m1, n, h->stream));
+  MTB_CUDA(dE.upload(E, n, h->stream));
+  MTB_CUDA(dout.ensure(n));
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  stopping_kernel<<<blocks, 128, h->smem_bytes, h->stream>>>(h->P, material, n, dZ.p, dm.p, dE.p, dout.p);
+  MTB_CUDA(cudaGetLastError());
+  MTB_CUDA(cudaMemcpyAsync(out, dout.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  return MTB_OK;
+}
+
+int
+mtb_measure_fp32_peak(int device, double * tflops, float * ms_out)
+{
+  if (!tflops)
+    return fail(MTB_EINVAL, "null argument");
+  MTB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MTB_CUDA(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  float * d = nullptr;
+  MTB_CUDA(cudaMalloc(&d, (size_t)blocks * threads * sizeof(float)));
+  cudaEvent_t e0, e1;
+  MTB_CUDA(cudaEventCreate(&e0));
+  MTB_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep)
+  {
+    MTB_CUDA(cudaEventRecord(e0));
+    fp32_peak_kernel<<<blocks, threads>>>(d, iters, 0.999f, 0.001f);
+    MTB_CUDA(cudaEventRecord(e1));
+    MTB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    MTB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep >= 1 && ms < best)
+      best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  const double flops = (double)blocks * threads * (double)iters * 16.0 * 8.0 * 2.0;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  if (ms_out)
+    *ms_out = best;
+  return MTB_OK;
+}
+
+int
+mtb_allreduce(mtb_handle ** handles, int n_handles)
+{
+  (void)handles;
+  (void)n_handles;
+  return fail(MTB_ENCCL, "mtb_allreduce: not built in this configuration");
+}
+
+} // extern "C"

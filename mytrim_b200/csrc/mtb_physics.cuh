@@ -1,0 +1,280 @@
+// mtb_physics.cuh — the per-collision physics of the transport kernel in single precision.
+//
+// Same algorithm as the reference's TrimBase::trim() body and MaterialBase::rstop/rpstop, but
+// written for the FP32 + SFU pipes of an SM: no libm calls, divisions as MUFU.RCP, powers as
+// EX2(y*LG2(x)), and every expression that cancels catastrophically in float is rearranged
+// (the closest-approach Newton solve runs in x = r - b, 1 - cos is formed directly, ...).
+// Each function cites the reference lines whose result it reproduces.
+#ifndef MTB_PHYSICS_CUH
+#define MTB_PHYSICS_CUH
+
+#include "mtb_math.cuh"
+#include "mtb_types.h"
+
+namespace mtb
+{
+
+// .5292 * .8853, the universal screening-length prefactor (material.C:84,104)
+#define MTB_SCREEN_K 0.46850076f
+#define MTB_PI_F 3.14159265358979323846f
+
+// Projectile description kept in registers while an ion is in flight.
+struct Projectile
+{
+  float fz;    // float(Z1)
+  float m;     // amu
+  float z023;  // Z1^0.23
+  float cbrt;  // Z1^(1/3)
+  float lfctr; // screening length factor of Z1
+  int Z;
+};
+
+// ZBL proton stopping, e in keV/amu — MaterialBase::rpstop, material.C:133-158.
+MTB_HD float
+proton_stopping(const DevElement & el, float e)
+{
+  const float pe = fmax2(25.0f, e);
+  const float l2 = flog2(pe);
+  const float sl = el.pc[0] * fexp2(el.pc[1] * l2) + el.pc[2] * fexp2(el.pc[3] * l2);
+  const float sh = el.pc[4] * fexp2(-el.pc[5] * l2) * flog(fdiv(el.pc[6], pe) + el.pc[7] * pe);
+  float sp = fdiv(sl * sh, sl + sh);
+  if (e <= 25.0f)
+    sp *= fpow(e * 0.04f, el.velpwr);
+  return sp;
+}
+
+// Electronic stopping cross-section of one target element — MaterialBase::rstop,
+// material.C:160-282.  E in eV.
+MTB_HD float
+element_stopping(const Projectile & ion, const DevElement & el, float E)
+{
+  const float e = fdiv(0.001f * E, ion.m); // keV/amu
+  float se;
+  if (ion.Z == 1)
+  {
+    se = proton_stopping(el, e); // material.C:187-191
+  }
+  else if (ion.Z == 2)
+  {
+    // material.C:192-212
+    const float he = fmax2(1.0f, e);
+    const float b = flog(he);
+    const float b2 = b * b;
+    const float b4 = b2 * b2;
+    float a = 0.2865f + 0.1266f * b - 0.001429f * b2 + 0.02402f * b * b2 - 0.01135f * b4 + 0.001475f * b4 * b;
+    float heh = 1.0f - fexp(-fmin2(30.0f, a));
+    const float t = 7.6f - b;
+    a = 1.0f + (0.007f + 0.00005f * el.fz) * fexp(-(t * t));
+    heh *= a * a;
+    se = proton_stopping(el, he) * heh * 4.0f;
+    if (e <= 1.0f)
+      se *= fsqrt(e);
+  }
+  else
+  {
+    // material.C:213-279
+    const float vfermi = el.vfermi;
+    const float v = fsqrt(e * 0.04f) * frcp(vfermi);
+    const float v2 = v * v;
+    float vr;
+    if (v >= 1.0f)
+      vr = v * vfermi * (1.0f + fdiv(0.2f, v2));
+    else
+      vr = (0.75f * vfermi) * (1.0f + v2 * (2.0f / 3.0f) - v2 * v2 * (1.0f / 15.0f));
+
+    const float cb = ion.cbrt;
+    const float icb2 = frcp(cb * cb);
+    const float ylow = fmax2(0.13f, icb2); // max(yrmin, vrmin / Z1^(2/3))
+    const float yr = fmax2(ylow, vr * icb2);
+    const float yr03 = fpow(yr, 0.3f);
+    float a = yr03 * (-0.803f + 1.3167f * yr03) + yr * (0.38157f + 0.008983f * yr);
+
+    const float q = fmin2(1.0f, fmax2(0.0f, 1.0f - fexp(-fmin2(a, 50.0f))));
+    const float icb = frcp(cb);
+    const float b = fmin2(0.43f, fmax2(0.32f, 0.12f + 0.025f * ion.fz)) * icb;
+    const float l0 = (0.8f - q * fmin2(1.2f, 0.6f + ion.fz * (1.0f / 30.0f))) * icb;
+    const float qa = fmax2(0.0f, 0.9f - 0.025f * ion.fz);
+    const float z16 = 0.025f * fmin2(16.0f, ion.fz);
+    float l1;
+    if (q < 0.2f)
+      l1 = 0.0f;
+    else if (q < qa)
+      l1 = fdiv(b * (q - 0.2f), fabsf(qa - 0.2000001f));
+    else if (q < fmax2(0.0f, 1.0f - z16))
+      l1 = b;
+    else
+      l1 = fdiv(b * (1.0f - q), z16);
+
+    const float l = fmax2(l1, l0 * ion.lfctr);
+    const float lx = 4.0f * l * vfermi * (1.0f / 1.919f);
+    float zeta = q + el.vf2inv * (1.0f - q) * flog(1.0f + lx * lx);
+
+    // Z1^3 effect: exp(-(7.6 - max(0, ln e))^2).  For e <= 1 the factor is 1 + O(1e-26) == 1.
+    if (e > 1.0f)
+    {
+      const float t = 7.6f - flog(e);
+      zeta *= 1.0f + fdiv(0.18f + 0.0015f * el.fz, ion.fz * ion.fz) * fexp(-(t * t));
+    }
+
+    const float zf = zeta * ion.fz;
+    if (yr <= ylow)
+    {
+      // velocity-proportional stopping below yrmin
+      const float vrmin = fmax2(1.0f, 0.13f * cb * cb);
+      const float vmin = 0.5f * (vrmin + fsqrt(fmax2(0.0f, vrmin * vrmin - 0.8f * vfermi * vfermi)));
+      const float eee = 25.0f * vmin * vmin;
+      const bool p375 = (el.Z == 6) || ((el.Z == 14 || el.Z == 32) && ion.Z <= 19);
+      const float ratio = fdiv(e, eee);
+      const float scale = p375 ? fpow(ratio, 0.375f) : fsqrt(ratio);
+      se = proton_stopping(el, eee) * (zf * zf) * scale;
+    }
+    else
+      se = proton_stopping(el, e) * (zf * zf);
+  }
+  return se * 10.0f;
+}
+
+// MaterialBase::getrstop — material.C:113-122 [eV/Ang]
+MTB_HD float
+material_stopping(const Projectile & ion, const DevMaterial & M, const DevElement * elements, float E)
+{
+  float se = 0.0f;
+  for (int i = 0; i < M.n_elem; ++i)
+  {
+    const DevElement & el = elements[M.first_elem + i];
+    se += element_stopping(ion, el, E) * el.t;
+  }
+  return se * M.arho;
+}
+
+// Scattering result of one binary collision in the centre-of-mass frame.
+struct Scatter
+{
+  float s2; // sin^2(theta/2)
+  float c2; // cos^2(theta/2)
+};
+
+// Biersack-Haggmark MAGIC scattering (trim.C:172-272) for reduced energy eps and reduced impact
+// parameter b.  The Newton iteration is the reference's (same start value, same map, same stop
+// test |q/r| <= 0.001) but carried in x = r - b so that distant collisions keep full relative
+// accuracy in single precision.
+MTB_HD Scatter
+magic_scatter(int potential, float eps, float b)
+{
+  Scatter out;
+  if (eps > 10.0f)
+  {
+    // Rutherford — trim.C:172-179
+    const float t = 2.0f * eps * b;
+    const float X = (1.0f + b * (1.0f + b)) * (t * t);
+    out.s2 = frcp(1.0f + X);
+    out.c2 = X * out.s2;
+    return out;
+  }
+
+  // first guess — trim.C:183-190
+  float x = 0.0f;
+  {
+    float rr = -2.7f * flog(eps * b);
+    if (rr >= b)
+    {
+      rr = -2.7f * flog(eps * rr);
+      if (rr >= b)
+        x = rr - b;
+    }
+  }
+
+  const float inv_eps = frcp(eps);
+  const float b2 = b * b;
+  float r, v, v1, q;
+  int guard = 0;
+  do
+  {
+    r = b + x;
+    const float inv_r = frcp(r);
+    float sum, dsum; // sum = v*r, dsum = -(v + v1*r)
+    if (potential == MTB_POT_UNIVERSAL)
+    {
+      const float ex1 = 0.18175f * fexp(-3.1998f * r);
+      const float ex2 = 0.50986f * fexp(-0.94229f * r);
+      const float ex3 = 0.28022f * fexp(-0.4029f * r);
+      const float ex4 = 0.028171f * fexp(-0.20162f * r);
+      sum = (ex1 + ex2) + (ex3 + ex4);
+      dsum = (3.1998f * ex1 + 0.94229f * ex2) + (0.4029f * ex3 + 0.20162f * ex4);
+    }
+    else if (potential == MTB_POT_MOLIERE)
+    {
+      const float ex1 = fexp(-0.3f * r);
+      const float ex2 = (ex1 * ex1) * (ex1 * ex1);
+      const float e22 = ex2 * ex2;
+      const float ex3 = ex2 * (e22 * e22);
+      sum = 0.35f * ex1 + 0.55f * ex2 + 0.1f * ex3;
+      dsum = 0.105f * ex1 + 0.66f * ex2 + 0.6f * ex3;
+    }
+    else
+    {
+      const float ex1 = fexp(-0.279f * r);
+      const float ex2 = fexp(-0.637f * r);
+      const float ex3 = fexp(-1.1919f * r);
+      sum = 0.191f * ex1 + 0.474f * ex2 + 0.335f * ex3;
+      dsum = 0.531865f * ex1 + 0.30181f * ex2 + 0.6437f * ex3;
+    }
+    v = sum * inv_r;
+    v1 = -(v + dsum) * inv_r;
+    // fr  = b^2/r + v r/eps - r        = sum/eps - x (2b + x)/r
+    // fr1 = -b^2/r^2 + (v + v1 r)/eps - 1 = -(b^2/r^2 + 1) - dsum/eps
+    const float fr = sum * inv_eps - x * (2.0f * b + x) * inv_r;
+    const float fr1 = -(b2 * inv_r * inv_r + 1.0f) - dsum * inv_eps;
+    q = fdiv(fr, fr1);
+    x -= q;
+  } while (fabsf(q) > 0.001f * fabsf(b + x) && ++guard < 64);
+  r = b + x;
+
+  // trim.C:235-271 (v, v1 are those of the last evaluated r, as in the reference)
+  const float roc = fdiv(-2.0f * (eps - v), v1);
+  const float sqe = fsqrt(eps);
+  float c_num, c_den, a_k, f_num, f_den;
+  if (potential == MTB_POT_UNIVERSAL)
+  {
+    c_num = 0.011615f; c_den = 0.0071222f; a_k = 0.99229f; f_num = 9.3066f; f_den = 14.813f;
+  }
+  else if (potential == MTB_POT_MOLIERE)
+  {
+    c_num = 0.009611f; c_den = 0.005175f; a_k = 0.6743f; f_num = 6.314f; f_den = 10.0f;
+  }
+  else
+  {
+    c_num = 0.235809f; c_den = 0.126000f; a_k = 1.0144f; f_num = 6935.0f; f_den = 83550.0f;
+  }
+  const float cc = fdiv(c_num + sqe, c_den + sqe);
+  const float aa = 2.0f * eps * (1.0f + fdiv(a_k, sqe)) * fpow(b, cc);
+  // sqrt(aa^2+1) - aa == 1/(sqrt(aa^2+1) + aa), the latter does not cancel
+  const float ff = fdiv(f_num + eps, (f_den + eps) * (fsqrt(aa * aa + 1.0f) + aa));
+  const float g = fdiv(aa * ff, ff + 1.0f); // delta = (r - b) * g
+  // co = (b + delta + roc)/(r + roc)  =>  1 - co = (r - b - delta)/(r + roc)
+  const float omc = fdiv(x * (1.0f - g), r + roc);
+  const float co = 1.0f - omc;
+  out.s2 = omc * (1.0f + co);
+  out.c2 = co * co;
+  return out;
+}
+
+// Ion/material dependent constants of MaterialBase::average (material.C:77-110) that the free
+// flight needs, and the impact-parameter scale.  Returns pmax and writes ls (trim.C:88-92).
+MTB_HD float
+flight_constants(const Projectile & ion, const DevMaterial & M, float tmin, float E, float * ls)
+{
+  const float a = fdiv(MTB_SCREEN_K, ion.z023 + M.az023);
+  const float mu = fdiv(ion.m, M.am);
+  const float f = fdiv(a * M.am, M.az * ion.fz * 14.4f * (ion.m + M.am));
+  const float opm = 1.0f + mu;
+  const float epsdg = fdiv(tmin * f * (opm * opm), 4.0f * mu);
+  const float eps = E * f;
+  const float eeg = fsqrt(eps * epsdg);
+  const float pmax = fdiv(a, eeg + fsqrt(eeg) + 0.125f * fpow(eeg, 0.1f));
+  *ls = frcp(MTB_PI_F * (pmax * pmax) * M.arho);
+  return pmax;
+}
+
+} // namespace mtb
+#endif

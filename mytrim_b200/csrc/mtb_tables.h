@@ -1,0 +1,306 @@
+// mtb_tables.h — host-side flattening of the MyTRIM plugin objects into device tables.
+//
+// Pure C++ (no CUDA calls): mtb_engine.cu uploads the vectors; tests/hostsim.cpp points the
+// kernels' LaunchParams straight at them.  All derived constants are computed in double and
+// rounded to float once.
+#ifndef MTB_TABLES_H
+#define MTB_TABLES_H
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mtb_types.h"
+
+namespace mtb
+{
+
+struct ZblRow
+{
+  double mm1, m1, mnat, rho, atrho, vfermi, heat, lfctr;
+  double pcoef[8];
+};
+
+inline const ZblRow *
+builtin_zbl()
+{
+  static const ZblRow rows[MTB_NZ] = {
+#include "zbl_tables.inc"
+  };
+  return rows;
+}
+
+constexpr int kSmemHistMax = 4096;
+
+struct HostConfig
+{
+  mtb_config cfg;
+  ZblRow zbl[MTB_NZ];
+  std::vector<mtb_material> materials;
+  std::vector<mtb_element> elements;
+  mtb_geometry geom;
+  std::vector<double> layer_thickness, cluster_xyzr;
+
+  HostConfig()
+  {
+    std::memset(&cfg, 0, sizeof(cfg));
+    std::memcpy(zbl, builtin_zbl(), sizeof(zbl));
+    std::memset(&geom, 0, sizeof(geom));
+    geom.kind = MTB_GEOM_SOLID;
+    for (int i = 0; i < 3; ++i)
+    {
+      geom.w[i] = 10000.0; // sample.h:37
+      geom.bc[i] = MTB_BC_PBC;
+    }
+  }
+};
+
+struct HostTables
+{
+  std::vector<DevElement> elements;
+  std::vector<DevMaterial> materials;
+  std::vector<DevIonZ> ionz;
+  std::vector<double> layer_cum;
+  std::vector<int32_t> layer_mat, cl_hash, cl_next;
+};
+
+inline void
+default_config(mtb_config * cfg)
+{
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->tmin = 0.2; // simconf.C:44-49
+  cfg->tau = 0.0;
+  cfg->cw = 0.001;
+  cfg->length_scale = 1.0;
+  cfg->potential = MTB_POT_UNIVERSAL;
+  cfg->follow = MTB_FOLLOW_ALL;
+  cfg->follow_max_gen = 1;
+  cfg->vacancy_model = MTB_VAC_COUNT;
+  cfg->vmap_z[0] = cfg->vmap_z[1] = cfg->vmap_z[2] = -1;
+}
+
+inline int
+check_materials(int n_materials, const mtb_material * materials, int n_elements, const mtb_element * elements,
+                std::string & err)
+{
+  if (!materials || !elements || n_materials < 1 || n_elements < 1)
+  {
+    err = "bad materials";
+    return MTB_EINVAL;
+  }
+  for (int i = 0; i < n_materials; ++i)
+  {
+    const mtb_material & m = materials[i];
+    if (m.n_elements < 1 || m.first_element < 0 || m.first_element + m.n_elements > n_elements || !(m.rho > 0.0))
+    {
+      err = "bad material " + std::to_string(i);
+      return MTB_EINVAL;
+    }
+  }
+  for (int i = 0; i < n_elements; ++i)
+    if (elements[i].Z < 1 || elements[i].Z > MTB_NZ || !(elements[i].m > 0.0))
+    {
+      err = "bad element " + std::to_string(i);
+      return MTB_EINVAL;
+    }
+  return MTB_OK;
+}
+
+inline int
+check_geometry(const mtb_geometry * g, std::string & err)
+{
+  if (!g || g->kind < MTB_GEOM_SOLID || g->kind > MTB_GEOM_CLUSTERS)
+  {
+    err = "unknown geometry kind";
+    return MTB_EINVAL;
+  }
+  if (g->kind == MTB_GEOM_LAYERS && (g->n_layers < 1 || !g->layer_thickness))
+  {
+    err = "layers geometry without layers";
+    return MTB_EINVAL;
+  }
+  if (g->kind == MTB_GEOM_CLUSTERS &&
+      (g->kn[0] < 1 || g->kn[1] < 1 || g->kn[2] < 1 || g->n_clusters < 0 || (g->n_clusters && !g->cluster_xyzr)))
+  {
+    err = "bad clusters geometry";
+    return MTB_EINVAL;
+  }
+  return MTB_OK;
+}
+
+// Fills T and every non-pointer field of P.  Pointer fields of P are left for the caller.
+inline int
+build_host_tables(const HostConfig & H, HostTables & T, LaunchParams & P, std::string & err)
+{
+  const mtb_config & c = H.cfg;
+  std::memset(&P, 0, sizeof(P));
+  if (H.materials.empty())
+  {
+    err = "mtb_set_materials has not been called";
+    return MTB_EINVAL;
+  }
+  P.tmin = (float)c.tmin;
+  P.tau = (float)c.tau;
+  P.cw = (float)c.cw;
+  P.inv_scale = (float)(1.0 / c.length_scale);
+  P.potential = c.potential;
+  P.follow = c.follow;
+  P.follow_max_gen = c.follow_max_gen;
+  P.vacancy_model = c.vacancy_model;
+  P.tally_mask = c.tally_mask;
+  for (int i = 0; i < 3; ++i)
+    P.vmap_z[i] = c.vmap_z[i];
+  P.ionlog_z = c.ionlog_z;
+
+  // materials: MaterialBase::prepare — material.C:36-74
+  T.elements.assign(H.elements.size(), DevElement());
+  T.materials.assign(H.materials.size(), DevMaterial());
+  for (size_t i = 0; i < H.materials.size(); ++i)
+  {
+    const mtb_material & m = H.materials[i];
+    double tt = 0.0;
+    for (int j = 0; j < m.n_elements; ++j)
+      tt += std::max(0.0, H.elements[m.first_element + j].t);
+    if (!(tt > 0.0))
+    {
+      err = "material with zero stoichiometry";
+      return MTB_EINVAL;
+    }
+    double am = 0.0, az = 0.0;
+    for (int j = 0; j < m.n_elements; ++j)
+    {
+      const mtb_element & e = H.elements[m.first_element + j];
+      const double t = std::max(0.0, e.t) / tt;
+      am += e.m * t;
+      az += (double)e.Z * t;
+      const ZblRow & row = H.zbl[e.Z - 1];
+      DevElement & d = T.elements[m.first_element + j];
+      std::memset(&d, 0, sizeof(d));
+      d.m = (float)e.m;
+      d.t = (float)t;
+      d.Edisp = (float)e.Edisp;
+      d.Elbind = (float)e.Elbind;
+      d.z023 = (float)std::pow((double)e.Z, 0.23);
+      d.fz = (float)e.Z;
+      d.vfermi = (float)row.vfermi;
+      d.vf2inv = (float)(1.0 / (2.0 * row.vfermi * row.vfermi));
+      for (int k = 0; k < 8; ++k)
+        d.pc[k] = (float)row.pcoef[k];
+      d.Z = e.Z;
+      d.velpwr = e.Z <= 6 ? 0.25f : 0.45f;
+    }
+    DevMaterial & d = T.materials[i];
+    d.arho = (float)(m.rho * 0.6022 / am);
+    d.am = (float)am;
+    d.az = (float)az;
+    d.az023 = (float)std::pow(az, 0.23);
+    d.n_elem = m.n_elements;
+    d.first_elem = m.first_element;
+    d.tag = m.tag;
+    d.user_index = (int32_t)i;
+  }
+  T.ionz.assign(MTB_NZ + 1, DevIonZ());
+  std::memset(T.ionz.data(), 0, sizeof(DevIonZ) * T.ionz.size());
+  for (int z = 1; z <= MTB_NZ; ++z)
+  {
+    T.ionz[z].z023 = (float)std::pow((double)z, 0.23);
+    T.ionz[z].cbrt = (float)std::cbrt((double)z);
+    T.ionz[z].lfctr = (float)H.zbl[z - 1].lfctr;
+    T.ionz[z].mm1 = (float)H.zbl[z - 1].mm1;
+  }
+  P.n_elements = (int32_t)T.elements.size();
+  P.n_materials = (int32_t)T.materials.size();
+  if (P.n_elements + SPECIES_ELEMENT0 > SPECIES_MASK)
+  {
+    err = "too many elements";
+    return MTB_EINVAL;
+  }
+
+  // geometry
+  const mtb_geometry & g = H.geom;
+  P.geom_kind = g.kind;
+  for (int i = 0; i < 3; ++i)
+  {
+    P.bc[i] = g.bc[i];
+    P.w[i] = g.w[i];
+  }
+  double extent = g.w[0];
+  T.layer_cum.clear();
+  T.layer_mat.clear();
+  T.cl_hash.clear();
+  T.cl_next.clear();
+  if (g.kind == MTB_GEOM_LAYERS)
+  {
+    const int nl = (int)H.layer_thickness.size();
+    double d = 0.0;
+    for (int i = 0; i < nl; ++i)
+    {
+      d += H.layer_thickness[i]; // same running sum as sample_layers.C:32-37
+      T.layer_cum.push_back(d);
+      // a position beyond the last interface belongs to the last material (sample_layers.C:40-41)
+      T.layer_mat.push_back(std::min(i, P.n_materials - 1));
+    }
+    P.n_layers = nl;
+    extent = std::max(extent, d);
+  }
+  else if (g.kind == MTB_GEOM_BURIED_WIRE || g.kind == MTB_GEOM_CLUSTERS)
+  {
+    if (P.n_materials < 2)
+    {
+      err = "this geometry needs two materials";
+      return MTB_EINVAL;
+    }
+  }
+  if (g.kind == MTB_GEOM_CLUSTERS)
+  {
+    // sampleClusters::initSpatialhash + addCluster — sample_clusters.C:135-213
+    const size_t ncell = (size_t)g.kn[0] * g.kn[1] * g.kn[2];
+    const size_t ncl = H.cluster_xyzr.size() / 4;
+    T.cl_hash.assign(ncell, -1);
+    T.cl_next.assign(std::max<size_t>(ncl, 1), -1);
+    double cmr = 0.0;
+    for (size_t cidx = 0; cidx < ncl; ++cidx)
+    {
+      int k[3];
+      for (int i = 0; i < 3; ++i)
+      {
+        k[i] = (int)std::floor((H.cluster_xyzr[4 * cidx + i] * g.kn[i]) / g.w[i]) % g.kn[i];
+        if (k[i] < 0)
+          k[i] += g.kn[i];
+      }
+      const size_t cell = (size_t)k[0] + (size_t)g.kn[0] * ((size_t)k[1] + (size_t)g.kn[1] * (size_t)k[2]);
+      if (T.cl_hash[cell] < 0)
+        T.cl_hash[cell] = (int32_t)cidx;
+      else
+      {
+        int l = T.cl_hash[cell];
+        while (T.cl_next[l] >= 0)
+          l = T.cl_next[l];
+        T.cl_next[l] = (int32_t)cidx;
+      }
+      cmr = std::max(cmr, H.cluster_xyzr[4 * cidx + 3]);
+    }
+    for (int i = 0; i < 3; ++i)
+    {
+      P.kn[i] = g.kn[i];
+      P.kd[i] = g.w[i] / (double)g.kn[i];
+      P.cl_ks[i] = (int)(cmr / P.kd[i]) + 1;
+    }
+  }
+
+  // tally sizes
+  int bins = c.hist_bins;
+  if (bins <= 0)
+    bins = (int)std::min<double>(std::max(1024.0, std::ceil(extent) + 1.0), 1 << 20);
+  P.hist_bins = bins;
+  P.evac_rows = c.evac_rows > 0 ? c.evac_rows : 32;
+  P.smem_hist_bins = (c.tally_mask & MTB_TALLY_VAC_DEPTH) ? std::min(bins, kSmemHistMax) : 0;
+  P.ionlog_cap = (c.tally_mask & MTB_TALLY_IONLOG) ? (c.ionlog_capacity ? c.ionlog_capacity : (1ull << 20)) : 0;
+  P.range_cap = (c.tally_mask & MTB_TALLY_RANGE) ? (c.range_capacity ? c.range_capacity : (1ull << 22)) : 0;
+  return MTB_OK;
+}
+
+} // namespace mtb
+#endif

@@ -1,0 +1,844 @@
+// mtb_transport.cuh — the cascade loop of one lane (one CUDA thread).
+//
+// Replaces, for the primaries a lane draws from the global work counter, the reference's
+//   queue.push(pka); while(!queue.empty()){ r=pop; sample->averages(r); trim->trim(r,queue); }
+// (apps/runmytrim.C:76-92) together with the body of TrimBase::trim (trim.C:35-425).
+//
+// B200-first structure: a lane owns a whole cascade.  The ion in flight lives in registers
+// (position and energy in FP64 — cheap on B200 — everything else FP32); suspended ions live on a
+// lane-private 64-byte-per-entry stack in HBM/L2.  When a collision leaves two moving ions the
+// lane keeps the one with LESS energy and pushes the other, which bounds the stack depth by
+// log2(E0/E_threshold) <= 32 and never touches memory when the projectile stops in the same
+// collision.  Every ion draws its randoms from its own Philox4x32-10 stream keyed by a
+// scheduling-independent id, so the traversal order (depth first here, FIFO in the reference and
+// in the oracle) does not change any result.
+//
+// The file compiles for the host too (MTB_HOSTSIM): tests/hostsim.cpp drives the same loop
+// single-threaded to debug control flow without a GPU.  It is NOT a product fallback.
+#ifndef MTB_TRANSPORT_CUH
+#define MTB_TRANSPORT_CUH
+
+#include "mtb_physics.cuh"
+
+namespace mtb
+{
+
+#if MTB_DEVICE_CODE
+#define MTB_ATOMIC_ADD(ptr, val) atomicAdd((ptr), (val))
+#define MTB_ATOMIC_MAX(ptr, val) atomicMax((ptr), (val))
+#else
+template <class T, class U>
+inline T
+host_fetch_add(T * p, U v)
+{
+  T old = *p;
+  *p += (T)v;
+  return old;
+}
+template <class T, class U>
+inline T
+host_fetch_max(T * p, U v)
+{
+  T old = *p;
+  if ((T)v > old)
+    *p = (T)v;
+  return old;
+}
+#define MTB_ATOMIC_ADD(ptr, val) ::mtb::host_fetch_add((ptr), (val))
+#define MTB_ATOMIC_MAX(ptr, val) ::mtb::host_fetch_max((ptr), (val))
+#endif
+
+// Block-local views: the small tables staged in shared memory plus block accumulators.
+struct BlockCtx
+{
+  const DevElement * elements;
+  const DevMaterial * materials;
+  const DevIonZ * ionz;
+  const double * layer_cum;
+  const int32_t * layer_mat;
+  unsigned int * hist_vac;  // [smem_hist_bins] or null
+  unsigned int * hist_repl; // [smem_hist_bins] or null
+  unsigned long long * blk_u64; // [CNT_COUNT]
+  double * blk_f64;             // [2]
+};
+
+MTB_HD size_t
+off_vac(const LaunchParams &)
+{
+  return CNT_COUNT;
+}
+MTB_HD size_t
+off_repl(const LaunchParams & P)
+{
+  return CNT_COUNT + (size_t)P.hist_bins;
+}
+MTB_HD size_t
+off_evac(const LaunchParams & P)
+{
+  return CNT_COUNT + 2 * (size_t)P.hist_bins;
+}
+MTB_HD size_t
+off_vmap(const LaunchParams & P)
+{
+  return off_evac(P) + ((P.tally_mask & MTB_TALLY_VAC_ENERGY) ? (size_t)P.evac_rows * (size_t)P.hist_bins : 0);
+}
+MTB_HD size_t
+u64_block_size(const LaunchParams & P)
+{
+  return off_vmap(P) + MTB_VMAP_NX * MTB_VMAP_NY * 3;
+}
+
+// ---------------------------------------------------------------------------------------------
+// geometry: the lookupMaterial() family.  Returns the de-duplicated
+// material id, or -1 for vacuum; *cluster receives the cluster index (clusters geometry).
+// ---------------------------------------------------------------------------------------------
+MTB_HD int
+lookup_cluster(const LaunchParams & P, double px, double py, double pz)
+{
+  // sampleClusters::lookupCluster(pos, 0) — sample_clusters.C:59-133
+  const double pos[3] = {px, py, pz};
+  int k1[3], k2[3];
+  for (int i = 0; i < 3; ++i)
+  {
+    int k = (int)floor((pos[i] * P.kn[i]) / P.w[i]);
+    if (pos[i] < 0.0 || pos[i] >= P.w[i])
+    {
+      if (P.bc[i] == MTB_BC_CUT)
+        return -2;
+      if (P.bc[i] == MTB_BC_INF)
+        return -1;
+      k = k % P.kn[i];
+      if (k < 0)
+        k += P.kn[i];
+    }
+    k1[i] = k - P.cl_ks[i];
+    k2[i] = k + P.cl_ks[i];
+    if (k1[i] < 0 && P.bc[i] != MTB_BC_PBC)
+      k1[i] = 0;
+    if (k2[i] >= P.kn[i] && P.bc[i] != MTB_BC_PBC)
+      k2[i] = P.kn[i] - 1;
+  }
+  for (int j0 = k1[0]; j0 <= k2[0]; ++j0)
+  {
+    int c0 = j0 % P.kn[0];
+    if (c0 < 0)
+      c0 += P.kn[0];
+    for (int j1 = k1[1]; j1 <= k2[1]; ++j1)
+    {
+      int c1 = j1 % P.kn[1];
+      if (c1 < 0)
+        c1 += P.kn[1];
+      for (int j2 = k1[2]; j2 <= k2[2]; ++j2)
+      {
+        int c2 = j2 % P.kn[2];
+        if (c2 < 0)
+          c2 += P.kn[2];
+        int l = P.cl_hash[c0 + P.kn[0] * (c1 + P.kn[1] * c2)];
+        while (l >= 0)
+        {
+          double r2 = 0.0;
+          for (int i = 0; i < 3; ++i)
+          {
+            double dif = pos[i] - P.cl_xyzr[4 * l + i];
+            if (P.bc[i] == MTB_BC_PBC)
+              dif -= rint(dif / P.w[i]) * P.w[i]; // ::round differs only at exact .5
+            r2 += dif * dif;
+          }
+          const double rr = P.cl_xyzr[4 * l + 3];
+          if (r2 < rr * rr)
+            return l;
+          l = P.cl_next[l];
+        }
+      }
+    }
+  }
+  return -1;
+}
+
+MTB_HD int
+lookup_material(const LaunchParams & P, const BlockCtx & S, double px, double py, double pz, int * cluster)
+{
+  *cluster = -1;
+  switch (P.geom_kind)
+  {
+    case MTB_GEOM_SOLID: // sample_solid.C:25-29
+      return 0;
+    case MTB_GEOM_LAYERS: // sample_layers.C:26-49
+    {
+      // first layer whose cumulative thickness exceeds x; beyond the stack -> last layer
+      int lo = 0, hi = P.n_layers - 1;
+      while (lo < hi)
+      {
+        const int mid = (lo + hi) >> 1;
+        if (px < S.layer_cum[mid])
+          hi = mid;
+        else
+          lo = mid + 1;
+      }
+      return S.layer_mat[lo];
+    }
+    case MTB_GEOM_WIRE: // sample_wire.C:37-46
+    {
+      const double x = (px / P.w[0]) * 2.0 - 1.0;
+      const double y = (py / P.w[1]) * 2.0 - 1.0;
+      return (x * x + y * y) > 1.0 ? -1 : 0;
+    }
+    case MTB_GEOM_BURIED_WIRE: // sample_burried_wire.C:38-55
+    {
+      if (pz < 0.0 && pz >= -250.0)
+        return 1;
+      if (pz > P.w[2] || pz < -250.0)
+        return -1;
+      const double x = (px / P.w[0]) * 2.0 - 1.0;
+      const double y = (py / P.w[1]) * 2.0 - 1.0;
+      return (x * x + y * y) > 1.0 ? 1 : 0;
+    }
+    case MTB_GEOM_CLUSTERS: // sample_clusters.C:43-55
+    {
+      const int l = lookup_cluster(P, px, py, pz);
+      if (l == -2)
+        return -1;
+      if (l == -1)
+        return 0;
+      *cluster = l;
+      return 1;
+    }
+  }
+  return -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lane state
+// ---------------------------------------------------------------------------------------------
+struct Lane
+{
+  // ion in flight
+  double px, py, pz, E;
+  float dx, dy, dz;
+  uint32_t ic;
+  uint64_t uid;
+  uint32_t packed;
+  int32_t tag;
+  Projectile proj;
+  // current cascade
+  uint64_t prim;
+  int32_t pZ;
+  float pm, Ef;
+  double casEel, casEnuc;
+  uint32_t casVac, casRepl, casSteps, casIons;
+};
+
+MTB_HD void
+set_projectile(Lane & L, const BlockCtx & S)
+{
+  const uint32_t species = L.packed & SPECIES_MASK;
+  int Z;
+  float m;
+  if (species == SPECIES_PRIMARY)
+  {
+    Z = L.pZ;
+    m = L.pm;
+  }
+  else
+  {
+    const DevElement & el = S.elements[species - SPECIES_ELEMENT0];
+    Z = el.Z;
+    m = el.m;
+  }
+  const DevIonZ & iz = S.ionz[Z];
+  L.proj.Z = Z;
+  L.proj.fz = (float)Z;
+  L.proj.m = (m == 0.0f) ? iz.mm1 : m;
+  L.proj.z023 = iz.z023;
+  L.proj.cbrt = iz.cbrt;
+  L.proj.lfctr = iz.lfctr;
+}
+
+MTB_HD void
+stack_store(StackEntry * dst, const Lane & L)
+{
+  StackEntry e;
+  e.pos[0] = L.px;
+  e.pos[1] = L.py;
+  e.pos[2] = L.pz;
+  e.E = L.E;
+  e.dir[0] = L.dx;
+  e.dir[1] = L.dy;
+  e.dir[2] = L.dz;
+  e.ic = L.ic;
+  e.uid = L.uid;
+  e.packed = L.packed;
+  e.tag = L.tag;
+#if MTB_DEVICE_CODE
+  const uint4 * s = reinterpret_cast<const uint4 *>(&e);
+  uint4 * d = reinterpret_cast<uint4 *>(dst);
+  d[0] = s[0];
+  d[1] = s[1];
+  d[2] = s[2];
+  d[3] = s[3];
+#else
+  *dst = e;
+#endif
+}
+
+MTB_HD void
+stack_load(const StackEntry * src, Lane & L)
+{
+  StackEntry e;
+#if MTB_DEVICE_CODE
+  const uint4 * s = reinterpret_cast<const uint4 *>(src);
+  uint4 * d = reinterpret_cast<uint4 *>(&e);
+  d[0] = s[0];
+  d[1] = s[1];
+  d[2] = s[2];
+  d[3] = s[3];
+#else
+  e = *src;
+#endif
+  L.px = e.pos[0];
+  L.py = e.pos[1];
+  L.pz = e.pos[2];
+  L.E = e.E;
+  L.dx = e.dir[0];
+  L.dy = e.dir[1];
+  L.dz = e.dir[2];
+  L.ic = e.ic;
+  L.uid = e.uid;
+  L.packed = e.packed;
+  L.tag = e.tag;
+}
+
+MTB_HD void
+log_birth(const LaunchParams & P, const Lane & L)
+{
+  if (!(P.tally_mask & MTB_TALLY_IONLOG))
+    return;
+  if (P.ionlog_z && L.proj.Z != P.ionlog_z)
+    return;
+  const unsigned long long i = MTB_ATOMIC_ADD(&P.u64[CNT_IONLOG_N], 1ull);
+  if (i >= P.ionlog_cap)
+    return;
+  mtb_ion_log & o = P.ionlog[i];
+  o.pos0[0] = L.px;
+  o.pos0[1] = L.py;
+  o.pos0[2] = L.pz;
+  o.pos1[0] = o.pos1[1] = o.pos1[2] = 0.0;
+  o.E0 = L.E;
+  o.E1 = 0.0;
+  o.uid = L.uid;
+  o.primary = L.prim;
+  o.Z = L.proj.Z;
+  o.gen = (int32_t)((L.packed >> GEN_SHIFT) & GEN_MASK);
+  o.tag = L.tag;
+  o.state = -1; // birth half; mtb_get_ion_log joins it with the death half
+}
+
+// an ion has stopped (or left the sample): primary record + death half of the ion log
+MTB_HD void
+finish_ion(const LaunchParams & P, const Lane & L, int state)
+{
+  if ((L.packed & FLAG_PRIMARY) && P.records)
+  {
+    mtb_record & r = P.records[L.prim - P.first_index];
+    r.pos[0] = L.px;
+    r.pos[1] = L.py;
+    r.pos[2] = L.pz;
+    r.E = L.E;
+    r.state = state;
+    r.primary_steps = L.ic;
+  }
+  if (P.tally_mask & MTB_TALLY_IONLOG)
+  {
+    if (P.ionlog_z && L.proj.Z != P.ionlog_z)
+      return;
+    const unsigned long long i = MTB_ATOMIC_ADD(&P.u64[CNT_IONLOG_N], 1ull);
+    if (i >= P.ionlog_cap)
+      return;
+    mtb_ion_log & o = P.ionlog[i];
+    o.pos0[0] = o.pos0[1] = o.pos0[2] = 0.0;
+    o.pos1[0] = L.px;
+    o.pos1[1] = L.py;
+    o.pos1[2] = L.pz;
+    o.E0 = 0.0;
+    o.E1 = L.E;
+    o.uid = L.uid;
+    o.primary = L.prim;
+    o.Z = L.proj.Z;
+    o.gen = (int32_t)((L.packed >> GEN_SHIFT) & GEN_MASK);
+    o.tag = L.tag;
+    o.state = state;
+  }
+}
+
+MTB_HD void
+depth_tally(const LaunchParams & P, const BlockCtx & S, unsigned int * smem_hist, size_t goff, int x)
+{
+  if (x < 0)
+    return;
+  if (x >= P.hist_bins)
+  {
+    MTB_ATOMIC_ADD(&S.blk_u64[CNT_CLAMPED], 1ull);
+    x = P.hist_bins - 1;
+  }
+  if (x < P.smem_hist_bins)
+    MTB_ATOMIC_ADD(&smem_hist[x], 1u);
+  else
+    MTB_ATOMIC_ADD(&P.u64[goff + (size_t)x], 1ull);
+}
+
+// vacancyCreation() of the in-tree subclasses
+MTB_HD void
+vacancy_creation(const LaunchParams & P, const BlockCtx & S, Lane & L, const DevMaterial & M,
+                 const DevElement & el, double rx, double ry, float Erec, int rec_gen)
+{
+  switch (P.vacancy_model)
+  {
+    case MTB_VAC_COUNT: // trim.C:439-443
+      L.casVac++;
+      break;
+    case MTB_VAC_NRT: // apps/src/TrimRange.C:31-47
+    {
+      const float ed = 0.0115f * fpow(el.fz, -7.0f / 3.0f) * Erec;
+      const float kd = 0.1337f * fpow(el.fz, 2.0f / 3.0f) * frsqrt(el.m);
+      const float g = 3.4008f * fpow(ed, 1.0f / 6.0f) + 0.40244f * fpow(ed, 0.75f) + ed;
+      const float Ev = fdiv(Erec, 1.0f + kd * g);
+      if (Ev >= el.Edisp)
+        L.casVac += (Ev >= el.Edisp * 2.5f) ? (uint32_t)(Ev * 0.4f / el.Edisp) : 1u;
+      break;
+    }
+    case MTB_VAC_KP: // TrimPrimaries::vacancyCreation — trim.C:445-464
+      L.casVac++;
+      if (rec_gen == P.follow_max_gen)
+      {
+        const float ed = 0.0115f * fpow(M.az, -7.0f / 3.0f) * Erec;
+        const float g = 3.4008f * fpow(ed, 1.0f / 6.0f) + 0.40244f * fpow(ed, 0.75f) + ed;
+        const float kd = 0.1337f * fpow(M.az, 2.0f / 3.0f) * frsqrt(M.am);
+        const float Ev = fdiv(Erec, 1.0f + kd * g);
+        L.casVac += (uint32_t)(int)(0.8f * Ev / (2.0f * el.Edisp));
+      }
+      break;
+    default:
+      break;
+  }
+  const int x = (int)rx; // truncation toward zero — TrimVacCount.C:35
+  if (P.tally_mask & MTB_TALLY_VAC_DEPTH)
+    depth_tally(P, S, S.hist_vac, off_vac(P), x);
+  if ((P.tally_mask & MTB_TALLY_VAC_ENERGY) && x >= 0) // TrimVacEnergyCount.C:31-53
+  {
+    int le = (int)flog(Erec);
+    le = le < 0 ? 0 : (le >= P.evac_rows ? P.evac_rows - 1 : le);
+    int xb = x;
+    if (xb >= P.hist_bins)
+    {
+      MTB_ATOMIC_ADD(&S.blk_u64[CNT_CLAMPED], 1ull);
+      xb = P.hist_bins - 1;
+    }
+    MTB_ATOMIC_ADD(&P.u64[off_evac(P) + (size_t)le * (size_t)P.hist_bins + (size_t)xb], 1ull);
+  }
+  if (P.tally_mask & MTB_TALLY_VACMAP) // TrimVacMap::vacancyCreation — trim.C:483-501
+  {
+    int vx = (int)((rx * MTB_VMAP_NX) / P.w[0]);
+    int vy = (int)((ry * MTB_VMAP_NY) / P.w[1]);
+    vx -= (vx / MTB_VMAP_NX) * MTB_VMAP_NX;
+    vy -= (vy / MTB_VMAP_NY) * MTB_VMAP_NY;
+    int s = -1;
+    if (el.Z == P.vmap_z[0])
+      s = 0;
+    else if (el.Z == P.vmap_z[1])
+      s = 1;
+    else if (el.Z == P.vmap_z[2])
+      s = 2;
+    if (s >= 0 && vx >= 0 && vy >= 0)
+      MTB_ATOMIC_ADD(&P.u64[off_vmap(P) + (size_t)((vx * MTB_VMAP_NY + vy) * 3 + s)], 1ull);
+  }
+}
+
+// close a cascade: per-primary record + block totals
+MTB_HD void
+close_cascade(const LaunchParams & P, const BlockCtx & S, Lane & L)
+{
+  if (P.records)
+  {
+    mtb_record & r = P.records[L.prim - P.first_index];
+    r.Eel = L.casEel;
+    r.Enuc = L.casEnuc;
+    r.vacancies = L.casVac;
+    r.replacements = L.casRepl;
+    r.steps = L.casSteps;
+    r.ions = L.casIons;
+  }
+  MTB_ATOMIC_ADD(&S.blk_u64[CNT_VAC], (unsigned long long)L.casVac);
+  MTB_ATOMIC_ADD(&S.blk_u64[CNT_REPL], (unsigned long long)L.casRepl);
+  MTB_ATOMIC_ADD(&S.blk_u64[CNT_STEPS], (unsigned long long)L.casSteps);
+  MTB_ATOMIC_ADD(&S.blk_u64[CNT_IONS], (unsigned long long)L.casIons);
+  MTB_ATOMIC_ADD(&S.blk_u64[CNT_PRIMARIES], 1ull);
+  MTB_ATOMIC_ADD(&S.blk_f64[0], L.casEel);
+  MTB_ATOMIC_ADD(&S.blk_f64[1], L.casEnuc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the lane loop.  EVENTS=true is the single-ion mode behind mtb_trim_one: one ion, recoils are
+// never followed, every collision is reported.
+// ---------------------------------------------------------------------------------------------
+template <bool EVENTS>
+MTB_HD void
+lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
+{
+  Lane L;
+  StackEntry * const stack = EVENTS ? nullptr : P.stacks + (size_t)lane_global * MTB_STACK_DEPTH;
+  int sp = 0, sp_max = 0;
+  bool active = false, open = false, started = false;
+  unsigned long long n_events = 0;
+  L.prim = 0;
+  L.casEel = L.casEnuc = 0.0;
+  L.casVac = L.casRepl = L.casSteps = L.casIons = 0;
+
+  for (;;)
+  {
+    // ---------------- refill: next suspended ion, else next primary ----------------
+    if (!active)
+    {
+      if (sp > 0)
+      {
+        --sp;
+        stack_load(stack + sp, L);
+        set_projectile(L, S);
+      }
+      else
+      {
+        if (open)
+        {
+          close_cascade(P, S, L);
+          open = false;
+        }
+        unsigned long long idx;
+        if (EVENTS)
+        {
+          if (started || lane_global != 0)
+            break;
+          idx = 0;
+        }
+        else
+          idx = MTB_ATOMIC_ADD(&P.u64[CNT_NEXT_PRIMARY], 1ull);
+        started = true;
+        if (idx >= P.n_primaries)
+          break;
+        const mtb_ion & src = P.primaries ? P.primaries[idx] : P.beam;
+        L.px = src.pos[0];
+        L.py = src.pos[1];
+        L.pz = src.pos[2];
+        L.dx = (float)src.dir[0];
+        L.dy = (float)src.dir[1];
+        L.dz = (float)src.dir[2];
+        L.E = src.E;
+        L.ic = 0;
+        L.prim = P.first_index + idx;
+        L.uid = EVENTS ? P.single_uid : L.prim;
+        L.packed = SPECIES_PRIMARY | (((uint32_t)src.gen & GEN_MASK) << GEN_SHIFT) | FLAG_PRIMARY;
+        L.tag = src.tag;
+        L.pZ = src.Z;
+        L.pm = (float)src.m;
+        L.Ef = (float)src.Ef;
+        L.casEel = L.casEnuc = 0.0;
+        L.casVac = L.casRepl = L.casSteps = 0;
+        L.casIons = 1;
+        open = true;
+        set_projectile(L, S);
+        if (!EVENTS)
+          log_birth(P, L);
+      }
+      active = true;
+    }
+
+    // ---------------- one collision: trim.C:74-424 ----------------
+    if (!(L.E > 0.0))
+    {
+      // the reference would produce NaNs for a projectile without energy; park it instead
+      finish_ion(P, L, MTB_INTERSTITIAL);
+      active = false;
+      if (EVENTS)
+        break;
+      continue;
+    }
+    ++L.ic;
+    int cluster;
+    const int mi = lookup_material(P, S, L.px, L.py, L.pz, &cluster);
+    if (mi < 0)
+    {
+      // vacuum: the reference breaks out with the state still MOVING (trim.C:80-82)
+      MTB_ATOMIC_ADD(&S.blk_u64[CNT_LEFT], 1ull);
+      --L.ic;
+      finish_ion(P, L, MTB_MOVING);
+      active = false;
+      if (EVENTS)
+        break;
+      continue;
+    }
+    const DevMaterial & M = S.materials[mi];
+    const int mtag = (P.geom_kind == MTB_GEOM_CLUSTERS && mi == 1) ? cluster : M.tag;
+    L.casSteps++;
+
+    // v_norm(dir) — trim.C:85
+    {
+      const float inv = frsqrt(L.dx * L.dx + L.dy * L.dy + L.dz * L.dz);
+      L.dx *= inv;
+      L.dy *= inv;
+      L.dz *= inv;
+    }
+
+    // the four uniforms of this step: one Philox block
+    uint32_t w[4];
+    philox4x32_10(L.ic, (uint32_t)L.uid, (uint32_t)(L.uid >> 32), 0u, P.key0, P.key1, w);
+    const float r2 = u01(w[0]);
+    float hh = u01(w[1]);
+    const float uphi = u01(w[2]);
+    const float r1 = u01(w[3]);
+
+    const float E0 = (float)L.E;
+
+    // free flight path and impact parameter — trim.C:88-94, 143-144
+    float ls;
+    const float pmax = flight_constants(L.proj, M, P.tmin, E0, &ls);
+    if (L.ic == 1)
+      ls = r1 * fmin2(ls, P.cw);
+    const float p = pmax * fsqrt(r2);
+
+    // target element — trim.C:147-156
+    int nn = 0;
+    for (; nn < M.n_elem - 1; ++nn)
+    {
+      hh -= S.elements[M.first_elem + nn].t;
+      if (hh <= 0.0f)
+        break;
+    }
+    const DevElement & el = S.elements[M.first_elem + nn];
+
+    // element part of MaterialBase::average — material.C:99-108
+    const float my = fdiv(L.proj.m, el.m);
+    const float opmy = 1.0f + my;
+    const float ec = fdiv(4.0f * my, opmy * opmy);
+    const float ai = fdiv(MTB_SCREEN_K, L.proj.z023 + el.z023);
+    const float fi = fdiv(ai * el.m, L.proj.fz * el.fz * 14.4f * (L.proj.m + el.m));
+
+    const float eps = fi * E0; // trim.C:159-160
+    const float b = fdiv(p, ai);
+
+    const float see = material_stopping(L.proj, M, S.elements, E0); // trim.C:166
+    const float dee_f = ls * see;
+
+    const Scatter sc = magic_scatter(P.potential, eps, b);
+
+    // energy bookkeeping in FP64 — trim.C:275-296
+    double dee = (double)dee_f;
+    if (dee > L.E)
+      dee = L.E;
+    L.E -= dee;
+    L.casEel += dee;
+    const float p1 = fsqrt(2.0f * L.proj.m * (float)L.E);
+    double den = (double)(ec * sc.s2 * E0);
+    if (den > L.E)
+      den = L.E;
+    L.E -= den;
+    const float p2 = fsqrt(2.0f * L.proj.m * (float)L.E);
+
+    // recoil is born at the previous collision site — trim.C:306-310
+    const double rx = L.px, ry = L.py, rz = L.pz;
+    const float flight = (ls - P.tau) * P.inv_scale;
+    L.px = fma((double)L.dx, (double)flight, L.px);
+    L.py = fma((double)L.dy, (double)flight, L.py);
+    L.pz = fma((double)L.dz, (double)flight, L.pz);
+
+    // unit vector perpendicular to dir with uniform azimuth (replaces trim.C:322-333)
+    float qx, qy, qz;
+    {
+      const float sg = copysignf(1.0f, L.dz);
+      const float a = -frcp(sg + L.dz);
+      const float bb = L.dx * L.dy * a;
+      float sphi, cphi;
+      fsincos2pi(uphi, &sphi, &cphi);
+      const float ex = cphi * (1.0f + sg * L.dx * L.dx * a) + sphi * bb;
+      const float ey = cphi * (sg * bb) + sphi * (sg + L.dy * L.dy * a);
+      const float ez = cphi * (-sg * L.dx) + sphi * (-L.dy);
+
+      // lab scattering angle: psi = atan2(st, ct + my) — trim.C:336-341
+      const float ct = 1.0f - 2.0f * sc.s2;
+      const float st = 2.0f * fsqrt(sc.s2 * sc.c2);
+      const float X = ct + my;
+      const float h2 = st * st + X * X;
+      float cpsi = 1.0f, spsi = 0.0f;
+      if (h2 > 1e-30f)
+      {
+        const float ih = frsqrt(h2);
+        cpsi = X * ih;
+        spsi = st * ih;
+      }
+      const float nx = L.dx * cpsi + ex * spsi;
+      const float ny = L.dy * cpsi + ey * spsi;
+      const float nz = L.dz * cpsi + ez * spsi;
+      // recoil momentum = p1*dir_old - p2*dir_new
+      qx = fmaf(-p2, nx, L.dx * p1);
+      qy = fmaf(-p2, ny, L.dy * p1);
+      qz = fmaf(-p2, nz, L.dz * p1);
+      L.dx = nx;
+      L.dy = ny;
+      L.dz = nz;
+    }
+
+    // CUT boundaries — trim.C:344-352
+    int state = MTB_MOVING;
+    if ((P.bc[0] == MTB_BC_CUT && (L.px > P.w[0] || L.px < 0.0)) ||
+        (P.bc[1] == MTB_BC_CUT && (L.py > P.w[1] || L.py < 0.0)) ||
+        (P.bc[2] == MTB_BC_CUT && (L.pz > P.w[2] || L.pz < 0.0)))
+    {
+      state = MTB_LOST;
+      MTB_ATOMIC_ADD(&S.blk_u64[CNT_LOST], 1ull);
+    }
+
+    // fate of recoil and projectile — trim.C:357-411
+    const float Erec = (float)den - el.Elbind;
+    const int rec_gen = (int)((L.packed >> GEN_SHIFT) & GEN_MASK) + 1;
+    bool above = false, follow = false;
+    if (state != MTB_LOST)
+    {
+      if (Erec > el.Edisp - el.Elbind)
+      {
+        above = true;
+        if (P.tally_mask & MTB_TALLY_PHONON)
+          L.casEnuc += (double)el.Elbind; // TrimPhononOut::followRecoil
+        follow = !EVENTS && (P.follow == MTB_FOLLOW_ALL ||
+                             (P.follow == MTB_FOLLOW_GEN_LT && rec_gen < P.follow_max_gen));
+        if (L.E > (double)el.Edisp)
+          vacancy_creation(P, S, L, M, el, rx, ry, Erec, rec_gen);
+        else
+        {
+          L.casRepl++;
+          if (P.tally_mask & MTB_TALLY_VAC_DEPTH)
+            depth_tally(P, S, S.hist_repl, off_repl(P), (int)rx);
+          state = (L.proj.Z == el.Z) ? MTB_REPLACEMENT : MTB_SUBSTITUTIONAL;
+        }
+      }
+      else
+      {
+        if (P.tally_mask & MTB_TALLY_RANGE) // TrimRange::dissipateRecoilEnergy
+        {
+          const unsigned long long i = MTB_ATOMIC_ADD(&P.u64[CNT_RANGE_N], 1ull);
+          if (i < P.range_cap)
+          {
+            P.range[i].x = (float)rx;
+            P.range[i].Z = el.Z;
+          }
+        }
+        if (P.tally_mask & MTB_TALLY_PHONON)
+          L.casEnuc += den; // recoil.E + Elbind — TrimPhononOut::dissipateRecoilEnergy
+        if (L.E < (double)L.Ef)
+          state = MTB_INTERSTITIAL;
+      }
+      // TrimPhononOut::checkPKAState — trim.C:503-511
+      if ((P.tally_mask & MTB_TALLY_PHONON) && state != MTB_MOVING)
+        L.casEnuc += L.E;
+    }
+
+    if (EVENTS)
+    {
+      if (n_events < P.events_cap)
+      {
+        mtb_event & ev = P.events[n_events];
+        ev.pka_pos[0] = L.px; ev.pka_pos[1] = L.py; ev.pka_pos[2] = L.pz;
+        ev.pka_dir[0] = L.dx; ev.pka_dir[1] = L.dy; ev.pka_dir[2] = L.dz;
+        ev.pka_E = L.E;
+        ev.recoil_pos[0] = rx; ev.recoil_pos[1] = ry; ev.recoil_pos[2] = rz;
+        float qs = 1.0f;
+        if (above)
+          qs = frsqrt(qx * qx + qy * qy + qz * qz);
+        ev.recoil_dir[0] = qx * qs; ev.recoil_dir[1] = qy * qs; ev.recoil_dir[2] = qz * qs;
+        ev.recoil_E = (double)Erec;
+        ev.ls = (double)ls;
+        ev.dee = dee;
+        ev.den = den;
+        ev.material = M.user_index;
+        ev.element = nn;
+        ev.material_tag = mtag;
+        ev.pka_state = state;
+        ev.recoil_above_threshold = above ? 1 : 0;
+        ev._pad = 0;
+      }
+      ++n_events;
+      if (state != MTB_MOVING)
+      {
+        finish_ion(P, L, state);
+        break;
+      }
+      continue;
+    }
+
+    // ---------------- who flies next ----------------
+    if (follow)
+    {
+      L.casIons++;
+      MTB_ATOMIC_ADD(&S.blk_u64[CNT_QUEUED], 1ull);
+      const float qs = frsqrt(qx * qx + qy * qy + qz * qz);
+      const uint64_t ruid = child_uid(L.uid, L.ic);
+      const uint32_t rpacked = (uint32_t)(SPECIES_ELEMENT0 + M.first_elem + nn) | ((uint32_t)rec_gen << GEN_SHIFT);
+      const bool keep_projectile = (state == MTB_MOVING) && (L.E <= (double)Erec);
+      if (state == MTB_MOVING && !keep_projectile)
+      {
+        // both move on and the recoil has less energy: suspend the projectile, fly the recoil
+        if (sp < MTB_STACK_DEPTH)
+          stack_store(stack + sp++, L);
+        else
+          MTB_ATOMIC_ADD(&P.u64[CNT_ERROR], 1ull);
+      }
+      if (state != MTB_MOVING)
+        finish_ion(P, L, state);
+      if (keep_projectile)
+      {
+        // suspend the recoil instead
+        Lane R;
+        R.px = rx; R.py = ry; R.pz = rz;
+        R.E = (double)Erec;
+        R.dx = qx * qs; R.dy = qy * qs; R.dz = qz * qs;
+        R.ic = 0;
+        R.uid = ruid;
+        R.packed = rpacked;
+        R.tag = mtag;
+        if (P.tally_mask & MTB_TALLY_IONLOG)
+        {
+          R.prim = L.prim;
+          R.proj.Z = el.Z;
+          log_birth(P, R);
+        }
+        if (sp < MTB_STACK_DEPTH)
+          stack_store(stack + sp++, R);
+        else
+          MTB_ATOMIC_ADD(&P.u64[CNT_ERROR], 1ull);
+      }
+      else
+      {
+        L.px = rx; L.py = ry; L.pz = rz;
+        L.E = (double)Erec;
+        L.dx = qx * qs; L.dy = qy * qs; L.dz = qz * qs;
+        L.ic = 0;
+        L.uid = ruid;
+        L.packed = rpacked;
+        L.tag = mtag;
+        set_projectile(L, S);
+        log_birth(P, L);
+      }
+      if (sp > sp_max)
+        sp_max = sp;
+    }
+    else if (state != MTB_MOVING)
+    {
+      finish_ion(P, L, state);
+      active = false;
+    }
+  }
+
+  if (!EVENTS)
+    MTB_ATOMIC_MAX(&S.blk_u64[CNT_STACKMAX], (unsigned long long)sp_max);
+  else if (lane_global == 0)
+    P.u64[CNT_EVENTS_N] = n_events;
+}
+
+} // namespace mtb
+#endif

@@ -1,0 +1,167 @@
+// mtb_types.h — flattened, device-resident form of the MyTRIM plugin objects.
+//
+// The host side (mtb_capi.cu) turns {SimconfType tables, MaterialBase/Element vectors, a
+// SampleBase subclass + parameters, the Trim subclass' hook behaviour} into these PODs once per
+// configuration; kernels copy the small tables into shared memory at start-up.
+#ifndef MTB_TYPES_H
+#define MTB_TYPES_H
+
+#include <stdint.h>
+#include "../../include/mytrim_b200.h"
+
+namespace mtb
+{
+
+// One target element of one material.  Everything MaterialBase::average (material.C:99-108) and
+// MaterialBase::rstop/rpstop (material.C:133-282) need about the TARGET atom, in float.
+struct DevElement
+{
+  float m;      // amu
+  float t;      // normalised stoichiometric fraction
+  float Edisp;  // eV
+  float Elbind; // eV
+  float z023;   // Z^0.23 (universal screening length)
+  float fz;     // float(Z)
+  float vfermi; // scoef[Z-1].vfermi
+  float vf2inv; // 1/(2 vfermi^2)
+  float pc[8];  // scoef[Z-1].pcoef[0..7]
+  int32_t Z;
+  float velpwr; // 0.25 (Z<=6) or 0.45: rpstop low-energy exponent (material.C:151-155)
+  int32_t pad[2];
+};
+static_assert(sizeof(DevElement) == 80, "DevElement layout");
+
+// One material (prepare() results, material.C:36-74).
+struct DevMaterial
+{
+  float arho;  // atoms/Ang^3
+  float am;    // mean mass
+  float az;    // mean Z
+  float az023; // az^0.23
+  int32_t n_elem;
+  int32_t first_elem;
+  int32_t tag;
+  int32_t user_index; // index in the caller's material list (before de-duplication)
+};
+static_assert(sizeof(DevMaterial) == 32, "DevMaterial layout");
+
+// Per projectile-Z constants (indexed by Z, entry 0 unused).
+struct DevIonZ
+{
+  float z023;  // Z^0.23
+  float cbrt;  // Z^(1/3)
+  float lfctr; // scoef[Z-1].lfctr
+  float mm1;   // scoef[Z-1].mm1 (used when an ion has mass 0, material.C:181-184)
+};
+
+// Suspended ion on a lane's private stack: exactly two 32-byte sectors.
+struct __attribute__((aligned(16))) StackEntry
+{
+  double pos[3];
+  double E;
+  float dir[3];
+  uint32_t ic;     // collision steps already taken by this ion
+  uint64_t uid;    // Philox stream id
+  uint32_t packed; // species | gen << 12 | flags << 28
+  int32_t tag;
+};
+static_assert(sizeof(StackEntry) == 64, "StackEntry layout");
+
+enum
+{
+  SPECIES_PRIMARY = 0,   // (Z, m) of the lane's current primary
+  SPECIES_ELEMENT0 = 1,  // 1 + global element index
+  SPECIES_MASK = 0xFFF,
+  GEN_SHIFT = 12,
+  GEN_MASK = 0xFFFF,
+  FLAG_PRIMARY = 1u << 28
+};
+
+#define MTB_STACK_DEPTH 32
+
+// Indices into the u64 counter block (mtb_counters order, then histograms).
+enum
+{
+  CNT_VAC = 0,
+  CNT_REPL,
+  CNT_STEPS,
+  CNT_IONS,
+  CNT_PRIMARIES,
+  CNT_QUEUED,
+  CNT_LOST,
+  CNT_LEFT,
+  CNT_CLAMPED,
+  CNT_STACKMAX,
+  CNT_NEXT_PRIMARY, // work counter (not reduced)
+  CNT_IONLOG_N,
+  CNT_RANGE_N,
+  CNT_ERROR,
+  CNT_EVENTS_N,
+  CNT_RESERVED,
+  CNT_COUNT = 16
+};
+
+struct RangeEntry
+{
+  float x;
+  int32_t Z;
+};
+
+// Everything a transport launch needs, passed by value (lives in the constant bank).
+struct LaunchParams
+{
+  // run constants
+  float tmin, tau, cw, inv_scale;
+  int32_t potential, follow, follow_max_gen, vacancy_model;
+  uint32_t tally_mask;
+  int32_t vmap_z[3];
+  int32_t ionlog_z;
+  // tables (global memory, copied to shared at kernel start)
+  const DevElement * elements;
+  const DevMaterial * materials;
+  const DevIonZ * ionz; // [93]
+  int32_t n_elements, n_materials;
+  // geometry
+  int32_t geom_kind;
+  int32_t bc[3];
+  double w[3];
+  int32_t n_layers;
+  const double * layer_cum;     // cumulative thickness, [n_layers]
+  const int32_t * layer_mat;    // de-duplicated material id per layer
+  int32_t kn[3];
+  int32_t cl_ks[3];             // int(cmr/kd)+1 per axis
+  const int32_t * cl_hash;      // sh[]
+  const int32_t * cl_next;      // cl[]
+  const double * cl_xyzr;       // 4 per cluster
+  double kd[3];
+  // primaries
+  const mtb_ion * primaries;    // device copy, or null for beam mode
+  mtb_ion beam;
+  uint64_t n_primaries, first_index;
+  uint32_t key0, key1;
+  // outputs
+  unsigned long long * u64;     // counter + histogram block
+  double * f64;                 // [0]=Eel, [1]=Enuc
+  int32_t hist_bins, evac_rows;
+  int32_t smem_hist_bins;       // depth bins mirrored in shared memory
+  mtb_record * records;         // [n_primaries] or null
+  mtb_ion_log * ionlog;
+  unsigned long long ionlog_cap;
+  RangeEntry * range;
+  unsigned long long range_cap;
+  StackEntry * stacks;          // [lanes][MTB_STACK_DEPTH]
+  // single-ion event mode
+  mtb_event * events;
+  unsigned long long events_cap;
+  uint64_t single_uid;
+};
+
+// offsets inside the u64 block
+inline size_t
+u64_off_vac(const LaunchParams &)
+{
+  return CNT_COUNT;
+}
+
+} // namespace mtb
+#endif

@@ -218,6 +218,7 @@ cascadeLoop(const Job * job, Worker * w, const std::vector<unsigned> * seeds, mt
     std::memset(&rec, 0, sizeof(rec));
 
     recoils.push(pka);
+    bool is_primary = true; // FIFO: the first ion popped is the primary itself
     while (!recoils.empty())
     {
       IonBase * ion = recoils.front();
@@ -226,8 +227,9 @@ cascadeLoop(const Job * job, Worker * w, const std::vector<unsigned> * seeds, mt
       const unsigned long s0 = w->probe->steps;
       w->trim->trim(ion, recoils);
       ++w->ions;
-      if (ion == pka)
+      if (is_primary)
       {
+        is_primary = false;
         for (int i = 0; i < 3; ++i)
           rec.pos[i] = ion->_pos(i);
         rec.E = ion->_E;

@@ -1,0 +1,114 @@
+#!/usr/bin/env python3
+"""Generates the committed golden fixtures from the UNMODIFIED reference compiled in this
+container (oracle/_ref, see oracle/Makefile).  Run from the repo root:
+
+    python tests/golden/make_golden.py
+
+Fixtures:
+  uo2_out.{Erec,clcoor,dist}  `MYTRIM_SEED=39172 mytrim_uo2 out 10 0.1 1` (tests/uo2/test.sh);
+                               byte-identical to the reference's tests/uo2/gold/ files.
+  rng_mt19937.txt             SimconfType::drand()/irand() sequences (simconf.h:52-53).
+  stopping.json               MaterialBase::getrstop + average() known answers.
+  ref_records_<cfg>.npz       per-primary records of the reference for fixed 32-bit seeds.
+  vacancy_count_published.json the reference's published vacancies/ion table
+                               (validation/vacancy_count/vacancy_count_comparison.dat).
+"""
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from tests import util  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def uo2():
+    with tempfile.TemporaryDirectory() as tmp:
+        env = util.ref_env()
+        env["MYTRIM_SEED"] = "39172"
+        subprocess.run([util.REF_UO2, "out", "10", "0.1", "1"], cwd=tmp, env=env, check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        for ext in ("Erec", "clcoor", "dist"):
+            shutil.copy(os.path.join(tmp, "out." + ext), os.path.join(HERE, "uo2_out." + ext))
+
+
+def rng():
+    lines = util.run_reference("rng 39172 64\nrng 2344 64\n")
+    with open(os.path.join(HERE, "rng_mt19937.txt"), "w") as f:
+        f.write("# seed 39172: 64 drand (hexfloat) then 64 irand; then the same for seed 2344\n")
+        f.write("\n".join(lines) + "\n")
+
+
+STOPPING_CASES = [
+    # (name, ion Z, m, material, energies)
+    ("cu_on_cu", 29, 63.546, util.CU, [25.0, 1e2, 1e3, 1e4, 1.5e5, 1e6, 1e7, 1e8]),
+    ("h_on_fe", 1, 1.008, util.FE, [1e2, 1e3, 1e4, 2e4, 3e4, 1e5, 1e6, 1e7]),
+    ("he_on_fe", 2, 4.003, util.FE, [1e2, 3e3, 4e3, 5e3, 1e4, 1e5, 1e6, 1e7]),
+    ("c_on_w", 6, 12.0, util.W, [1e2, 1e4, 1e5, 1e6, 1e7, 1e8]),
+    ("xe_on_uo2", 54, 131.904, {"rho": 10.97, "elements": [{"Z": 92, "m": 238.03, "t": 1}, {"Z": 8, "m": 15.999, "t": 2}]},
+     [1e3, 1e5, 1e7, 1e8, 1e9]),
+    ("si_on_c", 14, 28.086, {"rho": 2.26, "elements": [{"Z": 6, "m": 12.011, "t": 1}]}, [1e2, 1e4, 1e6, 1e8]),
+    ("o_on_zro2", 8, 16.0, util.ZRO2, [30.0, 1e3, 1e5, 1e7]),
+    ("u_on_uo2", 92, 235.0, util.UO2, [50.0, 1e4, 1e6, 1e8]),
+]
+
+
+def stopping():
+    out = {}
+    for name, Z, m, mat, energies in STOPPING_CASES:
+        lines = util.reference_script((Z, m, 0.0), [mat], [1000.0])
+        for E in energies:
+            lines.append("stopping %d %.17g %.17g" % (Z, m, E))
+        lines.append("average %d %.17g" % (Z, m))
+        res = util.run_reference("\n".join(lines) + "\n")
+        vals = [float(l.split()[4]) for l in res if l.startswith("stopping")]
+        avg = [float(x) for x in [l for l in res if l.startswith("average")][0].split()[3:]]
+        out[name] = {"Z": Z, "m": m, "material": mat, "E": energies, "getrstop": vals, "average": avg}
+    with open(os.path.join(HERE, "stopping.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+RECORD_CASES = {"cu_on_cu_10keV": 256, "cu_on_cu_1keV": 512, "h_on_fe_100keV": 256, "he_on_fe_100keV": 96,
+                "c_on_w_1MeV": 24, "xe_on_zro2_500keV": 12}
+
+
+def records():
+    for name, n in RECORD_CASES.items():
+        c = util.CONFIGS[name]
+        seeds = util.distinct_seeds(n)
+        rec, summary, hist = util.run_reference_cascades(c["ion"], c["materials"], c["thicknesses"], seeds,
+                                                         box=c.get("box"))
+        np.savez_compressed(os.path.join(HERE, "ref_records_%s.npz" % name), records=rec, seeds=seeds,
+                            vac=hist[:, 1].astype(np.uint64), repl=hist[:, 2].astype(np.uint64),
+                            summary=json.dumps(summary))
+
+
+def published():
+    src = "/root/reference/validation/vacancy_count/vacancy_count_comparison.dat"
+    rows = [l.strip().split(",") for l in open(src)][2:]
+    rows = [r for r in rows if len(r) >= 13 and r[0]]
+    data = {"energy_keV": [float(r[0]) for r in rows],
+            "si_on_c_kp": [float(r[1]) for r in rows], "si_on_c_exact": [float(r[2]) for r in rows],
+            "xe_on_u_kp": [float(r[5]) for r in rows], "xe_on_u_exact": [float(r[6]) for r in rows],
+            "cu_on_cu_kp": [float(r[9]) for r in rows], "cu_on_cu_exact": [float(r[10]) for r in rows],
+            "source": "validation/vacancy_count/vacancy_count_comparison.dat (MyTRIM: KP / MyTRIM: exact columns)"}
+    with open(os.path.join(HERE, "vacancy_count_published.json"), "w") as f:
+        json.dump(data, f, indent=1)
+
+
+if __name__ == "__main__":
+    import __graft_entry__ as g
+    g.build_test_infrastructure()
+    uo2()
+    rng()
+    stopping()
+    records()
+    published()
+    print("golden fixtures written to", HERE)

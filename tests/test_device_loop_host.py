@@ -1,0 +1,103 @@
+"""The CUDA kernel's lane loop (mytrim_b200/csrc/mtb_transport.cuh) compiled for the host
+(tests/hostsim.cpp) against the double-precision oracle with the same Philox streams.  This checks
+the FP32 reformulations, the depth-first stack traversal and the tallies without a GPU; the GPU
+tests repeat it through the real kernels."""
+import numpy as np
+import pytest
+
+from mytrim_b200 import capi
+from tests import util
+
+TOL = 1e-5  # north_star: per-ion trajectories within 1e-5 relative
+
+
+def _pair(cfg, name):
+    orc = util.OracleEngine(util.ORC_RNG_PHILOX, **cfg)
+    hs = util.HostSimEngine(**cfg)
+    c = util.setup_engine(orc, name)
+    util.setup_engine(hs, name)
+    return orc, hs, c
+
+
+@pytest.mark.parametrize("name,n", [("cu_on_cu_10keV", 200), ("cu_on_cu_1keV", 500), ("h_on_fe_100keV", 200),
+                                    ("he_on_fe_100keV", 60), ("c_on_w_1MeV", 12), ("xe_on_zro2_500keV", 6)])
+def test_trajectories_match_oracle(name, n):
+    cfg = dict(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS | capi.TALLY_PHONON)
+    orc, hs, c = _pair(cfg, name)
+    ions = util.primaries_for(c, n)
+    ro = orc.run(ions, seed=2344, records=True)
+    rh = hs.run(ions, seed=2344, records=True)
+    same = (ro["vacancies"] == rh["vacancies"]) & (ro["steps"] == rh["steps"]) & (ro["ions"] == rh["ions"])
+    assert same.mean() >= 0.8
+    path = np.maximum(np.linalg.norm(ro["pos"] - ions["pos"], axis=1), 1.0)
+    sel = ro["primary_steps"] == rh["primary_steps"]
+    assert sel.mean() >= 0.95
+    assert (np.linalg.norm(ro["pos"] - rh["pos"], axis=1) / path)[sel].max() < TOL
+    assert np.abs(ro["Eel"][same] - rh["Eel"][same]).max() <= TOL * ro["Eel"][same].max()
+    co, ch = orc.counters(), hs.counters()
+    # energy partition closes: E0 = Eel + Enuc for every non-lost cascade
+    E0 = c["ion"][2] * n
+    assert abs(ch["EelTotal"] + ch["EnucTotal"] - E0) < 1e-6 * E0
+    assert abs(co["EelTotal"] + co["EnucTotal"] - E0) < 1e-9 * E0
+    assert ch["stack_max"] <= 32
+
+
+def test_stopping_matches_oracle():
+    import json, os
+    data = json.load(open(os.path.join(util.GOLDEN, "stopping.json")))
+    for name, d in data.items():
+        E = np.logspace(1.5, 8.5, 200)
+        with util.OracleEngine(util.ORC_RNG_PHILOX) as orc, util.HostSimEngine() as hs:
+            orc.set_materials([d["material"]])
+            hs.set_materials([d["material"]])
+            a = orc.stopping(0, d["Z"], d["m"], E)
+            b = hs.stopping(0, d["Z"], d["m"], E)
+        assert np.abs(b / a - 1).max() < 5e-6, name
+
+
+def test_follow_policies_and_vacancy_models():
+    for cfg in (dict(follow=capi.FOLLOW_NONE, vacancy_model=capi.VAC_NRT, tally_mask=capi.TALLY_RANGE),
+                dict(follow=capi.FOLLOW_GEN_LT, follow_max_gen=2, vacancy_model=capi.VAC_KP),
+                dict(follow=capi.FOLLOW_GEN_LT, follow_max_gen=1, vacancy_model=capi.VAC_KP),
+                dict(tally_mask=capi.TALLY_VAC_ENERGY | capi.TALLY_VACMAP, vmap_z=(29, 8, -1))):
+        orc, hs, c = _pair(cfg, "cu_on_cu_10keV")
+        ions = util.primaries_for(c, 150)
+        orc.run(ions, seed=11)
+        hs.run(ions, seed=11)
+        co, ch = orc.counters(), hs.counters()
+        for k in ("steps", "ions", "replacements", "recoils_queued"):
+            assert co[k] == ch[k], (cfg, k)
+        assert abs(co["vacancies_created"] - ch["vacancies_created"]) <= 2e-4 * co["vacancies_created"] + 1
+        if cfg.get("tally_mask", 0) & capi.TALLY_RANGE:
+            xo, zo = orc.range_list()
+            xh, zh = hs.range_list()
+            assert len(xo) == len(xh) and np.array_equal(np.sort(zo), np.sort(zh))
+            assert np.allclose(np.sort(xo), np.sort(xh), rtol=0, atol=1e-3)
+        if cfg.get("tally_mask", 0) & capi.TALLY_VAC_ENERGY:
+            eo, eh = orc.vac_energy(), hs.vac_energy()
+            assert eo.sum() == eh.sum() and np.abs(eo.astype(int) - eh.astype(int)).sum() <= 1e-3 * eo.sum()
+            assert np.array_equal(orc.vacmap(), hs.vacmap())
+
+
+def test_ion_log_and_events():
+    cfg = dict(tally_mask=capi.TALLY_IONLOG, ionlog_z=8)
+    orc, hs, c = _pair(cfg, "xe_on_zro2_500keV")
+    ions = util.primaries_for(c, 2)
+    orc.run(ions, seed=5)
+    hs.run(ions, seed=5)
+    lo, lh = orc.ion_log(), hs.ion_log()
+    assert len(lo) == len(lh) > 100
+    lo, lh = np.sort(lo, order="uid"), np.sort(lh, order="uid")
+    assert np.array_equal(lo["uid"], lh["uid"]) and np.array_equal(lo["gen"], lh["gen"])
+    assert (lo["Z"] == 8).all() and np.array_equal(lo["state"], lh["state"])
+    assert np.abs(lo["pos1"] - lh["pos1"]).max() < 1e-3
+    # single-ion event mode (mtb_trim_one): the hooks' view of every collision
+    ion = ions[0]
+    fo, so, eo = orc.trim_one(ion, 99, 1234)
+    fh, sh, eh = hs.trim_one(ion, 99, 1234)
+    assert so == sh and len(eo) == len(eh) > 10
+    for f in ("material", "element", "pka_state", "recoil_above_threshold"):
+        assert np.array_equal(eo[f], eh[f]), f
+    assert np.abs(eo["pka_pos"] - eh["pka_pos"]).max() < 1e-5 * np.abs(eo["pka_pos"]).max()
+    assert np.abs(eo["recoil_E"] - eh["recoil_E"]).max() <= 1e-5 * np.abs(eo["recoil_E"]).max()
+    assert np.abs(fo["pos"] - fh["pos"]).max() < 1e-5 * np.abs(fo["pos"]).max()

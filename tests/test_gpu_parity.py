@@ -1,0 +1,191 @@
+"""Parity tests proper: the CUDA path through the C ABI against the oracle with the same Philox
+streams (deterministic criterion, 1e-5 relative) and against golden records of the unmodified
+reference (statistical criterion).  All need a B200."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from mytrim_b200 import capi
+from tests import util
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5  # north_star: per-ion trajectories within 1e-5 relative of the CPU replay
+
+
+def _pair(cfg, name):
+    eng = capi.Engine(**cfg)
+    orc = util.OracleEngine(util.ORC_RNG_PHILOX, **cfg)
+    c = util.setup_engine(eng, name)
+    util.setup_engine(orc, name)
+    return eng, orc, c
+
+
+@pytest.mark.parametrize("name,n", [("cu_on_cu_10keV", 1000), ("cu_on_cu_1keV", 4000), ("h_on_fe_100keV", 1000),
+                                    ("he_on_fe_100keV", 300), ("c_on_w_1MeV", 48), ("xe_on_zro2_500keV", 24)])
+def test_trajectories_match_oracle(name, n):
+    cfg = dict(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS | capi.TALLY_PHONON)
+    eng, orc, c = _pair(cfg, name)
+    ions = util.primaries_for(c, n)
+    rg = eng.run(ions, seed=2344, records=True)
+    ro = orc.run(ions, seed=2344, records=True)
+    same = (ro["vacancies"] == rg["vacancies"]) & (ro["steps"] == rg["steps"]) & (ro["ions"] == rg["ions"])
+    assert same.mean() >= 0.8, same.mean()
+    path = np.maximum(np.linalg.norm(ro["pos"] - ions["pos"], axis=1), 1.0)
+    sel = ro["primary_steps"] == rg["primary_steps"]
+    assert sel.mean() >= 0.95
+    rel = (np.linalg.norm(ro["pos"] - rg["pos"], axis=1) / path)[sel]
+    assert rel.max() < TOL, rel.max()
+    assert np.abs(ro["Eel"][same] - rg["Eel"][same]).max() <= TOL * ro["Eel"][same].max()
+    cg, co = eng.counters(), orc.counters()
+    E0 = c["ion"][2] * n
+    assert abs(cg["EelTotal"] + cg["EnucTotal"] - E0) < 1e-6 * E0   # energy partition closes
+    for k in ("vacancies_created", "replacements", "steps", "ions"):
+        assert abs(cg[k] - co[k]) <= 0.02 * co[k], k
+    vg, rpg = eng.vac_depth()
+    vo, rpo = orc.vac_depth()
+    assert vg.sum() == cg["vacancies_created"] - cg["hist_clamped"] or vg.sum() <= cg["vacancies_created"]
+    m = max(len(vg), len(vo))
+    d = np.abs(np.pad(vg, (0, m - len(vg))).astype(int) - np.pad(vo, (0, m - len(vo))).astype(int)).sum()
+    assert d <= 0.05 * vo.sum() + 5
+    eng.close()
+
+
+def test_stopping_matches_oracle():
+    data = json.load(open(os.path.join(util.GOLDEN, "stopping.json")))
+    for name, d in data.items():
+        E = np.logspace(1.5, 8.5, 400)
+        with capi.Engine() as eng, util.OracleEngine(util.ORC_RNG_PHILOX) as orc:
+            eng.set_materials([d["material"]])
+            orc.set_materials([d["material"]])
+            a = orc.stopping(0, d["Z"], d["m"], E)
+            b = eng.stopping(0, np.full(len(E), d["Z"]), np.full(len(E), d["m"]), E)
+            # golden known answers of the compiled reference
+            g = eng.stopping(0, np.full(len(d["E"]), d["Z"]), np.full(len(d["E"]), d["m"]), d["E"])
+        assert np.abs(b / a - 1).max() < TOL, (name, np.abs(b / a - 1).max())
+        assert np.abs(g / np.array(d["getrstop"]) - 1).max() < TOL, name
+
+
+def test_sharding_invariance():
+    """Results do not depend on how primaries are split across launches / GPUs (global Philox ids)."""
+    cfg = dict(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS)
+    c = util.CONFIGS["cu_on_cu_10keV"]
+    ions = util.primaries_for(c, 3000)
+    with capi.Engine(**cfg) as a, capi.Engine(**cfg) as b:
+        util.setup_engine(a, c)
+        util.setup_engine(b, c)
+        ra = a.run(ions, seed=77, records=True)
+        rb = np.concatenate([b.run(ions[:1100], seed=77, first_index=0, records=True),
+                             b.run(ions[1100:], seed=77, first_index=1100, records=True)])
+        for f in ra.dtype.names:
+            assert np.array_equal(ra[f], rb[f]), f
+        va, _ = a.vac_depth()
+        vb, _ = b.vac_depth()
+        assert np.array_equal(va, vb)
+        ca, cb = a.counters(), b.counters()
+        assert ca["steps"] == cb["steps"] and ca["vacancies_created"] == cb["vacancies_created"]
+        # beam mode (template ion) is the same thing without the per-primary host array
+        b.reset_tallies()
+        rc = b.run_beam(3000, ions[0], seed=77, records=True)
+        for f in ra.dtype.names:
+            assert np.array_equal(ra[f], rc[f]), f
+
+
+def test_follow_policies_and_vacancy_models():
+    for cfg in (dict(follow=capi.FOLLOW_NONE, vacancy_model=capi.VAC_NRT, tally_mask=capi.TALLY_RANGE),
+                dict(follow=capi.FOLLOW_GEN_LT, follow_max_gen=2, vacancy_model=capi.VAC_KP),
+                dict(follow=capi.FOLLOW_GEN_LT, follow_max_gen=1, vacancy_model=capi.VAC_KP),
+                dict(tally_mask=capi.TALLY_VAC_ENERGY | capi.TALLY_VACMAP, vmap_z=(29, 8, -1))):
+        eng, orc, c = _pair(cfg, "cu_on_cu_10keV")
+        ions = util.primaries_for(c, 600)
+        eng.run(ions, seed=11)
+        orc.run(ions, seed=11)
+        cg, co = eng.counters(), orc.counters()
+        for k in ("steps", "ions", "replacements", "recoils_queued", "vacancies_created"):
+            assert abs(cg[k] - co[k]) <= 0.01 * co[k] + 1, (cfg, k, cg[k], co[k])
+        if cfg.get("tally_mask", 0) & capi.TALLY_RANGE:
+            xg, zg = eng.range_list()
+            xo, zo = orc.range_list()
+            assert abs(len(xg) - len(xo)) <= 0.01 * len(xo)
+            assert abs(np.mean(xg) - np.mean(xo)) < 0.02 * abs(np.mean(xo))
+        if cfg.get("tally_mask", 0) & capi.TALLY_VAC_ENERGY:
+            eg, eo = eng.vac_energy(), orc.vac_energy()
+            assert abs(int(eg.sum()) - int(eo.sum())) <= 0.01 * eo.sum()
+            assert np.abs(eg.sum(axis=1).astype(int) - eo.sum(axis=1).astype(int)).sum() <= 0.02 * eo.sum()
+            assert abs(int(eng.vacmap().sum()) - int(orc.vacmap().sum())) <= 0.01 * orc.vacmap().sum()
+        eng.close()
+
+
+def test_ion_log_and_single_ion_events():
+    cfg = dict(tally_mask=capi.TALLY_IONLOG, ionlog_z=8)
+    eng, orc, c = _pair(cfg, "xe_on_zro2_500keV")
+    ions = util.primaries_for(c, 2)
+    eng.run(ions, seed=5)
+    orc.run(ions, seed=5)
+    lg, lo = eng.ion_log(), orc.ion_log()
+    assert abs(len(lg) - len(lo)) <= 0.05 * len(lo)
+    common = np.intersect1d(lg["uid"], lo["uid"])
+    assert len(common) >= 0.9 * len(lo)
+    ion = ions[0]
+    fg, sg, eg = eng.trim_one(ion, 99, 1234)
+    fo, so, eo = orc.trim_one(ion, 99, 1234)
+    assert sg == so and len(eg) == len(eo) > 10
+    for f in ("material", "element", "pka_state", "recoil_above_threshold"):
+        assert np.array_equal(eg[f], eo[f]), f
+    assert np.abs(eg["pka_pos"] - eo["pka_pos"]).max() < TOL * np.abs(eo["pka_pos"]).max()
+    assert np.abs(fg["pos"] - fo["pos"]).max() < TOL * np.abs(fo["pos"]).max()
+    eng.close()
+
+
+def test_wire_and_clusters_geometry():
+    """CUT boundaries / vacuum (SampleWire) and the spatial-hash cluster lookup (sampleClusters)."""
+    # wire: Cu wire 200 A across, ions start on the axis and fly along z
+    cfg = dict(tally_mask=capi.TALLY_RECORDS)
+    with capi.Engine(**cfg) as eng, util.OracleEngine(util.ORC_RNG_PHILOX, **cfg) as orc:
+        for e in (eng, orc):
+            e.set_materials([util.CU])
+            e.set_geometry(capi.GEOM_WIRE, (200.0, 200.0, 1000.0), bc=(capi.BC_CUT, capi.BC_CUT, capi.BC_PBC))
+        ions = capi.make_ions(400, 29, 63.546, 5e4, pos=(100.0, 60.0, 0.0), direction=(0.0, 0.3, 1.0))
+        rg = eng.run(ions, seed=3, records=True)
+        ro = orc.run(ions, seed=3, records=True)
+        cg, co = eng.counters(), orc.counters()
+        assert co["left_sample"] > 0
+        for k in ("steps", "ions", "left_sample", "lost", "vacancies_created"):
+            assert abs(cg[k] - co[k]) <= 0.02 * co[k] + 2, (k, cg[k], co[k])
+        assert (rg["state"] == ro["state"]).mean() > 0.97
+    # clusters: UO2 matrix with Xe bubbles (tests/uo2 geometry, 4 bubbles)
+    cl = np.loadtxt(os.path.join(util.GOLDEN, "uo2_out.clcoor"))[:, :4]
+    cfg = dict(tally_mask=capi.TALLY_RECORDS | capi.TALLY_IONLOG, ionlog_z=54)
+    with capi.Engine(**cfg) as eng, util.OracleEngine(util.ORC_RNG_PHILOX, **cfg) as orc:
+        for e in (eng, orc):
+            e.set_materials([util.UO2, util.XE_GAS])
+            e.set_geometry(capi.GEOM_CLUSTERS, (400.0, 400.0, 400.0), kn=(39, 39, 39), clusters=cl)
+        # Xe ions starting inside bubble 0, flying out through the matrix
+        ions = capi.make_ions(200, 54, 132.0, 3e4, pos=tuple(cl[0, :3]), direction=(0.6, 0.0, 0.8))
+        rg = eng.run(ions, seed=9, records=True)
+        ro = orc.run(ions, seed=9, records=True)
+        cg, co = eng.counters(), orc.counters()
+        for k in ("steps", "ions", "vacancies_created"):
+            assert abs(cg[k] - co[k]) <= 0.02 * co[k] + 2, (k, cg[k], co[k])
+        lg, lo = eng.ion_log(), orc.ion_log()
+        # Xe recoils knocked out of a bubble carry that bubble's index as tag
+        assert set(np.unique(lg["tag"])) <= {-1, 0, 1, 2, 3} and (lg["tag"] >= 0).sum() > 0
+        assert abs((lg["tag"] >= 0).sum() - (lo["tag"] >= 0).sum()) <= 0.05 * (lo["tag"] >= 0).sum() + 3
+
+
+@pytest.mark.parametrize("name", ["cu_on_cu_10keV", "h_on_fe_100keV", "he_on_fe_100keV"])
+def test_statistics_against_reference_golden(name):
+    """Two-sample KS against per-primary records of the unmodified reference (tests/golden)."""
+    from scipy import stats
+    gold = np.load(os.path.join(util.GOLDEN, "ref_records_%s.npz" % name))["records"]
+    c = util.CONFIGS[name]
+    n = 20000
+    with capi.Engine(tally_mask=capi.TALLY_RECORDS) as eng:
+        util.setup_engine(eng, c)
+        rec = eng.run(util.primaries_for(c, n), seed=4242, records=True)
+    for field, getter in (("x", lambda r: r["pos"][:, 0]), ("vacancies", lambda r: r["vacancies"].astype(float)),
+                          ("Eel", lambda r: r["Eel"]),
+                          ("lateral", lambda r: np.hypot(r["pos"][:, 1] - 50.0, r["pos"][:, 2] - 50.0))):
+        p = stats.ks_2samp(getter(rec), getter(gold)).pvalue
+        assert p > 0.001, (name, field, p)

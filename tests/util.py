@@ -1,0 +1,209 @@
+"""Test helpers: drive the CPU oracle, the host simulator of the device loop and the compiled
+reference with the same plain-struct inputs the CUDA engine takes."""
+import ctypes as C
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+from mytrim_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_LIB = os.path.join(ROOT, "oracle", "liboracle.so")
+HOSTSIM_LIB = os.path.join(ROOT, "tests", "libhostsim.so")
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+REF_DRIVER = os.path.join(REF_DIR, "ref_driver")
+REF_UO2 = os.path.join(REF_DIR, "mytrim_uo2")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+ORC_RNG_MT19937, ORC_RNG_PHILOX = 0, 1
+
+_libs = {}
+
+
+def _load(path, prefix):
+    if path not in _libs:
+        lib = C.CDLL(path)
+        capi.declare(lib, prefix)
+        _libs[path] = lib
+    return _libs[path]
+
+
+class OracleEngine(capi.EngineBase):
+    _prefix = "orc_"
+
+    def __init__(self, rng_mode=ORC_RNG_PHILOX, config=None, **kw):
+        lib = _load(ORACLE_LIB, "orc_")
+        cfg = config if config is not None else capi.default_config(**kw)
+        lib.orc_create.argtypes = [C.POINTER(capi.Config), C.c_int]
+        lib.orc_create.restype = C.c_void_p
+        lib.orc_getrstop.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
+        lib.orc_getrstop.restype = C.c_double
+        lib.orc_average.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_size_t]
+        lib.orc_average.restype = C.c_int
+        lib.orc_destroy.restype = None
+        super().__init__(lib, C.c_void_p(lib.orc_create(C.byref(cfg), rng_mode)))
+        self.config = cfg
+
+    def stopping(self, material, Z1, m1, E):
+        Z1 = np.broadcast_to(np.asarray(Z1), np.shape(E))
+        m1 = np.broadcast_to(np.asarray(m1, dtype=float), np.shape(E))
+        return np.array([self._lib.orc_getrstop(self._h, material, int(z), float(m), float(e))
+                         for z, m, e in zip(Z1, m1, np.asarray(E, dtype=float))])
+
+    def average(self, material, Z1, m1, n_elements):
+        out = np.zeros(6 + 4 * n_elements)
+        self._check(self._lib.orc_average(self._h, material, Z1, m1, out.ctypes.data, len(out)))
+        return out
+
+    def range_list(self, capacity=1 << 22):
+        x = np.zeros(capacity, dtype=np.float64)
+        z = np.zeros(capacity, dtype=np.int32)
+        n = C.c_size_t()
+        self._check(self._lib.orc_get_range_list(self._h, x.ctypes.data, z.ctypes.data, capacity, C.byref(n)))
+        return x[:n.value].copy(), z[:n.value].copy()
+
+
+class HostSimEngine(capi.EngineBase):
+    """The device lane loop compiled for the host (tests/hostsim.cpp)."""
+    _prefix = "hs_"
+
+    def __init__(self, config=None, **kw):
+        lib = _load(HOSTSIM_LIB, "hs_")
+        cfg = config if config is not None else capi.default_config(**kw)
+        lib.hs_create.argtypes = [C.POINTER(capi.Config)]
+        lib.hs_create.restype = C.c_void_p
+        lib.hs_error.argtypes = [C.c_void_p]
+        lib.hs_error.restype = C.c_char_p
+        lib.hs_destroy.restype = None
+        super().__init__(lib, C.c_void_p(lib.hs_create(C.byref(cfg))))
+        self.config = cfg
+
+    def _error_text(self):
+        return self._lib.hs_error(self._h).decode()
+
+    def reset_tallies(self):
+        raise NotImplementedError
+
+    def stopping(self, material, Z1, m1, E):
+        E = np.ascontiguousarray(E, dtype=np.float64)
+        Z1 = np.ascontiguousarray(np.broadcast_to(Z1, E.shape), dtype=np.int32)
+        m1 = np.ascontiguousarray(np.broadcast_to(m1, E.shape), dtype=np.float64)
+        out = np.zeros(len(E))
+        self._check(self._lib.hs_stopping(self._h, material, len(E), Z1.ctypes.data, m1.ctypes.data,
+                                          E.ctypes.data, out.ctypes.data))
+        return out
+
+    def range_list(self, capacity=1 << 22):
+        x = np.zeros(capacity, dtype=np.float32)
+        z = np.zeros(capacity, dtype=np.int32)
+        n = C.c_size_t()
+        self._check(self._lib.hs_get_range_list(self._h, x.ctypes.data, z.ctypes.data, capacity, C.byref(n)))
+        return x[:n.value].copy(), z[:n.value].copy()
+
+
+def have_reference():
+    return os.path.exists(REF_DRIVER)
+
+
+def ref_env():
+    env = dict(os.environ)
+    env["MYTRIM_DATADIR"] = os.path.join(REF_DIR, "data")
+    return env
+
+
+def run_reference(script, timeout=600):
+    """Feeds a command script to oracle/_ref/ref_driver; returns stdout lines."""
+    p = subprocess.run([REF_DRIVER], input=script, capture_output=True, text=True, env=ref_env(), timeout=timeout)
+    if p.returncode != 0:
+        raise RuntimeError("ref_driver failed: " + p.stderr)
+    return p.stdout.strip().split("\n")
+
+
+def reference_script(ion, materials, thicknesses, n=0, tally="vaccount", threads=1, seeds_file=None, master=2344,
+                     out=None, primaries_only=False, box=None, start=None, scale=None):
+    Z, m, E = ion
+    lines = ["ion %d %.17g %.17g" % (Z, m, E), "n %d" % n, "threads %d" % threads, "tally %s" % tally,
+             "master %d" % master, "primaries_only %d" % int(primaries_only)]
+    if scale is not None:
+        lines.append("scale %.17g" % scale)
+    if seeds_file:
+        lines.append("seeds %s" % seeds_file)
+    if box is not None:
+        lines.append("box %.17g %.17g %.17g" % tuple(box))
+    if start is not None:
+        lines.append("start " + " ".join("%.17g" % v for v in start))
+    if out:
+        lines.append("out %s" % out)
+    for mat, th in zip(materials, thicknesses):
+        lines.append("layer %.17g %.17g %d" % (th, mat["rho"], len(mat["elements"])))
+        for e in mat["elements"]:
+            lines.append("elem %d %.17g %.17g %.17g %.17g" % (e["Z"], e["m"], e["t"], e.get("Edisp", 25.0),
+                                                            e.get("Elbind", 3.0)))
+    return lines
+
+
+def run_reference_cascades(ion, materials, thicknesses, seeds, tally="vaccount", threads=1, **kw):
+    """Runs the unmodified reference for the given per-primary seeds; returns (records, summary dict)."""
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+    with tempfile.TemporaryDirectory() as tmp:
+        sf = os.path.join(tmp, "seeds.bin")
+        seeds.tofile(sf)
+        out = os.path.join(tmp, "out")
+        lines = reference_script(ion, materials, thicknesses, n=len(seeds), tally=tally, threads=threads,
+                                 seeds_file=sf, out=out, **kw)
+        lines.append("run")
+        stdout = run_reference("\n".join(lines) + "\n")
+        rec = np.fromfile(out + ".records", dtype=capi.RECORD_DTYPE)
+        hist = None
+        if os.path.exists(out + "_vac.dat"):
+            hist = np.loadtxt(out + "_vac.dat", ndmin=2)
+    return rec, json.loads(stdout[-1]), hist
+
+
+def distinct_seeds(n, master=2344):
+    """32-bit distinct per-primary seeds (SURVEY.md §8c caveat: runmytrim's irand() seeds are 16-bit)."""
+    x = (np.arange(n, dtype=np.uint64) + np.uint64((master * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF))
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    x = x ^ (x >> np.uint64(31))
+    return (x & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+
+
+# --- the BASELINE.json configurations -------------------------------------------
+CU = {"rho": 8.92, "elements": [{"Z": 29, "m": 63.546, "t": 1.0}]}
+FE = {"rho": 7.8658, "elements": [{"Z": 26, "m": 55.847, "t": 1.0}]}
+W = {"rho": 19.35, "elements": [{"Z": 74, "m": 183.85, "t": 1.0}]}
+ZRO2 = {"rho": 6.52, "elements": [{"Z": 40, "m": 90.0, "t": 1.0}, {"Z": 8, "m": 16.0, "t": 2.0}]}
+UO2 = {"rho": 10.0, "elements": [{"Z": 92, "m": 235.0, "t": 1.0}, {"Z": 8, "m": 16.0, "t": 2.0}]}
+XE_GAS = {"rho": 3.5, "elements": [{"Z": 54, "m": 132.0, "t": 1.0}]}
+
+CONFIGS = {
+    "cu_on_cu_10keV": dict(ion=(29, 63.546, 1.0e4), materials=[CU], thicknesses=[1000.0]),
+    "cu_on_cu_1keV": dict(ion=(29, 63.546, 1.0e3), materials=[CU], thicknesses=[100000.0]),
+    "h_on_fe_100keV": dict(ion=(1, 1.008, 1.0e5), materials=[FE], thicknesses=[100000.0]),
+    "he_on_fe_100keV": dict(ion=(2, 4.003, 1.0e5), materials=[FE], thicknesses=[100000.0]),
+    "c_on_w_1MeV": dict(ion=(6, 12.0, 1.0e6), materials=[W], thicknesses=[10000.0]),
+    "xe_on_zro2_500keV": dict(ion=(54, 131.0, 5.0e5), materials=[ZRO2] * 50, thicknesses=[10.0] * 50,
+                              box=(500.0, 100.0, 100.0)),
+}
+
+
+def setup_engine(eng, cfgname_or_dict):
+    c = CONFIGS[cfgname_or_dict] if isinstance(cfgname_or_dict, str) else cfgname_or_dict
+    eng.set_materials(c["materials"])
+    box = c.get("box")
+    if box:
+        eng.set_layers(c["thicknesses"], wy=box[1], wz=box[2], wx=box[0])
+    else:
+        eng.set_layers(c["thicknesses"])
+    return c
+
+
+def primaries_for(c, n, seeds=None):
+    Z, m, E = c["ion"]
+    box = c.get("box")
+    wy, wz = (box[1], box[2]) if box else (100.0, 100.0)
+    return capi.make_ions(n, Z, m, E, pos=(0.0, wy / 2.0, wz / 2.0), seeds=seeds)
