@@ -97,7 +97,7 @@ class MytrimError(RuntimeError):
 
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libmytrim_b200.so")
+LIB_PATH = os.environ.get("MYTRIM_B200_LIB", os.path.join(_PKG_DIR, "libmytrim_b200.so"))
 _lib = None
 
 

@@ -41,14 +41,21 @@ fail(int code, const std::string & msg)
       return fail(MTB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(err__));                     \
   } while (0)
 
-constexpr int kBlock = 128;
+#ifndef MTB_BLOCK
+#define MTB_BLOCK 128
+#endif
+constexpr int kBlock = MTB_BLOCK;
+#ifndef MTB_MIN_BLOCKS
+#define MTB_MIN_BLOCKS 6
+#endif
+constexpr int kMinBlocks = MTB_MIN_BLOCKS;
 
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
 struct SmemLayout
 {
-  size_t elements, materials, ionz, layer_cum, layer_mat, hist_vac, hist_repl, blk_u64, blk_f64, total;
+  size_t elements, materials, ionz, lowstop, layer_cum, layer_mat, hist_vac, hist_repl, blk_u64, blk_f64, total;
 };
 
 __host__ __device__ inline size_t
@@ -74,6 +81,8 @@ smem_layout(const LaunchParams & P)
   o += (size_t)P.n_materials * sizeof(DevMaterial);
   L.ionz = o = align_up(o, 16);
   o += (MTB_NZ + 1) * sizeof(DevIonZ);
+  L.lowstop = o;
+  o += (size_t)(MTB_NZ + 1) * (size_t)P.n_zslots * sizeof(LowStop);
   L.layer_mat = o;
   o += (size_t)P.n_layers * sizeof(int32_t);
   L.hist_vac = o = align_up(o, 16);
@@ -103,6 +112,7 @@ stage_block(const LaunchParams & P, unsigned char * smem)
   DevElement * el = reinterpret_cast<DevElement *>(smem + L.elements);
   DevMaterial * mat = reinterpret_cast<DevMaterial *>(smem + L.materials);
   DevIonZ * iz = reinterpret_cast<DevIonZ *>(smem + L.ionz);
+  LowStop * lw = reinterpret_cast<LowStop *>(smem + L.lowstop);
   double * lc = reinterpret_cast<double *>(smem + L.layer_cum);
   int32_t * lm = reinterpret_cast<int32_t *>(smem + L.layer_mat);
   unsigned int * hv = reinterpret_cast<unsigned int *>(smem + L.hist_vac);
@@ -112,6 +122,7 @@ stage_block(const LaunchParams & P, unsigned char * smem)
   block_copy(el, P.elements, (size_t)P.n_elements);
   block_copy(mat, P.materials, (size_t)P.n_materials);
   block_copy(iz, P.ionz, (size_t)MTB_NZ + 1);
+  block_copy(lw, P.lowstop, (size_t)(MTB_NZ + 1) * (size_t)P.n_zslots);
   if (P.n_layers > 0)
   {
     block_copy(lc, P.layer_cum, (size_t)P.n_layers);
@@ -127,6 +138,7 @@ stage_block(const LaunchParams & P, unsigned char * smem)
   S.elements = el;
   S.materials = mat;
   S.ionz = iz;
+  S.lowstop = lw;
   S.layer_cum = lc;
   S.layer_mat = lm;
   S.hist_vac = hv;
@@ -160,12 +172,13 @@ flush_block(const LaunchParams & P, const BlockCtx & S)
     atomicAdd(&P.f64[threadIdx.x], S.blk_f64[threadIdx.x]);
 }
 
-__global__ void __launch_bounds__(kBlock)
+template <class TR>
+__global__ void __launch_bounds__(kBlock, kMinBlocks)
 transport_kernel(const __grid_constant__ LaunchParams P)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   const BlockCtx S = stage_block(P, smem);
-  lane_loop<false>(P, S, blockIdx.x * blockDim.x + threadIdx.x);
+  lane_loop<TR>(P, S, blockIdx.x * blockDim.x + threadIdx.x);
   flush_block(P, S);
 }
 
@@ -175,7 +188,7 @@ trim_one_kernel(const __grid_constant__ LaunchParams P)
   extern __shared__ __align__(16) unsigned char smem[];
   const BlockCtx S = stage_block(P, smem);
   if (threadIdx.x == 0)
-    lane_loop<true>(P, S, 0);
+    lane_loop<TraitsEvents>(P, S, 0);
   flush_block(P, S);
 }
 
@@ -188,14 +201,7 @@ stopping_kernel(const __grid_constant__ LaunchParams P, int material, size_t n, 
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n)
   {
-    Projectile pr;
-    const DevIonZ & iz = S.ionz[Z1[i]];
-    pr.Z = Z1[i];
-    pr.fz = (float)Z1[i];
-    pr.m = m1[i] == 0.0 ? iz.mm1 : (float)m1[i];
-    pr.z023 = iz.z023;
-    pr.cbrt = iz.cbrt;
-    pr.lfctr = iz.lfctr;
+    const Projectile pr = make_projectile(P, S, Z1[i], (float)m1[i]);
     out[i] = (double)material_stopping(pr, S.materials[material], S.elements, (float)E[i]);
   }
 }
@@ -272,6 +278,8 @@ struct mtb_handle
   DevBuf<DevElement> d_elements;
   DevBuf<DevMaterial> d_materials;
   DevBuf<DevIonZ> d_ionz;
+  DevBuf<LowStop> d_lowstop;
+  bool fast = false;
   DevBuf<double> d_layer_cum, d_cl_xyzr;
   DevBuf<int32_t> d_layer_mat, d_cl_hash, d_cl_next;
   // outputs
@@ -313,7 +321,9 @@ build_tables(mtb_handle * h)
   MTB_CUDA(h->d_ionz.upload(T.ionz.data(), T.ionz.size(), h->stream));
   P.elements = h->d_elements.p;
   P.materials = h->d_materials.p;
+  MTB_CUDA(h->d_lowstop.upload(T.lowstop.data(), T.lowstop.size(), h->stream));
   P.ionz = h->d_ionz.p;
+  P.lowstop = h->d_lowstop.p;
   if (P.n_layers)
   {
     MTB_CUDA(h->d_layer_cum.upload(T.layer_cum.data(), T.layer_cum.size(), h->stream));
@@ -361,11 +371,16 @@ build_tables(mtb_handle * h)
   h->smem_bytes = smem_layout(P).total;
   if (h->smem_bytes > 200 * 1024)
     return fail(MTB_EINVAL, "configuration tables do not fit in shared memory");
-  MTB_CUDA(cudaFuncSetAttribute(transport_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  h->fast = fast_path_ok(P);
+  MTB_CUDA(cudaFuncSetAttribute(transport_kernel<TraitsGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  MTB_CUDA(cudaFuncSetAttribute(transport_kernel<TraitsFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   MTB_CUDA(cudaFuncSetAttribute(trim_one_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   MTB_CUDA(cudaFuncSetAttribute(stopping_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   int bps = 0;
-  MTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, transport_kernel, kBlock, h->smem_bytes));
+  if (h->fast)
+    MTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, transport_kernel<TraitsFast>, kBlock, h->smem_bytes));
+  else
+    MTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, transport_kernel<TraitsGeneric>, kBlock, h->smem_bytes));
   h->blocks_per_sm = std::max(bps, 1);
   h->dirty = false;
   return MTB_OK;
@@ -411,7 +426,10 @@ launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, cons
   P.stacks = h->d_stacks.p;
   MTB_CUDA(cudaMemsetAsync(&P.u64[CNT_NEXT_PRIMARY], 0, sizeof(unsigned long long), h->stream));
   MTB_CUDA(cudaEventRecord(h->ev0, h->stream));
-  transport_kernel<<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+  if (h->fast && fast_path_ok(P))
+    transport_kernel<TraitsFast><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+  else
+    transport_kernel<TraitsGeneric><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
   MTB_CUDA(cudaGetLastError());
   MTB_CUDA(cudaEventRecord(h->ev1, h->stream));
   h->timing_pending = true;

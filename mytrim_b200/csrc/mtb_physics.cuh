@@ -26,6 +26,8 @@ struct Projectile
   float z023;  // Z1^0.23
   float cbrt;  // Z1^(1/3)
   float lfctr; // screening length factor of Z1
+  float inv_km; // 0.001 / m: eV -> keV/amu
+  const LowStop * low; // row of the low-velocity stopping table for this Z1
   int Z;
 };
 
@@ -48,7 +50,15 @@ proton_stopping(const DevElement & el, float e)
 MTB_HD float
 element_stopping(const Projectile & ion, const DevElement & el, float E)
 {
-  const float e = fdiv(0.001f * E, ion.m); // keV/amu
+  const float e = E * ion.inv_km; // keV/amu
+  if (ion.Z >= 3)
+  {
+    // velocity-proportional regime (material.C:259-273): rstop = coef(Z1,Z2) * e^power, with the
+    // (Z1, Z2)-only part tabulated in double on the host (mtb_tables.h)
+    const LowStop ls = ion.low[el.zslot];
+    if (e <= ls.e_max)
+      return ls.coef * (ls.power == 0.5f ? fsqrt(e) : fpow(e, ls.power));
+  }
   float se;
   if (ion.Z == 1)
   {
@@ -195,10 +205,11 @@ magic_scatter(int potential, float eps, float b)
     float sum, dsum; // sum = v*r, dsum = -(v + v1*r)
     if (potential == MTB_POT_UNIVERSAL)
     {
-      const float ex1 = 0.18175f * fexp(-3.1998f * r);
-      const float ex2 = 0.50986f * fexp(-0.94229f * r);
-      const float ex3 = 0.28022f * fexp(-0.4029f * r);
-      const float ex4 = 0.028171f * fexp(-0.20162f * r);
+      // c_i * exp(-d_i r) as c_i * 2^(-d_i log2(e) r)
+      const float ex1 = 0.18175f * fexp2(-4.6163355918f * r);
+      const float ex2 = 0.50986f * fexp2(-1.3594371101f * r);
+      const float ex3 = 0.28022f * fexp2(-0.58126183197f * r);
+      const float ex4 = 0.028171f * fexp2(-0.29087617414f * r);
       sum = (ex1 + ex2) + (ex3 + ex4);
       dsum = (3.1998f * ex1 + 0.94229f * ex2) + (0.4029f * ex3 + 0.20162f * ex4);
     }

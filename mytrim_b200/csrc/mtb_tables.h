@@ -34,6 +34,81 @@ builtin_zbl()
 
 constexpr int kSmemHistMax = 4096;
 
+// ZBL proton stopping in double — MaterialBase::rpstop, material.C:133-158
+inline double
+host_proton_stopping(const ZblRow & row, int z2, double e)
+{
+  const double pe = std::max(25.0, e);
+  const double sl = row.pcoef[0] * std::pow(pe, row.pcoef[1]) + row.pcoef[2] * std::pow(pe, row.pcoef[3]);
+  const double sh = row.pcoef[4] / std::pow(pe, row.pcoef[5]) * std::log(row.pcoef[6] / pe + row.pcoef[7] * pe);
+  double sp = sl * sh / (sl + sh);
+  if (e <= 25.0)
+    sp *= std::pow(e / 25.0, z2 <= 6 ? 0.25 : 0.45);
+  return sp;
+}
+
+// Constants of the velocity-proportional heavy-ion regime (material.C:213-273 with yr == its
+// lower clamp): effective charge zeta, matching energy eee, exponent.
+inline LowStop
+host_low_velocity_stopping(const ZblRow * zbl, int z1, int z2)
+{
+  LowStop out = {0.f, 0.f, 0.5f, 0.f};
+  if (z1 < 3)
+    return out;
+  const double fz1 = z1;
+  const double vfermi = zbl[z2 - 1].vfermi, lfctr = zbl[z1 - 1].lfctr;
+  const double cb = std::cbrt(fz1), cb2 = cb * cb;
+  const double yr = std::max(0.13, 1.0 / cb2);
+  const double yr03 = std::pow(yr, 0.3);
+  const double a = -0.803 * yr03 + 1.3167 * yr03 * yr03 + 0.38157 * yr + 0.008983 * yr * yr;
+  const double q = std::min(1.0, std::max(0.0, 1.0 - std::exp(-std::min(a, 50.0))));
+  const double b = std::min(0.43, std::max(0.32, 0.12 + 0.025 * fz1)) / cb;
+  const double l0 = (0.8 - q * std::min(1.2, 0.6 + fz1 / 30.0)) / cb;
+  const double qa = std::max(0.0, 0.9 - 0.025 * fz1), z16 = 0.025 * std::min(16.0, fz1);
+  double l1;
+  if (q < 0.2)
+    l1 = 0.0;
+  else if (q < qa)
+    l1 = b * (q - 0.2) / std::abs(qa - 0.2000001);
+  else if (q < std::max(0.0, 1.0 - z16))
+    l1 = b;
+  else
+    l1 = b * (1.0 - q) / z16;
+  const double l = std::max(l1, l0 * lfctr);
+  const double lx = 4.0 * l * vfermi / 1.919;
+  const double zeta = q + (1.0 / (2.0 * vfermi * vfermi)) * (1.0 - q) * std::log(1.0 + lx * lx);
+  const double vrmin = std::max(1.0, 0.13 * cb2);
+  const double vmin = 0.5 * (vrmin + std::sqrt(std::max(0.0, vrmin * vrmin - 0.8 * vfermi * vfermi)));
+  const double eee = 25.0 * vmin * vmin;
+  const double power = (z2 == 6 || ((z2 == 14 || z2 == 32) && z1 <= 19)) ? 0.375 : 0.5;
+  const double zf = zeta * fz1;
+  // e at which vr(e) / Z1^(2/3) leaves the clamp: vr is monotonic in e, bisect vr(e) = vrmin
+  auto vr_of = [&](double e) {
+    const double v = std::sqrt(e / 25.0) / vfermi, v2 = v * v;
+    return v >= 1.0 ? v * vfermi * (1.0 + 1.0 / (5.0 * v2)) : (3.0 * vfermi / 4.0) * (1.0 + (2.0 * v2 / 3.0) - v2 * v2 / 15.0);
+  };
+  double e_sw = 0.0;
+  if (vr_of(0.0) <= vrmin)
+  {
+    double lo = 0.0, hi = 1.0e7;
+    for (int it = 0; it < 200; ++it)
+    {
+      const double mid = 0.5 * (lo + hi);
+      if (vr_of(mid) <= vrmin)
+        lo = mid;
+      else
+        hi = mid;
+    }
+    e_sw = lo;
+  }
+  // stay a hair inside the regime so that float rounding of e never selects the shortcut beyond it,
+  // and below 20 keV/amu where the Z1^3 factor of material.C:254-255 is 1 to better than 1e-10
+  out.e_max = (float)(std::min(e_sw, 20.0) * (1.0 - 1e-6));
+  out.coef = (float)(10.0 * host_proton_stopping(zbl[z2 - 1], z2, eee) * zf * zf / std::pow(eee, power));
+  out.power = (float)power;
+  return out;
+}
+
 struct HostConfig
 {
   mtb_config cfg;
@@ -62,6 +137,7 @@ struct HostTables
   std::vector<DevElement> elements;
   std::vector<DevMaterial> materials;
   std::vector<DevIonZ> ionz;
+  std::vector<LowStop> lowstop; // [MTB_NZ + 1][n_zslots]
   std::vector<double> layer_cum;
   std::vector<int32_t> layer_mat, cl_hash, cl_next;
 };
@@ -210,6 +286,23 @@ build_host_tables(const HostConfig & H, HostTables & T, LaunchParams & P, std::s
     T.ionz[z].lfctr = (float)H.zbl[z - 1].lfctr;
     T.ionz[z].mm1 = (float)H.zbl[z - 1].mm1;
   }
+  // low-velocity stopping table over the distinct target Z of this configuration
+  std::vector<int> zlist;
+  for (auto & d : T.elements)
+  {
+    auto it = std::find(zlist.begin(), zlist.end(), d.Z);
+    if (it == zlist.end())
+    {
+      zlist.push_back(d.Z);
+      it = zlist.end() - 1;
+    }
+    d.zslot = (int32_t)(it - zlist.begin());
+  }
+  P.n_zslots = (int32_t)zlist.size();
+  T.lowstop.assign((size_t)(MTB_NZ + 1) * zlist.size(), LowStop{0.f, 0.f, 0.5f, 0.f});
+  for (int z1 = 1; z1 <= MTB_NZ; ++z1)
+    for (size_t k = 0; k < zlist.size(); ++k)
+      T.lowstop[(size_t)z1 * zlist.size() + k] = host_low_velocity_stopping(H.zbl, z1, zlist[k]);
   P.n_elements = (int32_t)T.elements.size();
   P.n_materials = (int32_t)T.materials.size();
   if (P.n_elements + SPECIES_ELEMENT0 > SPECIES_MASK)

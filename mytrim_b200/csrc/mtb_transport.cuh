@@ -48,12 +48,49 @@ host_fetch_max(T * p, U v)
 #define MTB_ATOMIC_MAX(ptr, val) ::mtb::host_fetch_max((ptr), (val))
 #endif
 
+// Compile-time specialisation of the lane loop.  The generic variant reads every option from
+// LaunchParams; the fast variant fixes the options of the north-star workload (UNIVERSAL
+// potential, follow ALL, vacancies_created++, TrimVacCount depth tallies, solid/layered sample
+// without CUT boundaries) so that the unused hook code is not even in the instruction cache.
+struct TraitsGeneric
+{
+  static constexpr bool kEvents = false, kGeneric = true;
+  static constexpr uint32_t kTally = 0;
+};
+struct TraitsEvents
+{
+  static constexpr bool kEvents = true, kGeneric = true;
+  static constexpr uint32_t kTally = 0;
+};
+struct TraitsFast
+{
+  static constexpr bool kEvents = false, kGeneric = false;
+  static constexpr uint32_t kTally = MTB_TALLY_VAC_DEPTH;
+};
+
+template <class TR>
+MTB_HD bool
+tally_on(const LaunchParams & P, uint32_t bit)
+{
+  return TR::kGeneric ? (P.tally_mask & bit) != 0 : (TR::kTally & bit) != 0;
+}
+
+// Does this configuration qualify for TraitsFast?
+inline bool
+fast_path_ok(const LaunchParams & P)
+{
+  return P.potential == MTB_POT_UNIVERSAL && P.follow == MTB_FOLLOW_ALL && P.vacancy_model == MTB_VAC_COUNT &&
+         (P.tally_mask & ~(uint32_t)MTB_TALLY_RECORDS) == MTB_TALLY_VAC_DEPTH && (P.geom_kind == MTB_GEOM_SOLID || P.geom_kind == MTB_GEOM_LAYERS) &&
+         P.bc[0] != MTB_BC_CUT && P.bc[1] != MTB_BC_CUT && P.bc[2] != MTB_BC_CUT;
+}
+
 // Block-local views: the small tables staged in shared memory plus block accumulators.
 struct BlockCtx
 {
   const DevElement * elements;
   const DevMaterial * materials;
   const DevIonZ * ionz;
+  const LowStop * lowstop;
   const double * layer_cum;
   const int32_t * layer_mat;
   unsigned int * hist_vac;  // [smem_hist_bins] or null
@@ -155,10 +192,26 @@ lookup_cluster(const LaunchParams & P, double px, double py, double pz)
   return -1;
 }
 
+template <class TR>
 MTB_HD int
 lookup_material(const LaunchParams & P, const BlockCtx & S, double px, double py, double pz, int * cluster)
 {
   *cluster = -1;
+  if (!TR::kGeneric)
+  {
+    if (P.geom_kind == MTB_GEOM_SOLID || P.n_layers == 1)
+      return 0;
+    int lo = 0, hi = P.n_layers - 1;
+    while (lo < hi)
+    {
+      const int mid = (lo + hi) >> 1;
+      if (px < S.layer_cum[mid])
+        hi = mid;
+      else
+        lo = mid + 1;
+    }
+    return S.layer_mat[lo];
+  }
   switch (P.geom_kind)
   {
     case MTB_GEOM_SOLID: // sample_solid.C:25-29
@@ -229,7 +282,7 @@ struct Lane
 };
 
 MTB_HD void
-set_projectile(Lane & L, const BlockCtx & S)
+set_projectile(const LaunchParams & P, Lane & L, const BlockCtx & S)
 {
   const uint32_t species = L.packed & SPECIES_MASK;
   int Z;
@@ -252,11 +305,39 @@ set_projectile(Lane & L, const BlockCtx & S)
   L.proj.z023 = iz.z023;
   L.proj.cbrt = iz.cbrt;
   L.proj.lfctr = iz.lfctr;
+  L.proj.inv_km = fdiv(0.001f, L.proj.m);
+  L.proj.low = S.lowstop + Z * P.n_zslots;
+}
+
+MTB_HD Projectile
+make_projectile(const LaunchParams & P, const BlockCtx & S, int Z, float m)
+{
+  Projectile pr;
+  const DevIonZ & iz = S.ionz[Z];
+  pr.Z = Z;
+  pr.fz = (float)Z;
+  pr.m = (m == 0.0f) ? iz.mm1 : m;
+  pr.z023 = iz.z023;
+  pr.cbrt = iz.cbrt;
+  pr.lfctr = iz.lfctr;
+  pr.inv_km = fdiv(0.001f, pr.m);
+  pr.low = S.lowstop + Z * P.n_zslots;
+  return pr;
 }
 
 MTB_HD void
 stack_store(StackEntry * dst, const Lane & L)
 {
+#if MTB_DEVICE_CODE
+  // four 16-byte stores straight from registers (no local-memory staging)
+  uint4 * d = reinterpret_cast<uint4 *>(dst);
+  const unsigned long long x = (unsigned long long)__double_as_longlong(L.px), y = (unsigned long long)__double_as_longlong(L.py),
+                           z = (unsigned long long)__double_as_longlong(L.pz), e = (unsigned long long)__double_as_longlong(L.E);
+  d[0] = make_uint4((uint32_t)x, (uint32_t)(x >> 32), (uint32_t)y, (uint32_t)(y >> 32));
+  d[1] = make_uint4((uint32_t)z, (uint32_t)(z >> 32), (uint32_t)e, (uint32_t)(e >> 32));
+  d[2] = make_uint4(__float_as_uint(L.dx), __float_as_uint(L.dy), __float_as_uint(L.dz), L.ic);
+  d[3] = make_uint4((uint32_t)L.uid, (uint32_t)(L.uid >> 32), L.packed, (uint32_t)L.tag);
+#else
   StackEntry e;
   e.pos[0] = L.px;
   e.pos[1] = L.py;
@@ -269,14 +350,6 @@ stack_store(StackEntry * dst, const Lane & L)
   e.uid = L.uid;
   e.packed = L.packed;
   e.tag = L.tag;
-#if MTB_DEVICE_CODE
-  const uint4 * s = reinterpret_cast<const uint4 *>(&e);
-  uint4 * d = reinterpret_cast<uint4 *>(dst);
-  d[0] = s[0];
-  d[1] = s[1];
-  d[2] = s[2];
-  d[3] = s[3];
-#else
   *dst = e;
 #endif
 }
@@ -284,17 +357,22 @@ stack_store(StackEntry * dst, const Lane & L)
 MTB_HD void
 stack_load(const StackEntry * src, Lane & L)
 {
-  StackEntry e;
 #if MTB_DEVICE_CODE
   const uint4 * s = reinterpret_cast<const uint4 *>(src);
-  uint4 * d = reinterpret_cast<uint4 *>(&e);
-  d[0] = s[0];
-  d[1] = s[1];
-  d[2] = s[2];
-  d[3] = s[3];
+  const uint4 a = s[0], b = s[1], c = s[2], d = s[3];
+  L.px = __longlong_as_double((long long)(((unsigned long long)a.y << 32) | a.x));
+  L.py = __longlong_as_double((long long)(((unsigned long long)a.w << 32) | a.z));
+  L.pz = __longlong_as_double((long long)(((unsigned long long)b.y << 32) | b.x));
+  L.E = __longlong_as_double((long long)(((unsigned long long)b.w << 32) | b.z));
+  L.dx = __uint_as_float(c.x);
+  L.dy = __uint_as_float(c.y);
+  L.dz = __uint_as_float(c.z);
+  L.ic = c.w;
+  L.uid = ((uint64_t)d.y << 32) | d.x;
+  L.packed = d.z;
+  L.tag = (int32_t)d.w;
 #else
-  e = *src;
-#endif
+  const StackEntry e = *src;
   L.px = e.pos[0];
   L.py = e.pos[1];
   L.pz = e.pos[2];
@@ -306,12 +384,14 @@ stack_load(const StackEntry * src, Lane & L)
   L.uid = e.uid;
   L.packed = e.packed;
   L.tag = e.tag;
+#endif
 }
 
+template <class TR>
 MTB_HD void
 log_birth(const LaunchParams & P, const Lane & L)
 {
-  if (!(P.tally_mask & MTB_TALLY_IONLOG))
+  if (!tally_on<TR>(P, MTB_TALLY_IONLOG))
     return;
   if (P.ionlog_z && L.proj.Z != P.ionlog_z)
     return;
@@ -334,6 +414,7 @@ log_birth(const LaunchParams & P, const Lane & L)
 }
 
 // an ion has stopped (or left the sample): primary record + death half of the ion log
+template <class TR>
 MTB_HD void
 finish_ion(const LaunchParams & P, const Lane & L, int state)
 {
@@ -347,7 +428,7 @@ finish_ion(const LaunchParams & P, const Lane & L, int state)
     r.state = state;
     r.primary_steps = L.ic;
   }
-  if (P.tally_mask & MTB_TALLY_IONLOG)
+  if (tally_on<TR>(P, MTB_TALLY_IONLOG))
   {
     if (P.ionlog_z && L.proj.Z != P.ionlog_z)
       return;
@@ -387,10 +468,17 @@ depth_tally(const LaunchParams & P, const BlockCtx & S, unsigned int * smem_hist
 }
 
 // vacancyCreation() of the in-tree subclasses
+template <class TR>
 MTB_HD void
 vacancy_creation(const LaunchParams & P, const BlockCtx & S, Lane & L, const DevMaterial & M,
                  const DevElement & el, double rx, double ry, float Erec, int rec_gen)
 {
+  if (!TR::kGeneric)
+  {
+    L.casVac++;
+    depth_tally(P, S, S.hist_vac, off_vac(P), (int)rx);
+    return;
+  }
   switch (P.vacancy_model)
   {
     case MTB_VAC_COUNT: // trim.C:439-443
@@ -471,6 +559,7 @@ close_cascade(const LaunchParams & P, const BlockCtx & S, Lane & L)
   MTB_ATOMIC_ADD(&S.blk_u64[CNT_REPL], (unsigned long long)L.casRepl);
   MTB_ATOMIC_ADD(&S.blk_u64[CNT_STEPS], (unsigned long long)L.casSteps);
   MTB_ATOMIC_ADD(&S.blk_u64[CNT_IONS], (unsigned long long)L.casIons);
+  MTB_ATOMIC_ADD(&S.blk_u64[CNT_QUEUED], (unsigned long long)(L.casIons - 1u));
   MTB_ATOMIC_ADD(&S.blk_u64[CNT_PRIMARIES], 1ull);
   MTB_ATOMIC_ADD(&S.blk_f64[0], L.casEel);
   MTB_ATOMIC_ADD(&S.blk_f64[1], L.casEnuc);
@@ -480,10 +569,12 @@ close_cascade(const LaunchParams & P, const BlockCtx & S, Lane & L)
 // the lane loop.  EVENTS=true is the single-ion mode behind mtb_trim_one: one ion, recoils are
 // never followed, every collision is reported.
 // ---------------------------------------------------------------------------------------------
-template <bool EVENTS>
+template <class TR>
 MTB_HD void
 lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
 {
+  constexpr bool EVENTS = TR::kEvents;
+  const int potential = TR::kGeneric ? P.potential : (int)MTB_POT_UNIVERSAL;
   Lane L;
   StackEntry * const stack = EVENTS ? nullptr : P.stacks + (size_t)lane_global * MTB_STACK_DEPTH;
   int sp = 0, sp_max = 0;
@@ -502,7 +593,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       {
         --sp;
         stack_load(stack + sp, L);
-        set_projectile(L, S);
+        set_projectile(P, L, S);
       }
       else
       {
@@ -543,9 +634,9 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
         L.casVac = L.casRepl = L.casSteps = 0;
         L.casIons = 1;
         open = true;
-        set_projectile(L, S);
+        set_projectile(P, L, S);
         if (!EVENTS)
-          log_birth(P, L);
+          log_birth<TR>(P, L);
       }
       active = true;
     }
@@ -554,7 +645,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     if (!(L.E > 0.0))
     {
       // the reference would produce NaNs for a projectile without energy; park it instead
-      finish_ion(P, L, MTB_INTERSTITIAL);
+      finish_ion<TR>(P, L, MTB_INTERSTITIAL);
       active = false;
       if (EVENTS)
         break;
@@ -562,20 +653,20 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     }
     ++L.ic;
     int cluster;
-    const int mi = lookup_material(P, S, L.px, L.py, L.pz, &cluster);
+    const int mi = lookup_material<TR>(P, S, L.px, L.py, L.pz, &cluster);
     if (mi < 0)
     {
       // vacuum: the reference breaks out with the state still MOVING (trim.C:80-82)
       MTB_ATOMIC_ADD(&S.blk_u64[CNT_LEFT], 1ull);
       --L.ic;
-      finish_ion(P, L, MTB_MOVING);
+      finish_ion<TR>(P, L, MTB_MOVING);
       active = false;
       if (EVENTS)
         break;
       continue;
     }
     const DevMaterial & M = S.materials[mi];
-    const int mtag = (P.geom_kind == MTB_GEOM_CLUSTERS && mi == 1) ? cluster : M.tag;
+    const int mtag = (TR::kGeneric && P.geom_kind == MTB_GEOM_CLUSTERS && mi == 1) ? cluster : M.tag;
     L.casSteps++;
 
     // v_norm(dir) — trim.C:85
@@ -626,7 +717,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     const float see = material_stopping(L.proj, M, S.elements, E0); // trim.C:166
     const float dee_f = ls * see;
 
-    const Scatter sc = magic_scatter(P.potential, eps, b);
+    const Scatter sc = magic_scatter(potential, eps, b);
 
     // energy bookkeeping in FP64 — trim.C:275-296
     double dee = (double)dee_f;
@@ -686,9 +777,10 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
 
     // CUT boundaries — trim.C:344-352
     int state = MTB_MOVING;
-    if ((P.bc[0] == MTB_BC_CUT && (L.px > P.w[0] || L.px < 0.0)) ||
+    if (TR::kGeneric &&
+        ((P.bc[0] == MTB_BC_CUT && (L.px > P.w[0] || L.px < 0.0)) ||
         (P.bc[1] == MTB_BC_CUT && (L.py > P.w[1] || L.py < 0.0)) ||
-        (P.bc[2] == MTB_BC_CUT && (L.pz > P.w[2] || L.pz < 0.0)))
+        (P.bc[2] == MTB_BC_CUT && (L.pz > P.w[2] || L.pz < 0.0))))
     {
       state = MTB_LOST;
       MTB_ATOMIC_ADD(&S.blk_u64[CNT_LOST], 1ull);
@@ -703,23 +795,23 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       if (Erec > el.Edisp - el.Elbind)
       {
         above = true;
-        if (P.tally_mask & MTB_TALLY_PHONON)
+        if (tally_on<TR>(P, MTB_TALLY_PHONON))
           L.casEnuc += (double)el.Elbind; // TrimPhononOut::followRecoil
-        follow = !EVENTS && (P.follow == MTB_FOLLOW_ALL ||
+        follow = !EVENTS && (!TR::kGeneric || P.follow == MTB_FOLLOW_ALL ||
                              (P.follow == MTB_FOLLOW_GEN_LT && rec_gen < P.follow_max_gen));
         if (L.E > (double)el.Edisp)
-          vacancy_creation(P, S, L, M, el, rx, ry, Erec, rec_gen);
+          vacancy_creation<TR>(P, S, L, M, el, rx, ry, Erec, rec_gen);
         else
         {
           L.casRepl++;
-          if (P.tally_mask & MTB_TALLY_VAC_DEPTH)
+          if (tally_on<TR>(P, MTB_TALLY_VAC_DEPTH))
             depth_tally(P, S, S.hist_repl, off_repl(P), (int)rx);
           state = (L.proj.Z == el.Z) ? MTB_REPLACEMENT : MTB_SUBSTITUTIONAL;
         }
       }
       else
       {
-        if (P.tally_mask & MTB_TALLY_RANGE) // TrimRange::dissipateRecoilEnergy
+        if (tally_on<TR>(P, MTB_TALLY_RANGE)) // TrimRange::dissipateRecoilEnergy
         {
           const unsigned long long i = MTB_ATOMIC_ADD(&P.u64[CNT_RANGE_N], 1ull);
           if (i < P.range_cap)
@@ -728,13 +820,13 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
             P.range[i].Z = el.Z;
           }
         }
-        if (P.tally_mask & MTB_TALLY_PHONON)
+        if (tally_on<TR>(P, MTB_TALLY_PHONON))
           L.casEnuc += den; // recoil.E + Elbind — TrimPhononOut::dissipateRecoilEnergy
         if (L.E < (double)L.Ef)
           state = MTB_INTERSTITIAL;
       }
       // TrimPhononOut::checkPKAState — trim.C:503-511
-      if ((P.tally_mask & MTB_TALLY_PHONON) && state != MTB_MOVING)
+      if (tally_on<TR>(P, MTB_TALLY_PHONON) && state != MTB_MOVING)
         L.casEnuc += L.E;
     }
 
@@ -765,7 +857,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       ++n_events;
       if (state != MTB_MOVING)
       {
-        finish_ion(P, L, state);
+        finish_ion<TR>(P, L, state);
         break;
       }
       continue;
@@ -775,7 +867,6 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     if (follow)
     {
       L.casIons++;
-      MTB_ATOMIC_ADD(&S.blk_u64[CNT_QUEUED], 1ull);
       const float qs = frsqrt(qx * qx + qy * qy + qz * qz);
       const uint64_t ruid = child_uid(L.uid, L.ic);
       const uint32_t rpacked = (uint32_t)(SPECIES_ELEMENT0 + M.first_elem + nn) | ((uint32_t)rec_gen << GEN_SHIFT);
@@ -789,7 +880,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           MTB_ATOMIC_ADD(&P.u64[CNT_ERROR], 1ull);
       }
       if (state != MTB_MOVING)
-        finish_ion(P, L, state);
+        finish_ion<TR>(P, L, state);
       if (keep_projectile)
       {
         // suspend the recoil instead
@@ -801,11 +892,11 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
         R.uid = ruid;
         R.packed = rpacked;
         R.tag = mtag;
-        if (P.tally_mask & MTB_TALLY_IONLOG)
+        if (tally_on<TR>(P, MTB_TALLY_IONLOG))
         {
           R.prim = L.prim;
           R.proj.Z = el.Z;
-          log_birth(P, R);
+          log_birth<TR>(P, R);
         }
         if (sp < MTB_STACK_DEPTH)
           stack_store(stack + sp++, R);
@@ -821,15 +912,15 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
         L.uid = ruid;
         L.packed = rpacked;
         L.tag = mtag;
-        set_projectile(L, S);
-        log_birth(P, L);
+        set_projectile(P, L, S);
+        log_birth<TR>(P, L);
       }
       if (sp > sp_max)
         sp_max = sp;
     }
     else if (state != MTB_MOVING)
     {
-      finish_ion(P, L, state);
+      finish_ion<TR>(P, L, state);
       active = false;
     }
   }

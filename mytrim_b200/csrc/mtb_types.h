@@ -27,7 +27,8 @@ struct DevElement
   float pc[8];  // scoef[Z-1].pcoef[0..7]
   int32_t Z;
   float velpwr; // 0.25 (Z<=6) or 0.45: rpstop low-energy exponent (material.C:151-155)
-  int32_t pad[2];
+  int32_t zslot; // column of this element's Z in the low-velocity stopping table
+  int32_t pad;
 };
 static_assert(sizeof(DevElement) == 80, "DevElement layout");
 
@@ -44,6 +45,19 @@ struct DevMaterial
   int32_t user_index; // index in the caller's material list (before de-duplication)
 };
 static_assert(sizeof(DevMaterial) == 32, "DevMaterial layout");
+
+// Low-velocity heavy-ion stopping of projectile Z1 in target Z2 (one entry per (Z1, distinct Z2)).
+// In the velocity-proportional regime of MaterialBase::rstop (material.C:259-273, yr clamped at
+// yrmin) everything except (e/eee)^power depends on (Z1, Z2) only:
+//     rstop = coef * e^power        for Z1 >= 3 and e = E/(1000 m1) <= e_max  [keV/amu]
+// coef is evaluated on the host in double precision.
+struct LowStop
+{
+  float coef;  // 10 * rpstop(Z2, eee) * (zeta * Z1)^2 / eee^power
+  float e_max; // min(e at which yr leaves the clamp, 20 keV/amu); 0 disables the shortcut
+  float power; // 0.5 or 0.375
+  float pad;
+};
 
 // Per projectile-Z constants (indexed by Z, entry 0 unused).
 struct DevIonZ
@@ -120,6 +134,8 @@ struct LaunchParams
   const DevElement * elements;
   const DevMaterial * materials;
   const DevIonZ * ionz; // [93]
+  const LowStop * lowstop; // [93][n_zslots]
+  int32_t n_zslots;
   int32_t n_elements, n_materials;
   // geometry
   int32_t geom_kind;

@@ -32,6 +32,7 @@ struct hs_engine
   std::vector<mtb_ion_log> ionlog;
   std::vector<RangeEntry> range;
   std::string err;
+  bool force_generic = false;
 };
 
 static int
@@ -45,6 +46,7 @@ hs_prepare(hs_engine * e)
   P.elements = e->T.elements.data();
   P.materials = e->T.materials.data();
   P.ionz = e->T.ionz.data();
+  P.lowstop = e->T.lowstop.data();
   P.layer_cum = e->T.layer_cum.data();
   P.layer_mat = e->T.layer_mat.data();
   P.cl_hash = e->T.cl_hash.data();
@@ -72,6 +74,7 @@ hs_ctx(hs_engine * e)
   S.elements = e->P.elements;
   S.materials = e->P.materials;
   S.ionz = e->P.ionz;
+  S.lowstop = e->P.lowstop;
   S.layer_cum = e->P.layer_cum;
   S.layer_mat = e->P.layer_mat;
   S.hist_vac = e->hist.data();
@@ -166,9 +169,18 @@ hs_run(hs_engine * e, uint64_t n, const mtb_ion * primaries, uint64_t seed, uint
   P.records = records;
   P.u64[CNT_NEXT_PRIMARY] = 0;
   const BlockCtx S = hs_ctx(e);
-  lane_loop<false>(P, S, 0);
+  if (fast_path_ok(P) && !e->force_generic)
+    lane_loop<TraitsFast>(P, S, 0);
+  else
+    lane_loop<TraitsGeneric>(P, S, 0);
   hs_flush(e);
   return P.u64[CNT_ERROR] ? MTB_ESTACK : MTB_OK;
+}
+
+void
+hs_force_generic(hs_engine * e, int on)
+{
+  e->force_generic = on != 0;
 }
 
 int
@@ -303,7 +315,7 @@ hs_trim_one(hs_engine * e, mtb_ion * ion, uint64_t seed, uint64_t uid, int32_t *
   P.tally_mask = 0;
   P.u64[CNT_EVENTS_N] = 0;
   const BlockCtx S = hs_ctx(e);
-  lane_loop<true>(P, S, 0);
+  lane_loop<TraitsEvents>(P, S, 0);
   const size_t cnt = (size_t)P.u64[CNT_EVENTS_N];
   if (n_events)
     *n_events = cnt;
@@ -328,16 +340,10 @@ hs_stopping(hs_engine * e, int material, size_t n, const int32_t * Z1, const dou
 {
   if (int rc = hs_prepare(e))
     return rc;
+  const BlockCtx S = hs_ctx(e);
   for (size_t i = 0; i < n; ++i)
   {
-    Projectile pr;
-    const DevIonZ & iz = e->P.ionz[Z1[i]];
-    pr.Z = Z1[i];
-    pr.fz = (float)Z1[i];
-    pr.m = m1[i] == 0.0 ? iz.mm1 : (float)m1[i];
-    pr.z023 = iz.z023;
-    pr.cbrt = iz.cbrt;
-    pr.lfctr = iz.lfctr;
+    const Projectile pr = make_projectile(e->P, S, Z1[i], (float)m1[i]);
     out[i] = (double)material_stopping(pr, e->P.materials[material], e->P.elements, (float)E[i]);
   }
   return MTB_OK;
