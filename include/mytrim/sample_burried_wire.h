@@ -1,0 +1,6 @@
+// sample_burried_wire.h — kept so that sources written against the reference's header layout compile unchanged;
+// the whole plugin surface lives in mytrim.h.
+#ifndef MYTRIM_B200_FWD_SAMPLE_BURRIED_WIRE_H
+#define MYTRIM_B200_FWD_SAMPLE_BURRIED_WIRE_H
+#include "mytrim.h"
+#endif

@@ -1,0 +1,6 @@
+// sample_clusters.h — kept so that sources written against the reference's header layout compile unchanged;
+// the whole plugin surface lives in mytrim.h.
+#ifndef MYTRIM_B200_FWD_SAMPLE_CLUSTERS_H
+#define MYTRIM_B200_FWD_SAMPLE_CLUSTERS_H
+#include "mytrim.h"
+#endif

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <sstream>
+#include <typeinfo>
 
 #include "mtb_tables.h"
 
@@ -749,9 +750,10 @@ TrimBase::vacancyCreation()
 void
 TrimBase::deviceHooks(DeviceHooks & h) const
 {
-  // Plain TrimBase is known.  A subclass that inherits this implementation but overrides hooks
-  // is caught in ensureEngine() by comparing typeid with the in-tree classes.
-  h.known = true;
+  // Only plain TrimBase is known here.  A subclass that inherits this implementation (TrimHistory,
+  // TrimDefectLog, any user class) has hooks the device cannot see: it must override deviceHooks()
+  // or use trim() per ion.
+  h.known = typeid(*this) == typeid(TrimBase);
 }
 
 mtb_handle *

@@ -1,0 +1,128 @@
+// facade_check.cpp — exercises the C++ plugin surface (include/mytrim) the way reference apps do;
+// prints one JSON object that tests/test_gpu_facade.py compares with the oracle.  GPU only.
+#include <cstdio>
+#include <queue>
+#include <vector>
+
+#include "mytrim/simconf.h"
+#include "mytrim/sample_layers.h"
+#include "mytrim/sample_solid.h"
+#include "mytrim/trim.h"
+#include "mytrim/include/TrimVacCount.h"
+
+using namespace MyTRIM_NS;
+
+// a user-defined Trim subclass with host-only hooks, as in the reference's documentation
+class CountingTrim : public TrimBase
+{
+public:
+  CountingTrim(SimconfType * s, SampleBase * b) : TrimBase(s, b), vac(0), repl(0), sub(0), followed(0), steps(0) {}
+  long vac, repl, sub, followed, steps;
+  double recoil_energy_sum = 0.0;
+
+protected:
+  virtual bool followRecoil()
+  {
+    ++followed;
+    recoil_energy_sum += _recoil->_E;
+    return true;
+  }
+  virtual void vacancyCreation()
+  {
+    ++vac;
+    _simconf->vacancies_created++;
+  }
+  virtual void replacementCollision() { ++repl; }
+  virtual void dissipateRecoilEnergy() { ++sub; }
+  virtual void checkPKAState() { ++steps; }
+};
+
+static MaterialBase *
+copper(SimconfType * sc)
+{
+  MaterialBase * m = new MaterialBase(sc, 8.92);
+  Element e;
+  e._Z = 29;
+  e._m = 63.546;
+  e._t = 1.0;
+  m->_element.push_back(e);
+  m->prepare();
+  return m;
+}
+
+int
+main()
+{
+  // --- 1. batched cascades with an in-tree tally class (what runmytrim does) ---
+  SimconfType sc;
+  sc.seed(2344);
+  SampleLayers sample(1000.0, 100.0, 100.0);
+  sample.material.push_back(copper(&sc));
+  sample.layerThickness.push_back(1000.0);
+  TrimVacCount trim(&sc, &sample);
+  const int n = 2000;
+  std::vector<IonBase *> prim;
+  for (int i = 0; i < n; ++i)
+  {
+    IonBase * p = new IonBase(29, 63.546, 1.0e4);
+    p->_gen = 0;
+    p->_dir = Point(1, 0, 0);
+    p->_pos = Point(0, 50, 50);
+    prim.push_back(p);
+  }
+  std::vector<mtb_record> rec;
+  if (!trim.trimBatch(prim, &rec))
+  {
+    std::fprintf(stderr, "trimBatch failed: %s\n", trim.lastError().c_str());
+    return 1;
+  }
+  unsigned long hist_vac = 0, hist_repl = 0;
+  for (unsigned v : trim.vacancies())
+    hist_vac += v;
+  for (unsigned v : trim.replacements())
+    hist_repl += v;
+  double xsum = 0;
+  for (auto * p : prim)
+    xsum += p->_pos(0);
+  std::printf("{\"batch\": {\"n\": %d, \"vacancies\": %d, \"Eel\": %.10g, \"hist_vac\": %lu, \"hist_repl\": %lu, "
+              "\"mean_x\": %.10g, \"bins\": %zu, \"rec0_vac\": %u, \"rec0_x\": %.10g},\n",
+              n, sc.vacancies_created, sc.EelTotal, hist_vac, hist_repl, xsum / n, trim.vacancies().size(),
+              rec[0].vacancies, rec[0].pos[0]);
+
+  // --- 2. the reference's per-ion loop with a user subclass: trim() + host hooks ---
+  SimconfType sc2;
+  sc2.seed(77);
+  SampleSolid solid(1000.0, 100.0, 100.0);
+  solid.material.push_back(copper(&sc2));
+  CountingTrim ct(&sc2, &solid);
+  const int n2 = 60;
+  std::queue<IonBase *> recoils;
+  long ions = 0;
+  double primary_x = 0;
+  for (int i = 0; i < n2; ++i)
+  {
+    IonBase * pka = new IonBase(29, 63.546, 1.0e4);
+    pka->_gen = 0;
+    pka->_dir = Point(1, 0, 0);
+    pka->_pos = Point(0, 50, 50);
+    recoils.push(pka);
+    bool first = true;
+    while (!recoils.empty())
+    {
+      IonBase * ion = recoils.front();
+      recoils.pop();
+      solid.averages(ion);
+      ct.trim(ion, recoils);
+      ++ions;
+      if (first)
+        primary_x += ion->_pos(0);
+      first = false;
+      delete ion;
+    }
+  }
+  std::printf(" \"single\": {\"n\": %d, \"vac\": %ld, \"repl\": %ld, \"sub\": %ld, \"followed\": %ld, \"steps\": %ld, "
+              "\"ions\": %ld, \"Eel\": %.10g, \"simconf_vac\": %d, \"mean_x\": %.10g, \"mean_recoil_E\": %.10g}}\n",
+              n2, ct.vac, ct.repl, ct.sub, ct.followed, ct.steps, ions, sc2.EelTotal, sc2.vacancies_created,
+              primary_x / n2, ct.recoil_energy_sum / ct.followed);
+  return 0;
+}
