@@ -144,7 +144,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--primaries", type=int, default=1 << 20, help="cascades per GPU per step")
+    ap.add_argument("--primaries", type=int, default=1 << 22, help="cascades per GPU per step")
     ap.add_argument("--ref-cascades", type=int, default=0, help="cascades per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -191,25 +191,16 @@ def main():
         torch.cuda.synchronize()
 
     # tallies as torch tensors over the engine's device memory (for the NCCL reduction)
-    pu, nu, pf, nf = eng.tally_device_views()
-
-    class _Raw:
-        def __init__(self, ptr, n, typestr):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
-
-    t_u64 = torch.as_tensor(_Raw(pu, nu, "<i8"), device="cuda")
-    t_f64 = torch.as_tensor(_Raw(pf, nf, "<f8"), device="cuda")
-    n_counters_reduced = 10  # mtb_counters u64 fields; the work counter / list cursors are per-GPU
+    from mytrim_b200 import dist as mdist
+    t_u64, t_f64 = mdist.tally_tensors(eng)
 
     def reduce_tallies():
-        """Only the additive tallies cross NVLink: one all-reduce over [counters | histograms], one over f64."""
+        """Only the additive tallies cross NVLink (mytrim_b200/dist.py): the analogue of threadJoin."""
         if world == 1:
             return 0.0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        dist.all_reduce(t_u64[:n_counters_reduced - 1])
-        dist.all_reduce(t_u64[16:])
-        dist.all_reduce(t_f64)
+        mdist.reduce_tallies(t_u64, t_f64)
         e1.record()
         e1.synchronize()
         return e0.elapsed_time(e1)
@@ -259,8 +250,8 @@ def main():
     value = cascades / (job_ms * 1e-3)
 
     # ---------------- end-to-end arm: host buffers through mtb_run ----------------
-    vac_host = np.zeros(1 << 12, dtype=np.uint64)
-    repl_host = np.zeros(1 << 12, dtype=np.uint64)
+    vac_host = np.zeros(1 << 14, dtype=np.uint64)
+    repl_host = np.zeros(1 << 14, dtype=np.uint64)
     nb = ctypes.c_size_t()
     cnt = capi.Counters()
     lib = capi.load_library()
@@ -286,8 +277,7 @@ def main():
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = cascades / float(t_e[0])
-    hist_bins = eng.tally_device_views()[1]
-    d2h = ctypes.sizeof(capi.Counters) + 2 * 8 * ((hist_bins - 16 - 1200) // 2)
+    d2h = ctypes.sizeof(capi.Counters) + vac_host.nbytes + repl_host.nbytes
 
     if rank != 0:
         if world > 1:

@@ -101,7 +101,8 @@ typedef struct {
   uint32_t tally_mask;
   int32_t vmap_z[3];    /* TrimVacMap z1,z2,z3 */
   int32_t ionlog_z;     /* log only ions with this Z; 0 = all */
-  int32_t hist_bins;    /* depth bins kept for VAC_DEPTH / VAC_ENERGY; 0 = derive from geometry */
+  int32_t hist_bins;    /* depth bins kept for VAC_DEPTH / VAC_ENERGY; 0 = max(16384, 4*extent); deeper
+                           events land in the last bin and are counted in mtb_counters.hist_clamped */
   int32_t evac_rows;    /* ln(E) rows kept for VAC_ENERGY; 0 = 32 */
   int32_t device;       /* CUDA device ordinal */
   uint64_t ionlog_capacity; /* entries; 0 = 1<<20 */

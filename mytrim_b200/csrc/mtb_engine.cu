@@ -7,6 +7,7 @@
 // The host part flattens the caller's configuration into device tables, owns all device
 // buffers, launches, and reads tallies back.  No torch types, no exceptions across the ABI.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -1012,12 +1013,94 @@ mtb_measure_fp32_peak(int device, double * tflops, float * ms_out)
   return MTB_OK;
 }
 
+// Single-process multi-GPU tally reduction (one handle per GPU): ncclAllReduce(sum) over the additive
+// u64 block and the f64 block, ncclAllReduce(max) over the stack high-water mark.  NCCL is loaded
+// with dlopen so the library has no link-time dependency on it; multi-process jobs (one rank per
+// GPU) reduce the same device blocks through torch.distributed instead (mytrim_b200/dist.py).
+namespace
+{
+struct NcclApi
+{
+  void * lib = nullptr;
+  int (*CommInitAll)(void **, int, const int *) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char * (*GetErrorString)(int) = nullptr;
+  bool load()
+  {
+    if (lib)
+      return true;
+    for (const char * name : {"libnccl.so.2", "libnccl.so"})
+      if ((lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL)))
+        break;
+    if (!lib)
+      return false;
+    CommInitAll = (int (*)(void **, int, const int *))dlsym(lib, "ncclCommInitAll");
+    CommDestroy = (int (*)(void *))dlsym(lib, "ncclCommDestroy");
+    AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    GroupStart = (int (*)())dlsym(lib, "ncclGroupStart");
+    GroupEnd = (int (*)())dlsym(lib, "ncclGroupEnd");
+    GetErrorString = (const char * (*)(int))dlsym(lib, "ncclGetErrorString");
+    return CommInitAll && CommDestroy && AllReduce && GroupStart && GroupEnd;
+  }
+};
+NcclApi g_nccl;
+constexpr int kNcclInt64 = 4, kNcclUint64 = 5, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
+} // namespace
+
 int
 mtb_allreduce(mtb_handle ** handles, int n_handles)
 {
-  (void)handles;
-  (void)n_handles;
-  return fail(MTB_ENCCL, "mtb_allreduce: not built in this configuration");
+  if (!handles || n_handles < 1)
+    return fail(MTB_EINVAL, "no handles");
+  if (n_handles == 1)
+    return MTB_OK;
+  for (int i = 0; i < n_handles; ++i)
+  {
+    if (int rc = ensure_ready(handles[i]))
+      return rc;
+    if (handles[i]->u64_size != handles[0]->u64_size)
+      return fail(MTB_EINVAL, "handles have different tally layouts");
+    MTB_CUDA(cudaStreamSynchronize(handles[i]->stream));
+  }
+  if (!g_nccl.load())
+    return fail(MTB_ENCCL, "libnccl.so.2 not found");
+  std::vector<void *> comms(n_handles, nullptr);
+  std::vector<int> devs(n_handles);
+  for (int i = 0; i < n_handles; ++i)
+    devs[i] = handles[i]->device;
+  int rc = g_nccl.CommInitAll(comms.data(), n_handles, devs.data());
+  if (rc != 0)
+    return fail(MTB_ENCCL, std::string("ncclCommInitAll: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+  const size_t nhist = handles[0]->u64_size - CNT_COUNT;
+  rc = g_nccl.GroupStart();
+  for (int i = 0; i < n_handles && rc == 0; ++i)
+  {
+    mtb_handle * h = handles[i];
+    cudaSetDevice(h->device);
+    rc = g_nccl.AllReduce(h->d_u64.p, h->d_u64.p, CNT_STACKMAX, kNcclUint64, kNcclSum, comms[i], h->stream);
+    if (rc == 0)
+      rc = g_nccl.AllReduce(h->d_u64.p + CNT_STACKMAX, h->d_u64.p + CNT_STACKMAX, 1, kNcclUint64, kNcclMax, comms[i], h->stream);
+    if (rc == 0)
+      rc = g_nccl.AllReduce(h->d_u64.p + CNT_COUNT, h->d_u64.p + CNT_COUNT, nhist, kNcclUint64, kNcclSum, comms[i], h->stream);
+    if (rc == 0)
+      rc = g_nccl.AllReduce(h->d_f64.p, h->d_f64.p, 2, kNcclFloat64, kNcclSum, comms[i], h->stream);
+  }
+  const int rc_end = g_nccl.GroupEnd();
+  if (rc == 0)
+    rc = rc_end;
+  for (int i = 0; i < n_handles; ++i)
+  {
+    cudaSetDevice(handles[i]->device);
+    cudaStreamSynchronize(handles[i]->stream);
+    g_nccl.CommDestroy(comms[i]);
+  }
+  if (rc != 0)
+    return fail(MTB_ENCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+  (void)kNcclInt64;
+  return MTB_OK;
 }
 
 } // extern "C"

@@ -386,7 +386,7 @@ build_host_tables(const HostConfig & H, HostTables & T, LaunchParams & P, std::s
   // tally sizes
   int bins = c.hist_bins;
   if (bins <= 0)
-    bins = (int)std::min<double>(std::max(1024.0, std::ceil(extent) + 1.0), 1 << 20);
+    bins = (int)std::min<double>(std::max(16384.0, 4.0 * std::ceil(extent) + 1.0), 1 << 20);
   P.hist_bins = bins;
   P.evac_rows = c.evac_rows > 0 ? c.evac_rows : 32;
   P.smem_hist_bins = (c.tally_mask & MTB_TALLY_VAC_DEPTH) ? std::min(bins, kSmemHistMax) : 0;

@@ -35,7 +35,9 @@ def test_facade_batch_and_user_subclass():
         vac, repl = orc.vac_depth()
     assert abs(b["vacancies"] - cnt["vacancies_created"]) <= 0.002 * cnt["vacancies_created"]
     assert abs(b["Eel"] - cnt["EelTotal"]) <= 1e-3 * cnt["EelTotal"]
-    assert b["hist_vac"] == b["vacancies"] and abs(b["hist_repl"] - repl.sum()) <= 0.002 * repl.sum()
+    # vacancies with int(x) < 0 are counted but not histogrammed (TrimVacCount.C:36-38)
+    assert b["hist_vac"] <= b["vacancies"] and abs(b["hist_vac"] - vac.sum()) <= 0.002 * vac.sum()
+    assert abs(b["hist_repl"] - repl.sum()) <= 0.002 * repl.sum()
     assert abs(b["mean_x"] - rec["pos"][:, 0].mean()) < 1e-3 * rec["pos"][:, 0].mean()
     assert b["rec0_vac"] == rec["vacancies"][0] and abs(b["rec0_x"] - rec["pos"][0, 0]) < 1e-4
     # 2. per-ion trim() with host hooks: statistically the same physics (different stream ids)

@@ -48,7 +48,7 @@ def test_trajectories_match_oracle(name, n):
         assert abs(cg[k] - co[k]) <= 0.02 * co[k], k
     vg, rpg = eng.vac_depth()
     vo, rpo = orc.vac_depth()
-    assert vg.sum() == cg["vacancies_created"] - cg["hist_clamped"] or vg.sum() <= cg["vacancies_created"]
+    assert cg["hist_clamped"] == 0 and vg.sum() <= cg["vacancies_created"]
     m = max(len(vg), len(vo))
     d = np.abs(np.pad(vg, (0, m - len(vg))).astype(int) - np.pad(vo, (0, m - len(vo))).astype(int)).sum()
     # cascades that took a different branch somewhere are statistically equivalent but place their
@@ -194,3 +194,31 @@ def test_statistics_against_reference_golden(name):
                           ("lateral", lambda r: np.hypot(r["pos"][:, 1] - 50.0, r["pos"][:, 2] - 50.0))):
         p = stats.ks_2samp(getter(rec), getter(gold)).pvalue
         assert p > 0.001, (name, field, p)
+
+
+def test_multi_gpu_allreduce_in_process():
+    """mtb_allreduce: two handles on two GPUs, primaries sharded by global index, NCCL tally reduction
+    equals one GPU running everything (needs >= 2 GPUs)."""
+    import ctypes as C
+    lib = capi.load_library()
+    if lib.mtb_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cfg = dict(tally_mask=capi.TALLY_VAC_DEPTH)
+    c = util.CONFIGS["cu_on_cu_10keV"]
+    n = 20000
+    ions = util.primaries_for(c, n)
+    with capi.Engine(device=0, **cfg) as one, capi.Engine(device=0, **cfg) as a, capi.Engine(device=1, **cfg) as b:
+        for e in (one, a, b):
+            util.setup_engine(e, c)
+        one.run(ions, seed=5)
+        a.run(ions[:n // 2], seed=5, first_index=0)
+        b.run(ions[n // 2:], seed=5, first_index=n // 2)
+        arr = (C.c_void_p * 2)(a._h, b._h)
+        lib.mtb_allreduce.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        assert lib.mtb_allreduce(arr, 2) == 0, lib.mtb_last_error()
+        c1, ca, cb = one.counters(), a.counters(), b.counters()
+        for k in ("vacancies_created", "replacements", "steps", "ions", "primaries"):
+            assert c1[k] == ca[k] == cb[k], k
+        assert abs(c1["EelTotal"] - ca["EelTotal"]) <= 1e-9 * c1["EelTotal"]
+        assert np.array_equal(one.vac_depth()[0], a.vac_depth()[0])
+        assert np.array_equal(one.vac_depth()[1], b.vac_depth()[1])
