@@ -65,3 +65,16 @@ def test_product_does_not_reference_oracle():
                         or "liboracle" in text or "hostsim" in text.replace("tests/hostsim.cpp", ""):
                     bad.append(os.path.join(d, f))
     assert not bad, bad
+
+
+def test_unmodified_reference_apps_compile_against_facade():
+    """Every reference driver that does not need jsoncpp compiles, unmodified, against include/mytrim
+    and links with libmytrim_b200.so (built by oracle/Makefile `facade_apps`; build container only)."""
+    import pytest
+    if not os.path.exists("/root/reference/trim.C"):
+        pytest.skip("reference tree not mounted")
+    apps = os.path.join(ROOT, "oracle", "_ref", "facade_apps")
+    want = ["mytrim_layers", "mytrim_uo2", "mytrim_solid", "mytrim_solid2", "mytrim_wire", "mytrim_wire2",
+            "mytrim_clusters", "mytrim_ODS", "mytrim_bobmsq", "mytrim_distance", "mytrim_moose_verification"]
+    for a in want:
+        assert os.path.exists(os.path.join(apps, a)), a

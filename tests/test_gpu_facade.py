@@ -114,3 +114,25 @@ def test_mytrim_layers_zro2(tmp_path):
     assert abs(nrec - len(rec)) <= 0.01 * len(rec)
     assert abs(sum_r2 - r2) <= 0.02 * r2
     assert 120 < nrec / 300 < 180
+
+
+def test_unmodified_reference_uo2_app_through_facade(tmp_path):
+    """The reference's own apps/mytrim_uo2.C, compiled unmodified against the façade (oracle/_ref/
+    facade_apps), run on the GPU through TrimBase::trim() + host hook replay.  Different random numbers
+    than the gold run, so the check is physics: cluster placement (host mt19937) is byte-identical to the
+    gold file, electronic losses are ~95 % of the fission energy as in the reference's run."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "facade_apps", "mytrim_uo2")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/facade_apps not built (reference tree was absent at build time)")
+    env = dict(os.environ, MYTRIM_SEED="39172")
+    out = subprocess.run([exe, "out", "10", "0.1", "1"], cwd=str(tmp_path), capture_output=True, text=True,
+                         timeout=900, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert open(tmp_path / "out.clcoor").read() == open(os.path.join(util.GOLDEN, "uo2_out.clcoor")).read()
+    lines = out.stdout.strip().split("\n")
+    eel, enuc, balance = float(lines[-3]), float(lines[-2]), float(lines[-1])
+    efiss = eel + enuc + balance
+    assert 1.7e8 < efiss < 2.0e8
+    assert 0.93 < eel / efiss < 0.98        # reference gold run: 1.75837e8 / 1.83473e8 = 0.958
+    nrec = len(open(tmp_path / "out.Erec").read().strip().split("\n"))
+    assert 0 <= nrec < 400                   # Xe recoils knocked out of the four bubbles (gold run: 21)
