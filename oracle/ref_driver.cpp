@@ -161,6 +161,9 @@ makeTrim(const Job & job, SimconfType * sc, SampleBase * sample, Probe *& probe)
   }
   if (job.tally == "phonon")
   {
+    // TrimPhononOut formats one text line per collision; a stream in the failed state makes every
+    // operator<< return at its sentry, so only the EnucTotal bookkeeping remains
+    null_stream.setstate(std::ios::badbit);
     auto * t = new Recording<TrimPhononOut>(sc, sample, std::ref(null_stream));
     probe = &t->probe;
     return t;

@@ -145,7 +145,7 @@ def reference_script(ion, materials, thicknesses, n=0, tally="vaccount", threads
     return lines
 
 
-def run_reference_cascades(ion, materials, thicknesses, seeds, tally="vaccount", threads=1, **kw):
+def run_reference_cascades(ion, materials, thicknesses, seeds, tally="vaccount", threads=1, timeout=600, **kw):
     """Runs the unmodified reference for the given per-primary seeds; returns (records, summary dict)."""
     seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
     with tempfile.TemporaryDirectory() as tmp:
@@ -155,7 +155,7 @@ def run_reference_cascades(ion, materials, thicknesses, seeds, tally="vaccount",
         lines = reference_script(ion, materials, thicknesses, n=len(seeds), tally=tally, threads=threads,
                                  seeds_file=sf, out=out, **kw)
         lines.append("run")
-        stdout = run_reference("\n".join(lines) + "\n")
+        stdout = run_reference("\n".join(lines) + "\n", timeout=timeout)
         rec = np.fromfile(out + ".records", dtype=capi.RECORD_DTYPE)
         hist = None
         if os.path.exists(out + "_vac.dat"):

@@ -32,7 +32,7 @@ n = args.n
 cores = os.cpu_count() or 1
 t0 = time.time()
 ref, summary, _ = util.run_reference_cascades(c["ion"], c["materials"], c["thicknesses"], util.distinct_seeds(n),
-                                              tally="phonon", threads=cores, box=c.get("box"))
+                                              tally="phonon", threads=cores, box=c.get("box"), timeout=2400)
 t_ref = time.time() - t0
 
 runs = {}
