@@ -107,7 +107,7 @@ def load_library():
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
-        _lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        _lib = C.CDLL(LIB_PATH)  # RTLD_LOCAL: its C++ symbols must not interpose other libraries
         declare(_lib, "mtb_")
         _lib.mtb_version.restype = C.c_char_p
         _lib.mtb_last_error.restype = C.c_char_p

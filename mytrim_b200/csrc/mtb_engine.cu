@@ -56,7 +56,7 @@ constexpr int kMinBlocks = MTB_MIN_BLOCKS;
 // ---------------------------------------------------------------------------------------------
 struct SmemLayout
 {
-  size_t elements, materials, ionz, lowstop, layer_cum, layer_mat, hist_vac, hist_repl, blk_u64, blk_f64, total;
+  size_t elements, materials, ionz, lowstop, pclass, pairm, paire, layer_cum, layer_mat, hist_vac, hist_repl, blk_u64, blk_f64, total;
 };
 
 __host__ __device__ inline size_t
@@ -84,6 +84,12 @@ smem_layout(const LaunchParams & P)
   o += (MTB_NZ + 1) * sizeof(DevIonZ);
   L.lowstop = o;
   o += (size_t)(MTB_NZ + 1) * (size_t)P.n_zslots * sizeof(LowStop);
+  L.pclass = o = align_up(o, 16);
+  o += (size_t)P.n_pclass * sizeof(ProjClass);
+  L.pairm = o;
+  o += (size_t)P.n_pclass * (size_t)P.n_materials * sizeof(PairM);
+  L.paire = o;
+  o += (size_t)P.n_pclass * (size_t)P.n_tclass * sizeof(PairE);
   L.layer_mat = o;
   o += (size_t)P.n_layers * sizeof(int32_t);
   L.hist_vac = o = align_up(o, 16);
@@ -114,6 +120,9 @@ stage_block(const LaunchParams & P, unsigned char * smem)
   DevMaterial * mat = reinterpret_cast<DevMaterial *>(smem + L.materials);
   DevIonZ * iz = reinterpret_cast<DevIonZ *>(smem + L.ionz);
   LowStop * lw = reinterpret_cast<LowStop *>(smem + L.lowstop);
+  ProjClass * pcl = reinterpret_cast<ProjClass *>(smem + L.pclass);
+  PairM * prm = reinterpret_cast<PairM *>(smem + L.pairm);
+  PairE * pre = reinterpret_cast<PairE *>(smem + L.paire);
   double * lc = reinterpret_cast<double *>(smem + L.layer_cum);
   int32_t * lm = reinterpret_cast<int32_t *>(smem + L.layer_mat);
   unsigned int * hv = reinterpret_cast<unsigned int *>(smem + L.hist_vac);
@@ -124,6 +133,9 @@ stage_block(const LaunchParams & P, unsigned char * smem)
   block_copy(mat, P.materials, (size_t)P.n_materials);
   block_copy(iz, P.ionz, (size_t)MTB_NZ + 1);
   block_copy(lw, P.lowstop, (size_t)(MTB_NZ + 1) * (size_t)P.n_zslots);
+  block_copy(pcl, P.pclass, (size_t)P.n_pclass);
+  block_copy(prm, P.pairm, (size_t)P.n_pclass * (size_t)P.n_materials);
+  block_copy(pre, P.paire, (size_t)P.n_pclass * (size_t)P.n_tclass);
   if (P.n_layers > 0)
   {
     block_copy(lc, P.layer_cum, (size_t)P.n_layers);
@@ -140,6 +152,9 @@ stage_block(const LaunchParams & P, unsigned char * smem)
   S.materials = mat;
   S.ionz = iz;
   S.lowstop = lw;
+  S.pclass = pcl;
+  S.pairm = prm;
+  S.paire = pre;
   S.layer_cum = lc;
   S.layer_mat = lm;
   S.hist_vac = hv;
@@ -202,8 +217,8 @@ stopping_kernel(const __grid_constant__ LaunchParams P, int material, size_t n, 
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n)
   {
-    const Projectile pr = make_projectile(P, S, Z1[i], (float)m1[i]);
-    out[i] = (double)material_stopping(pr, S.materials[material], S.elements, (float)E[i]);
+    const ProjClass pr = make_proj_class(S.ionz[Z1[i]], Z1[i], (float)m1[i]);
+    out[i] = (double)material_stopping(pr, S.lowstop + Z1[i] * P.n_zslots, S.materials[material], S.elements, (float)E[i]);
   }
 }
 
@@ -280,6 +295,9 @@ struct mtb_handle
   DevBuf<DevMaterial> d_materials;
   DevBuf<DevIonZ> d_ionz;
   DevBuf<LowStop> d_lowstop;
+  DevBuf<ProjClass> d_pclass;
+  DevBuf<PairM> d_pairm;
+  DevBuf<PairE> d_paire;
   bool fast = false;
   DevBuf<double> d_layer_cum, d_cl_xyzr;
   DevBuf<int32_t> d_layer_mat, d_cl_hash, d_cl_next;
@@ -325,6 +343,12 @@ build_tables(mtb_handle * h)
   MTB_CUDA(h->d_lowstop.upload(T.lowstop.data(), T.lowstop.size(), h->stream));
   P.ionz = h->d_ionz.p;
   P.lowstop = h->d_lowstop.p;
+  MTB_CUDA(h->d_pclass.upload(T.pclass.data(), T.pclass.size(), h->stream));
+  MTB_CUDA(h->d_pairm.upload(T.pairm.data(), T.pairm.size(), h->stream));
+  MTB_CUDA(h->d_paire.upload(T.paire.data(), T.paire.size(), h->stream));
+  P.pclass = h->d_pclass.p;
+  P.pairm = h->d_pairm.p;
+  P.paire = h->d_paire.p;
   if (P.n_layers)
   {
     MTB_CUDA(h->d_layer_cum.upload(T.layer_cum.data(), T.layer_cum.size(), h->stream));
@@ -372,7 +396,7 @@ build_tables(mtb_handle * h)
   h->smem_bytes = smem_layout(P).total;
   if (h->smem_bytes > 200 * 1024)
     return fail(MTB_EINVAL, "configuration tables do not fit in shared memory");
-  h->fast = fast_path_ok(P);
+  h->fast = fast_path_ok(P) && !h->host.custom_species;
   MTB_CUDA(cudaFuncSetAttribute(transport_kernel<TraitsGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   MTB_CUDA(cudaFuncSetAttribute(transport_kernel<TraitsFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   MTB_CUDA(cudaFuncSetAttribute(trim_one_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
@@ -427,7 +451,7 @@ launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, cons
   P.stacks = h->d_stacks.p;
   MTB_CUDA(cudaMemsetAsync(&P.u64[CNT_NEXT_PRIMARY], 0, sizeof(unsigned long long), h->stream));
   MTB_CUDA(cudaEventRecord(h->ev0, h->stream));
-  if (h->fast && fast_path_ok(P))
+  if (h->fast && fast_path_ok(P) && !h->host.custom_species)
     transport_kernel<TraitsFast><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
   else
     transport_kernel<TraitsGeneric><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
@@ -614,10 +638,15 @@ mtb_set_geometry(mtb_handle * h, const mtb_geometry * g)
 int
 mtb_upload_primaries(mtb_handle * h, uint64_t n, const mtb_ion * primaries)
 {
-  if (int rc = ensure_ready(h))
-    return rc;
+  if (!h)
+    return fail(MTB_EINVAL, "null handle");
   if (n && !primaries)
     return fail(MTB_EINVAL, "null primaries");
+  // species of the primaries get their own rows in the class tables
+  if (h->have_materials && register_primary_species(h->host, n, primaries))
+    h->dirty = true;
+  if (int rc = ensure_ready(h))
+    return rc;
   MTB_CUDA(h->d_primaries.upload(primaries, n, h->stream));
   h->n_resident = n;
   return MTB_OK;
@@ -685,10 +714,12 @@ int
 mtb_run_beam(mtb_handle * h, uint64_t n, const mtb_ion * ion, uint64_t seed, uint64_t first_index,
              mtb_record * records)
 {
+  if (!h || !ion)
+    return fail(MTB_EINVAL, "null argument");
+  if (h->have_materials && register_primary_species(h->host, 1, ion))
+    h->dirty = true;
   if (int rc = ensure_ready(h))
     return rc;
-  if (!ion)
-    return fail(MTB_EINVAL, "null ion");
   if (int rc = launch_transport(h, n, nullptr, ion, seed, first_index, records != nullptr))
     return rc;
   if (int rc = sync_and_check(h))
@@ -897,10 +928,12 @@ int
 mtb_trim_one(mtb_handle * h, mtb_ion * ion, uint64_t seed, uint64_t uid, int32_t * final_state,
              mtb_event * events, size_t capacity, size_t * n_events)
 {
+  if (!h || !ion)
+    return fail(MTB_EINVAL, "null argument");
+  if (h->have_materials && register_primary_species(h->host, 1, ion))
+    h->dirty = true;
   if (int rc = ensure_ready(h))
     return rc;
-  if (!ion)
-    return fail(MTB_EINVAL, "null ion");
   const size_t cap = std::max<size_t>(capacity, 1);
   MTB_CUDA(h->d_events.ensure(cap));
   LaunchParams P = h->P;

@@ -174,21 +174,32 @@ philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, u
   out[3] = c3;
 }
 
-// 32 random bits -> (0,1], identical on host and device (exactly rounded conversion + one fma)
+// 32 random bits -> uniform in (0,1): the top 23 bits become the mantissa of a float in [1,2),
+// minus 1, plus half a grid step.  Pure ALU/FMA-pipe work (an I2F conversion would occupy the SFU
+// pipe, the busiest one of the transport kernel), exactly the same on host and device.
 MTB_HD float
 u01(uint32_t x)
 {
-  return fmaf((float)x, 0x1p-32f, 0x1p-33f);
+  const uint32_t bits = 0x3f800000u | (x >> 9);
+  float f;
+#if MTB_DEVICE_CODE
+  f = __uint_as_float(bits);
+#else
+  union { uint32_t u; float f; } cvt;
+  cvt.u = bits;
+  f = cvt.f;
+#endif
+  return (f - 1.0f) + 0x1p-24f;
 }
 
-// stream id of a recoil: splitmix64 finaliser over (parent id, parent step number)
+// Stream id of a recoil: the spare word of the parent's Philox block of the collision that created
+// it (already a keyed hash of (parent id, collision index)) in the high half, a mixed copy of the
+// parent id and collision index in the low half.
 MTB_HD uint64_t
-child_uid(uint64_t uid, uint32_t ic)
+child_uid(uint64_t uid, uint32_t ic, uint32_t w3)
 {
-  uint64_t z = uid + 0x9E3779B97F4A7C15ull * (uint64_t)ic;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
+  const uint32_t lo = ((uint32_t)uid ^ (uint32_t)(uid >> 32)) * 0x9E3779B9u + ic * 0x85EBCA6Bu;
+  return ((uint64_t)w3 << 32) | (uint64_t)lo;
 }
 
 } // namespace mtb

@@ -18,19 +18,6 @@ namespace mtb
 #define MTB_SCREEN_K 0.46850076f
 #define MTB_PI_F 3.14159265358979323846f
 
-// Projectile description kept in registers while an ion is in flight.
-struct Projectile
-{
-  float fz;    // float(Z1)
-  float m;     // amu
-  float z023;  // Z1^0.23
-  float cbrt;  // Z1^(1/3)
-  float lfctr; // screening length factor of Z1
-  float inv_km; // 0.001 / m: eV -> keV/amu
-  const LowStop * low; // row of the low-velocity stopping table for this Z1
-  int Z;
-};
-
 // ZBL proton stopping, e in keV/amu — MaterialBase::rpstop, material.C:133-158.
 MTB_HD float
 proton_stopping(const DevElement & el, float e)
@@ -48,14 +35,14 @@ proton_stopping(const DevElement & el, float e)
 // Electronic stopping cross-section of one target element — MaterialBase::rstop,
 // material.C:160-282.  E in eV.
 MTB_HD float
-element_stopping(const Projectile & ion, const DevElement & el, float E)
+element_stopping(const ProjClass & ion, const LowStop * lowrow, const DevElement & el, float E)
 {
   const float e = E * ion.inv_km; // keV/amu
   if (ion.Z >= 3)
   {
     // velocity-proportional regime (material.C:259-273): rstop = coef(Z1,Z2) * e^power, with the
     // (Z1, Z2)-only part tabulated in double on the host (mtb_tables.h)
-    const LowStop ls = ion.low[el.zslot];
+    const LowStop ls = lowrow[el.zslot];
     if (e <= ls.e_max)
       return ls.coef * (ls.power == 0.5f ? fsqrt(e) : fpow(e, ls.power));
   }
@@ -146,13 +133,14 @@ element_stopping(const Projectile & ion, const DevElement & el, float E)
 
 // MaterialBase::getrstop — material.C:113-122 [eV/Ang]
 MTB_HD float
-material_stopping(const Projectile & ion, const DevMaterial & M, const DevElement * elements, float E)
+material_stopping(const ProjClass & ion, const LowStop * lowrow, const DevMaterial & M, const DevElement * elements,
+                  float E)
 {
   float se = 0.0f;
   for (int i = 0; i < M.n_elem; ++i)
   {
     const DevElement & el = elements[M.first_elem + i];
-    se += element_stopping(ion, el, E) * el.t;
+    se += element_stopping(ion, lowrow, el, E) * el.t;
   }
   return se * M.arho;
 }
@@ -270,21 +258,62 @@ magic_scatter(int potential, float eps, float b)
   return out;
 }
 
-// Ion/material dependent constants of MaterialBase::average (material.C:77-110) that the free
-// flight needs, and the impact-parameter scale.  Returns pmax and writes ls (trim.C:88-92).
+// Free flight (trim.C:88-92) from the tabulated (projectile class, material) constants:
+// returns pmax and writes the mean free flight path ls.
 MTB_HD float
-flight_constants(const Projectile & ion, const DevMaterial & M, float tmin, float E, float * ls)
+flight_from_pair(const PairM & pm, float E, float * ls)
 {
+  const float eeg = pm.K * fsqrt(E);
+  const float D = eeg + fsqrt(eeg) + 0.125f * fpow(eeg, 0.1f);
+  *ls = pm.C2 * (D * D);
+  return pm.a * frcp(D);
+}
+
+// On-the-fly versions of the pair tables (MaterialBase::average, material.C:77-110) for projectiles
+// that have no class (per-primary masses such as fission fragments).
+MTB_HD PairM
+make_pair_m(const ProjClass & ion, const DevMaterial & M, float tmin)
+{
+  PairM pm;
   const float a = fdiv(MTB_SCREEN_K, ion.z023 + M.az023);
   const float mu = fdiv(ion.m, M.am);
   const float f = fdiv(a * M.am, M.az * ion.fz * 14.4f * (ion.m + M.am));
   const float opm = 1.0f + mu;
   const float epsdg = fdiv(tmin * f * (opm * opm), 4.0f * mu);
-  const float eps = E * f;
-  const float eeg = fsqrt(eps * epsdg);
-  const float pmax = fdiv(a, eeg + fsqrt(eeg) + 0.125f * fpow(eeg, 0.1f));
-  *ls = frcp(MTB_PI_F * (pmax * pmax) * M.arho);
-  return pmax;
+  pm.a = a;
+  pm.K = fsqrt(f * epsdg);
+  pm.C2 = frcp(MTB_PI_F * M.arho * (a * a));
+  pm.pad = 0.0f;
+  return pm;
+}
+
+MTB_HD PairE
+make_pair_e(const ProjClass & ion, const DevElement & el)
+{
+  PairE pe;
+  pe.my = fdiv(ion.m, el.m);
+  const float opmy = 1.0f + pe.my;
+  pe.ec = fdiv(4.0f * pe.my, opmy * opmy);
+  const float ai = fdiv(MTB_SCREEN_K, ion.z023 + el.z023);
+  pe.inv_ai = frcp(ai);
+  pe.fi = fdiv(ai * el.m, ion.fz * el.fz * 14.4f * (ion.m + el.m));
+  return pe;
+}
+
+// ProjClass of an arbitrary (Z, m), computed on the device
+MTB_HD ProjClass
+make_proj_class(const DevIonZ & iz, int Z, float m)
+{
+  ProjClass c;
+  c.m = (m == 0.0f) ? iz.mm1 : m;
+  c.m2 = 2.0f * c.m;
+  c.inv_km = fdiv(0.001f, c.m);
+  c.fz = (float)Z;
+  c.z023 = iz.z023;
+  c.cbrt = iz.cbrt;
+  c.lfctr = iz.lfctr;
+  c.Z = Z;
+  return c;
 }
 
 } // namespace mtb

@@ -117,6 +117,9 @@ struct HostConfig
   std::vector<mtb_element> elements;
   mtb_geometry geom;
   std::vector<double> layer_thickness, cluster_xyzr;
+  // (Z, m) of primaries seen so far that are not target atoms: they get projectile classes too
+  std::vector<std::pair<int, double>> primary_species;
+  bool custom_species = false; // some primaries have no class (more distinct species than the cap)
 
   HostConfig()
   {
@@ -138,6 +141,9 @@ struct HostTables
   std::vector<DevMaterial> materials;
   std::vector<DevIonZ> ionz;
   std::vector<LowStop> lowstop; // [MTB_NZ + 1][n_zslots]
+  std::vector<ProjClass> pclass;
+  std::vector<PairM> pairm;
+  std::vector<PairE> paire;
   std::vector<double> layer_cum;
   std::vector<int32_t> layer_mat, cl_hash, cl_next;
 };
@@ -204,6 +210,47 @@ check_geometry(const mtb_geometry * g, std::string & err)
     return MTB_EINVAL;
   }
   return MTB_OK;
+}
+
+inline double
+c_tmin(const HostConfig & H)
+{
+  return H.cfg.tmin;
+}
+
+// Registers the distinct (Z, m) of a batch of primaries as projectile classes (at most `cap`
+// beyond the target atoms; further species are handled by the on-the-fly path of the generic
+// kernel).  Returns true if the tables have to be rebuilt.
+inline bool
+register_primary_species(HostConfig & H, uint64_t n, const mtb_ion * ions, size_t cap = 16)
+{
+  bool changed = false;
+  int lastZ = -1;
+  double lastM = -1.0;
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    if (ions[i].Z == lastZ && ions[i].m == lastM)
+      continue;
+    lastZ = ions[i].Z;
+    lastM = ions[i].m;
+    const std::pair<int, double> key(lastZ, lastM);
+    bool known = std::find(H.primary_species.begin(), H.primary_species.end(), key) != H.primary_species.end();
+    for (size_t e = 0; !known && e < H.elements.size(); ++e)
+      known = H.elements[e].Z == key.first && H.elements[e].m == key.second;
+    if (known)
+      continue;
+    if (H.primary_species.size() >= cap)
+    {
+      changed = changed || !H.custom_species;
+      H.custom_species = true; // too many species: the rest stays "custom" (generic kernel only)
+      return changed;
+    }
+    if (key.first < 1 || key.first > MTB_NZ)
+      continue;
+    H.primary_species.push_back(key);
+    changed = true;
+  }
+  return changed;
 }
 
 // Fills T and every non-pointer field of P.  Pointer fields of P are left for the caller.
@@ -303,6 +350,79 @@ build_host_tables(const HostConfig & H, HostTables & T, LaunchParams & P, std::s
   for (int z1 = 1; z1 <= MTB_NZ; ++z1)
     for (size_t k = 0; k < zlist.size(); ++k)
       T.lowstop[(size_t)z1 * zlist.size() + k] = host_low_velocity_stopping(H.zbl, z1, zlist[k]);
+  // projectile / target classes and their pair tables — MaterialBase::average, material.C:77-110
+  std::vector<std::pair<int, double>> classes;
+  for (size_t i = 0; i < H.elements.size(); ++i)
+  {
+    const std::pair<int, double> key(H.elements[i].Z, H.elements[i].m);
+    auto it = std::find(classes.begin(), classes.end(), key);
+    if (it == classes.end())
+    {
+      classes.push_back(key);
+      it = classes.end() - 1;
+    }
+    T.elements[i].tcls = (int32_t)(it - classes.begin());
+  }
+  const size_t nt = classes.size();
+  for (const auto & sp : H.primary_species)
+    if (std::find(classes.begin(), classes.end(), sp) == classes.end())
+      classes.push_back(sp);
+  const size_t np = classes.size(), nm = H.materials.size();
+  T.pclass.assign(np, ProjClass());
+  T.pairm.assign(np * nm, PairM());
+  T.paire.assign(np * nt, PairE());
+  for (size_t pc = 0; pc < np; ++pc)
+  {
+    const int z1 = classes[pc].first;
+    const double m1 = classes[pc].second == 0.0 ? H.zbl[z1 - 1].mm1 : classes[pc].second;
+    const double z1p = std::pow((double)z1, 0.23);
+    ProjClass & c = T.pclass[pc];
+    c.m2 = (float)(2.0 * m1);
+    c.inv_km = (float)(0.001 / m1);
+    c.m = (float)m1;
+    c.fz = (float)z1;
+    c.z023 = (float)z1p;
+    c.cbrt = (float)std::cbrt((double)z1);
+    c.lfctr = (float)H.zbl[z1 - 1].lfctr;
+    c.Z = z1;
+    for (size_t mi = 0; mi < nm; ++mi)
+    {
+      const mtb_material & m = H.materials[mi];
+      double tt = 0.0, am = 0.0, az = 0.0;
+      for (int j = 0; j < m.n_elements; ++j)
+        tt += std::max(0.0, H.elements[m.first_element + j].t);
+      for (int j = 0; j < m.n_elements; ++j)
+      {
+        const mtb_element & e = H.elements[m.first_element + j];
+        am += e.m * std::max(0.0, e.t) / tt;
+        az += (double)e.Z * std::max(0.0, e.t) / tt;
+      }
+      const double arho = m.rho * 0.6022 / am;
+      const double mu = m1 / am;
+      const double a = .5292 * .8853 / (z1p + std::pow(az, 0.23));
+      const double f = a * am / (az * (double)z1 * 14.4 * (m1 + am));
+      const double epsdg = c_tmin(H) * f * (1.0 + mu) * (1.0 + mu) / (4.0 * mu);
+      PairM & pm = T.pairm[pc * nm + mi];
+      pm.a = (float)a;
+      pm.K = (float)std::sqrt(f * epsdg);
+      pm.C2 = (float)(1.0 / (3.14159265358979323846 * arho * a * a));
+      pm.pad = 0.f;
+    }
+    for (size_t tc = 0; tc < nt; ++tc)
+    {
+      const int z2 = classes[tc].first;
+      const double m2 = classes[tc].second;
+      const double my = m1 / m2;
+      const double ai = .5292 * .8853 / (z1p + std::pow((double)z2, 0.23));
+      PairE & pe = T.paire[pc * nt + tc];
+      pe.my = (float)my;
+      pe.ec = (float)(4.0 * my / ((1.0 + my) * (1.0 + my)));
+      pe.inv_ai = (float)(1.0 / ai);
+      pe.fi = (float)(ai * m2 / ((double)z1 * (double)z2 * 14.4 * (m1 + m2)));
+    }
+  }
+  P.n_pclass = (int32_t)np;
+  P.n_tclass = (int32_t)nt;
   P.n_elements = (int32_t)T.elements.size();
   P.n_materials = (int32_t)T.materials.size();
   if (P.n_elements + SPECIES_ELEMENT0 > SPECIES_MASK)

@@ -75,7 +75,8 @@ tally_on(const LaunchParams & P, uint32_t bit)
   return TR::kGeneric ? (P.tally_mask & bit) != 0 : (TR::kTally & bit) != 0;
 }
 
-// Does this configuration qualify for TraitsFast?
+// Does this configuration qualify for TraitsFast?  (The launcher additionally requires that every
+// primary species has a projectile class; per-primary masses go through the generic kernel.)
 inline bool
 fast_path_ok(const LaunchParams & P)
 {
@@ -91,6 +92,9 @@ struct BlockCtx
   const DevMaterial * materials;
   const DevIonZ * ionz;
   const LowStop * lowstop;
+  const ProjClass * pclass;
+  const PairM * pairm;
+  const PairE * paire;
   const double * layer_cum;
   const int32_t * layer_mat;
   unsigned int * hist_vac;  // [smem_hist_bins] or null
@@ -268,61 +272,65 @@ struct Lane
   // ion in flight
   double px, py, pz, E;
   float dx, dy, dz;
+  float Ecur;      // float copy of E (saves double->float conversions on the SFU pipe)
   uint32_t ic;
   uint64_t uid;
   uint32_t packed;
   int32_t tag;
-  Projectile proj;
+  int32_t pcls;    // projectile class of the ion in flight, -1: custom (generic kernels only)
+  ProjClass cust;  // constants of a custom projectile
   // current cascade
   uint64_t prim;
+  int32_t prim_pcls;
   int32_t pZ;
   float pm, Ef;
   double casEel, casEnuc;
   uint32_t casVac, casRepl, casSteps, casIons;
 };
 
+// Select the projectile class after L.packed changed (new primary, pop, hand-over to a recoil).
+template <class TR>
 MTB_HD void
-set_projectile(const LaunchParams & P, Lane & L, const BlockCtx & S)
+set_species(const LaunchParams & P, Lane & L, const BlockCtx & S)
 {
   const uint32_t species = L.packed & SPECIES_MASK;
-  int Z;
-  float m;
   if (species == SPECIES_PRIMARY)
   {
-    Z = L.pZ;
-    m = L.pm;
+    L.pcls = L.prim_pcls;
+    if (TR::kGeneric && L.pcls < 0)
+      L.cust = make_proj_class(S.ionz[L.pZ], L.pZ, L.pm);
   }
   else
-  {
-    const DevElement & el = S.elements[species - SPECIES_ELEMENT0];
-    Z = el.Z;
-    m = el.m;
-  }
-  const DevIonZ & iz = S.ionz[Z];
-  L.proj.Z = Z;
-  L.proj.fz = (float)Z;
-  L.proj.m = (m == 0.0f) ? iz.mm1 : m;
-  L.proj.z023 = iz.z023;
-  L.proj.cbrt = iz.cbrt;
-  L.proj.lfctr = iz.lfctr;
-  L.proj.inv_km = fdiv(0.001f, L.proj.m);
-  L.proj.low = S.lowstop + Z * P.n_zslots;
+    L.pcls = S.elements[species - SPECIES_ELEMENT0].tcls;
+  (void)P;
 }
 
-MTB_HD Projectile
-make_projectile(const LaunchParams & P, const BlockCtx & S, int Z, float m)
+// Projectile class of a primary: a target class, a registered primary species, or -1 (custom).
+MTB_HD int
+find_class(const LaunchParams & P, const BlockCtx & S, int Z, float m)
 {
-  Projectile pr;
-  const DevIonZ & iz = S.ionz[Z];
-  pr.Z = Z;
-  pr.fz = (float)Z;
-  pr.m = (m == 0.0f) ? iz.mm1 : m;
-  pr.z023 = iz.z023;
-  pr.cbrt = iz.cbrt;
-  pr.lfctr = iz.lfctr;
-  pr.inv_km = fdiv(0.001f, pr.m);
-  pr.low = S.lowstop + Z * P.n_zslots;
-  return pr;
+  for (int c = 0; c < P.n_pclass; ++c)
+    if (S.pclass[c].Z == Z && S.pclass[c].m == m)
+      return c;
+  return -1;
+}
+
+template <class TR>
+MTB_HD ProjClass
+current_class(const Lane & L, const BlockCtx & S)
+{
+  if (TR::kGeneric && L.pcls < 0)
+    return L.cust;
+  return S.pclass[L.pcls];
+}
+
+template <class TR>
+MTB_HD int
+current_Z(const Lane & L, const BlockCtx & S)
+{
+  if (TR::kGeneric && L.pcls < 0)
+    return L.cust.Z;
+  return S.pclass[L.pcls].Z;
 }
 
 MTB_HD void
@@ -364,6 +372,7 @@ stack_load(const StackEntry * src, Lane & L)
   L.py = __longlong_as_double((long long)(((unsigned long long)a.w << 32) | a.z));
   L.pz = __longlong_as_double((long long)(((unsigned long long)b.y << 32) | b.x));
   L.E = __longlong_as_double((long long)(((unsigned long long)b.w << 32) | b.z));
+  L.Ecur = (float)L.E;
   L.dx = __uint_as_float(c.x);
   L.dy = __uint_as_float(c.y);
   L.dz = __uint_as_float(c.z);
@@ -377,6 +386,7 @@ stack_load(const StackEntry * src, Lane & L)
   L.py = e.pos[1];
   L.pz = e.pos[2];
   L.E = e.E;
+  L.Ecur = (float)e.E;
   L.dx = e.dir[0];
   L.dy = e.dir[1];
   L.dz = e.dir[2];
@@ -389,11 +399,11 @@ stack_load(const StackEntry * src, Lane & L)
 
 template <class TR>
 MTB_HD void
-log_birth(const LaunchParams & P, const Lane & L)
+log_birth(const LaunchParams & P, const Lane & L, int Z)
 {
   if (!tally_on<TR>(P, MTB_TALLY_IONLOG))
     return;
-  if (P.ionlog_z && L.proj.Z != P.ionlog_z)
+  if (P.ionlog_z && Z != P.ionlog_z)
     return;
   const unsigned long long i = MTB_ATOMIC_ADD(&P.u64[CNT_IONLOG_N], 1ull);
   if (i >= P.ionlog_cap)
@@ -407,7 +417,7 @@ log_birth(const LaunchParams & P, const Lane & L)
   o.E1 = 0.0;
   o.uid = L.uid;
   o.primary = L.prim;
-  o.Z = L.proj.Z;
+  o.Z = Z;
   o.gen = (int32_t)((L.packed >> GEN_SHIFT) & GEN_MASK);
   o.tag = L.tag;
   o.state = -1; // birth half; mtb_get_ion_log joins it with the death half
@@ -416,7 +426,7 @@ log_birth(const LaunchParams & P, const Lane & L)
 // an ion has stopped (or left the sample): primary record + death half of the ion log
 template <class TR>
 MTB_HD void
-finish_ion(const LaunchParams & P, const Lane & L, int state)
+finish_ion(const LaunchParams & P, const BlockCtx & S, const Lane & L, int state)
 {
   if ((L.packed & FLAG_PRIMARY) && P.records)
   {
@@ -430,7 +440,8 @@ finish_ion(const LaunchParams & P, const Lane & L, int state)
   }
   if (tally_on<TR>(P, MTB_TALLY_IONLOG))
   {
-    if (P.ionlog_z && L.proj.Z != P.ionlog_z)
+    const int Z = current_Z<TR>(L, S);
+    if (P.ionlog_z && Z != P.ionlog_z)
       return;
     const unsigned long long i = MTB_ATOMIC_ADD(&P.u64[CNT_IONLOG_N], 1ull);
     if (i >= P.ionlog_cap)
@@ -444,7 +455,7 @@ finish_ion(const LaunchParams & P, const Lane & L, int state)
     o.E1 = L.E;
     o.uid = L.uid;
     o.primary = L.prim;
-    o.Z = L.proj.Z;
+    o.Z = Z;
     o.gen = (int32_t)((L.packed >> GEN_SHIFT) & GEN_MASK);
     o.tag = L.tag;
     o.state = state;
@@ -593,7 +604,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       {
         --sp;
         stack_load(stack + sp, L);
-        set_projectile(P, L, S);
+        set_species<TR>(P, L, S);
       }
       else
       {
@@ -622,6 +633,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
         L.dy = (float)src.dir[1];
         L.dz = (float)src.dir[2];
         L.E = src.E;
+        L.Ecur = (float)src.E;
         L.ic = 0;
         L.prim = P.first_index + idx;
         L.uid = EVENTS ? P.single_uid : L.prim;
@@ -634,18 +646,19 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
         L.casVac = L.casRepl = L.casSteps = 0;
         L.casIons = 1;
         open = true;
-        set_projectile(P, L, S);
+        L.prim_pcls = find_class(P, S, L.pZ, L.pm);
+        set_species<TR>(P, L, S);
         if (!EVENTS)
-          log_birth<TR>(P, L);
+          log_birth<TR>(P, L, L.pZ);
       }
       active = true;
     }
 
     // ---------------- one collision: trim.C:74-424 ----------------
-    if (!(L.E > 0.0))
+    if (!(L.Ecur > 0.0f))
     {
       // the reference would produce NaNs for a projectile without energy; park it instead
-      finish_ion<TR>(P, L, MTB_INTERSTITIAL);
+      finish_ion<TR>(P, S, L, MTB_INTERSTITIAL);
       active = false;
       if (EVENTS)
         break;
@@ -659,7 +672,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       // vacuum: the reference breaks out with the state still MOVING (trim.C:80-82)
       MTB_ATOMIC_ADD(&S.blk_u64[CNT_LEFT], 1ull);
       --L.ic;
-      finish_ion<TR>(P, L, MTB_MOVING);
+      finish_ion<TR>(P, S, L, MTB_MOVING);
       active = false;
       if (EVENTS)
         break;
@@ -685,11 +698,19 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     const float uphi = u01(w[2]);
     const float r1 = u01(w[3]);
 
-    const float E0 = (float)L.E;
+    const float E0 = L.Ecur;
+    const ProjClass pc = current_class<TR>(L, S);
+    const LowStop * const lowrow = S.lowstop + pc.Z * P.n_zslots;
 
-    // free flight path and impact parameter — trim.C:88-94, 143-144
+    // free flight path and impact parameter — trim.C:88-94, 143-144 (constants of
+    // MaterialBase::average from the (projectile class, material) table)
+    PairM pm;
+    if (TR::kGeneric && L.pcls < 0)
+      pm = make_pair_m(pc, M, P.tmin);
+    else
+      pm = S.pairm[L.pcls * P.n_materials + mi];
     float ls;
-    const float pmax = flight_constants(L.proj, M, P.tmin, E0, &ls);
+    const float pmax = flight_from_pair(pm, E0, &ls);
     if (L.ic == 1)
       ls = r1 * fmin2(ls, P.cw);
     const float p = pmax * fsqrt(r2);
@@ -705,39 +726,52 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     const DevElement & el = S.elements[M.first_elem + nn];
 
     // element part of MaterialBase::average — material.C:99-108
-    const float my = fdiv(L.proj.m, el.m);
-    const float opmy = 1.0f + my;
-    const float ec = fdiv(4.0f * my, opmy * opmy);
-    const float ai = fdiv(MTB_SCREEN_K, L.proj.z023 + el.z023);
-    const float fi = fdiv(ai * el.m, L.proj.fz * el.fz * 14.4f * (L.proj.m + el.m));
+    PairE pe;
+    if (TR::kGeneric && L.pcls < 0)
+      pe = make_pair_e(pc, el);
+    else
+      pe = S.paire[L.pcls * P.n_tclass + el.tcls];
+    const float my = pe.my;
 
-    const float eps = fi * E0; // trim.C:159-160
-    const float b = fdiv(p, ai);
+    const float eps = pe.fi * E0; // trim.C:159-160
+    const float b = p * pe.inv_ai;
 
-    const float see = material_stopping(L.proj, M, S.elements, E0); // trim.C:166
+    const float see = material_stopping(pc, lowrow, M, S.elements, E0); // trim.C:166
     const float dee_f = ls * see;
 
     const Scatter sc = magic_scatter(potential, eps, b);
 
-    // energy bookkeeping in FP64 — trim.C:275-296
+    // energy bookkeeping — trim.C:275-296.  The running energy is FP64; the float images used by
+    // the physics are derived from it once per step.
+    const float den_f = pe.ec * sc.s2 * E0;
     double dee = (double)dee_f;
+    float E1 = E0 - dee_f; // energy after the electronic loss, before the collision
     if (dee > L.E)
+    {
       dee = L.E;
+      E1 = 0.0f;
+    }
     L.E -= dee;
     L.casEel += dee;
-    const float p1 = fsqrt(2.0f * L.proj.m * (float)L.E);
-    double den = (double)(ec * sc.s2 * E0);
+    const float p1 = fsqrt(pc.m2 * fmax2(E1, 0.0f));
+    double den = (double)den_f;
+    float Erec_den = den_f;
     if (den > L.E)
+    {
       den = L.E;
+      Erec_den = (float)den;
+    }
     L.E -= den;
-    const float p2 = fsqrt(2.0f * L.proj.m * (float)L.E);
+    const float E2 = (float)L.E;
+    L.Ecur = E2;
+    const float p2 = fsqrt(pc.m2 * E2);
 
     // recoil is born at the previous collision site — trim.C:306-310
     const double rx = L.px, ry = L.py, rz = L.pz;
     const float flight = (ls - P.tau) * P.inv_scale;
-    L.px = fma((double)L.dx, (double)flight, L.px);
-    L.py = fma((double)L.dy, (double)flight, L.py);
-    L.pz = fma((double)L.dz, (double)flight, L.pz);
+    L.px += (double)(L.dx * flight);
+    L.py += (double)(L.dy * flight);
+    L.pz += (double)(L.dz * flight);
 
     // unit vector perpendicular to dir with uniform azimuth (replaces trim.C:322-333)
     float qx, qy, qz;
@@ -787,7 +821,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     }
 
     // fate of recoil and projectile — trim.C:357-411
-    const float Erec = (float)den - el.Elbind;
+    const float Erec = Erec_den - el.Elbind;
     const int rec_gen = (int)((L.packed >> GEN_SHIFT) & GEN_MASK) + 1;
     bool above = false, follow = false;
     if (state != MTB_LOST)
@@ -799,14 +833,14 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           L.casEnuc += (double)el.Elbind; // TrimPhononOut::followRecoil
         follow = !EVENTS && (!TR::kGeneric || P.follow == MTB_FOLLOW_ALL ||
                              (P.follow == MTB_FOLLOW_GEN_LT && rec_gen < P.follow_max_gen));
-        if (L.E > (double)el.Edisp)
+        if (E2 > el.Edisp)
           vacancy_creation<TR>(P, S, L, M, el, rx, ry, Erec, rec_gen);
         else
         {
           L.casRepl++;
           if (tally_on<TR>(P, MTB_TALLY_VAC_DEPTH))
             depth_tally(P, S, S.hist_repl, off_repl(P), (int)rx);
-          state = (L.proj.Z == el.Z) ? MTB_REPLACEMENT : MTB_SUBSTITUTIONAL;
+          state = (pc.Z == el.Z) ? MTB_REPLACEMENT : MTB_SUBSTITUTIONAL;
         }
       }
       else
@@ -822,7 +856,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
         }
         if (tally_on<TR>(P, MTB_TALLY_PHONON))
           L.casEnuc += den; // recoil.E + Elbind — TrimPhononOut::dissipateRecoilEnergy
-        if (L.E < (double)L.Ef)
+        if (E2 < L.Ef)
           state = MTB_INTERSTITIAL;
       }
       // TrimPhononOut::checkPKAState — trim.C:503-511
@@ -857,7 +891,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       ++n_events;
       if (state != MTB_MOVING)
       {
-        finish_ion<TR>(P, L, state);
+        finish_ion<TR>(P, S, L, state);
         break;
       }
       continue;
@@ -868,9 +902,9 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     {
       L.casIons++;
       const float qs = frsqrt(qx * qx + qy * qy + qz * qz);
-      const uint64_t ruid = child_uid(L.uid, L.ic);
+      const uint64_t ruid = child_uid(L.uid, L.ic, w[3]);
       const uint32_t rpacked = (uint32_t)(SPECIES_ELEMENT0 + M.first_elem + nn) | ((uint32_t)rec_gen << GEN_SHIFT);
-      const bool keep_projectile = (state == MTB_MOVING) && (L.E <= (double)Erec);
+      const bool keep_projectile = (state == MTB_MOVING) && (E2 <= Erec);
       if (state == MTB_MOVING && !keep_projectile)
       {
         // both move on and the recoil has less energy: suspend the projectile, fly the recoil
@@ -880,7 +914,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           MTB_ATOMIC_ADD(&P.u64[CNT_ERROR], 1ull);
       }
       if (state != MTB_MOVING)
-        finish_ion<TR>(P, L, state);
+        finish_ion<TR>(P, S, L, state);
       if (keep_projectile)
       {
         // suspend the recoil instead
@@ -895,8 +929,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
         if (tally_on<TR>(P, MTB_TALLY_IONLOG))
         {
           R.prim = L.prim;
-          R.proj.Z = el.Z;
-          log_birth<TR>(P, R);
+          log_birth<TR>(P, R, el.Z);
         }
         if (sp < MTB_STACK_DEPTH)
           stack_store(stack + sp++, R);
@@ -907,20 +940,21 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       {
         L.px = rx; L.py = ry; L.pz = rz;
         L.E = (double)Erec;
+        L.Ecur = Erec;
         L.dx = qx * qs; L.dy = qy * qs; L.dz = qz * qs;
         L.ic = 0;
         L.uid = ruid;
         L.packed = rpacked;
         L.tag = mtag;
-        set_projectile(P, L, S);
-        log_birth<TR>(P, L);
+        L.pcls = el.tcls;
+        log_birth<TR>(P, L, el.Z);
       }
       if (sp > sp_max)
         sp_max = sp;
     }
     else if (state != MTB_MOVING)
     {
-      finish_ion<TR>(P, L, state);
+      finish_ion<TR>(P, S, L, state);
       active = false;
     }
   }

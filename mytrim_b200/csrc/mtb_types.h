@@ -28,7 +28,7 @@ struct DevElement
   int32_t Z;
   float velpwr; // 0.25 (Z<=6) or 0.45: rpstop low-energy exponent (material.C:151-155)
   int32_t zslot; // column of this element's Z in the low-velocity stopping table
-  int32_t pad;
+  int32_t tcls;  // target class: index of this element's (Z, m) among the distinct target atoms
 };
 static_assert(sizeof(DevElement) == 80, "DevElement layout");
 
@@ -57,6 +57,41 @@ struct LowStop
   float e_max; // min(e at which yr leaves the clamp, 20 keV/amu); 0 disables the shortcut
   float power; // 0.5 or 0.375
   float pad;
+};
+
+// Projectile class: a distinct (Z, m) that can be in flight — every target class (recoils) plus the
+// species of the primaries the host has seen.  Tabulating per-class constants on the host (double
+// precision, rounded once) replaces MaterialBase::average (material.C:77-110) on the device.
+struct ProjClass
+{
+  float m2;     // 2 m  (momentum = sqrt(m2 * E))
+  float inv_km; // 0.001 / m: eV -> keV/amu
+  float m;
+  float fz;     // float(Z)
+  float z023;   // Z^0.23
+  float cbrt;   // Z^(1/3)
+  float lfctr;  // screening length factor of Z
+  int32_t Z;
+};
+static_assert(sizeof(ProjClass) == 32, "ProjClass layout");
+
+// (projectile class, material): free-flight constants (material.C:80-93, trim.C:88-92)
+//   eeg = K sqrt(E);  D = eeg + sqrt(eeg) + 0.125 eeg^0.1;  pmax = a / D;  ls = C2 D^2
+struct PairM
+{
+  float a;  // screening length
+  float K;  // sqrt(f * epsdg)
+  float C2; // 1 / (pi arho a^2)
+  float pad;
+};
+
+// (projectile class, target class): collision constants (material.C:99-108)
+struct PairE
+{
+  float my;     // m1 / m2
+  float ec;     // 4 my / (1 + my)^2
+  float inv_ai; // 1 / screening length
+  float fi;     // reduced-energy factor
 };
 
 // Per projectile-Z constants (indexed by Z, entry 0 unused).
@@ -136,6 +171,10 @@ struct LaunchParams
   const DevIonZ * ionz; // [93]
   const LowStop * lowstop; // [93][n_zslots]
   int32_t n_zslots;
+  const ProjClass * pclass; // [n_pclass]: target classes first, then primary species
+  const PairM * pairm;      // [n_pclass][n_materials]
+  const PairE * paire;      // [n_pclass][n_tclass]
+  int32_t n_pclass, n_tclass;
   int32_t n_elements, n_materials;
   // geometry
   int32_t geom_kind;

@@ -113,21 +113,23 @@ orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* Stream id of a recoil: splitmix64 finaliser over (parent id, parent step number). */
+/* Stream id of a recoil: spare word of the parent's Philox block of the collision that created it in
+ * the high half, a mixed copy of (parent id, collision index) in the low half. */
 uint64_t
-orc_child_uid(uint64_t uid, uint32_t ic)
+orc_child_uid(uint64_t uid, uint32_t ic, uint32_t w3)
 {
-  uint64_t z = uid + 0x9E3779B97F4A7C15ull * (uint64_t)ic;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
+  const uint32_t lo = ((uint32_t)uid ^ (uint32_t)(uid >> 32)) * 0x9E3779B9u + ic * 0x85EBCA6Bu;
+  return ((uint64_t)w3 << 32) | (uint64_t)lo;
 }
 
-/* 32 random bits -> uniform in (0,1], computed in single precision exactly as on the device */
+/* 32 random bits -> uniform in (0,1): top 23 bits as the mantissa of a float in [1,2), minus 1, plus
+ * half a grid step; computed in single precision exactly as on the device */
 float
 orc_u01(uint32_t x)
 {
-  return fmaf((float)x, 0x1p-32f, 0x1p-33f);
+  union { uint32_t u; float f; } cvt;
+  cvt.u = 0x3f800000u | (x >> 9);
+  return (cvt.f - 1.0f) + 0x1p-24f;
 }
 
 /* ------------------------------------------------------------------------- */
@@ -1066,6 +1068,7 @@ transport_ion(orc_engine * e, orc_ion * pka, int collect_events)
 
     /* random numbers of this step */
     double r2, hh, uphi = 0.0;
+    uint32_t w3 = 0;
     if (mt)
     {
       r2 = orc_mt_drand(&e->mt); /* trim.C:143 */
@@ -1080,6 +1083,7 @@ transport_ion(orc_engine * e, orc_ion * pka, int collect_events)
       hh = (double)orc_u01(w[1]);
       uphi = (double)orc_u01(w[2]);
       r1 = (double)orc_u01(w[3]);
+      w3 = w[3];
     }
 
     /* maximum impact parameter and free flight path — trim.C:88-94 */
@@ -1257,7 +1261,7 @@ transport_ion(orc_engine * e, orc_ion * pka, int collect_events)
           rec.dir[2] *= s;
           rec.tag = mtag;
           rec.id = e->next_id++;
-          rec.uid = orc_child_uid(pka->uid, pka->ic);
+          rec.uid = orc_child_uid(pka->uid, pka->ic, w3);
           rec.ic = 0;
           memcpy(rec.pos0, rec.pos, sizeof(rec.pos0));
           rec.E0 = rec.E;

@@ -71,7 +71,7 @@ int orc_lookup_material(orc_engine * e, const double pos[3], int * cluster);
 
 /* random number primitives */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-uint64_t orc_child_uid(uint64_t uid, uint32_t ic);
+uint64_t orc_child_uid(uint64_t uid, uint32_t ic, uint32_t w3);
 float orc_u01(uint32_t x);
 typedef struct { uint32_t mt[624]; int idx; } orc_mt19937;
 void orc_mt_seed(orc_mt19937 * g, uint32_t seed);

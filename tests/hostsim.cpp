@@ -47,6 +47,9 @@ hs_prepare(hs_engine * e)
   P.materials = e->T.materials.data();
   P.ionz = e->T.ionz.data();
   P.lowstop = e->T.lowstop.data();
+  P.pclass = e->T.pclass.data();
+  P.pairm = e->T.pairm.data();
+  P.paire = e->T.paire.data();
   P.layer_cum = e->T.layer_cum.data();
   P.layer_mat = e->T.layer_mat.data();
   P.cl_hash = e->T.cl_hash.data();
@@ -75,6 +78,9 @@ hs_ctx(hs_engine * e)
   S.materials = e->P.materials;
   S.ionz = e->P.ionz;
   S.lowstop = e->P.lowstop;
+  S.pclass = e->P.pclass;
+  S.pairm = e->P.pairm;
+  S.paire = e->P.paire;
   S.layer_cum = e->P.layer_cum;
   S.layer_mat = e->P.layer_mat;
   S.hist_vac = e->hist.data();
@@ -158,6 +164,8 @@ hs_set_geometry(hs_engine * e, const mtb_geometry * g)
 int
 hs_run(hs_engine * e, uint64_t n, const mtb_ion * primaries, uint64_t seed, uint64_t first_index, mtb_record * records)
 {
+  if (register_primary_species(e->host, n, primaries))
+    e->dirty = true;
   if (int rc = hs_prepare(e))
     return rc;
   LaunchParams & P = e->P;
@@ -169,7 +177,7 @@ hs_run(hs_engine * e, uint64_t n, const mtb_ion * primaries, uint64_t seed, uint
   P.records = records;
   P.u64[CNT_NEXT_PRIMARY] = 0;
   const BlockCtx S = hs_ctx(e);
-  if (fast_path_ok(P) && !e->force_generic)
+  if (fast_path_ok(P) && !e->force_generic && !e->host.custom_species)
     lane_loop<TraitsFast>(P, S, 0);
   else
     lane_loop<TraitsGeneric>(P, S, 0);
@@ -299,6 +307,8 @@ int
 hs_trim_one(hs_engine * e, mtb_ion * ion, uint64_t seed, uint64_t uid, int32_t * final_state, mtb_event * events,
             size_t capacity, size_t * n_events)
 {
+  if (register_primary_species(e->host, 1, ion))
+    e->dirty = true;
   if (int rc = hs_prepare(e))
     return rc;
   LaunchParams P = e->P;
@@ -343,8 +353,9 @@ hs_stopping(hs_engine * e, int material, size_t n, const int32_t * Z1, const dou
   const BlockCtx S = hs_ctx(e);
   for (size_t i = 0; i < n; ++i)
   {
-    const Projectile pr = make_projectile(e->P, S, Z1[i], (float)m1[i]);
-    out[i] = (double)material_stopping(pr, e->P.materials[material], e->P.elements, (float)E[i]);
+    const ProjClass pr = make_proj_class(S.ionz[Z1[i]], Z1[i], (float)m1[i]);
+    out[i] = (double)material_stopping(pr, S.lowstop + Z1[i] * e->P.n_zslots, e->P.materials[material], e->P.elements,
+                                       (float)E[i]);
   }
   return MTB_OK;
 }
