@@ -699,9 +699,36 @@ int
 mtb_run(mtb_handle * h, uint64_t n, const mtb_ion * primaries, uint64_t seed, uint64_t first_index,
         mtb_record * records)
 {
-  if (int rc = mtb_upload_primaries(h, n, primaries))
-    return rc;
-  if (int rc = launch_transport(h, n, h->d_primaries.p, nullptr, seed, first_index, records != nullptr))
+  if (!h)
+    return fail(MTB_EINVAL, "null handle");
+  if (n && !primaries)
+    return fail(MTB_EINVAL, "null primaries");
+  // Page-locked caller memory (cudaHostAlloc / cudaHostRegister, e.g. a pinned torch tensor) is read
+  // by the lanes in place over PCIe: each primary is 88 bytes fetched once per cascade, so the
+  // transfer hides behind the transport instead of preceding it.  Pageable memory is staged.
+  const mtb_ion * dev_view = nullptr;
+  if (n)
+  {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, primaries) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+      dev_view = static_cast<const mtb_ion *>(attr.devicePointer);
+    else
+      (void)cudaGetLastError();
+  }
+  if (dev_view)
+  {
+    if (h->have_materials && register_primary_species(h->host, n, primaries))
+      h->dirty = true;
+    if (int rc = ensure_ready(h))
+      return rc;
+  }
+  else
+  {
+    if (int rc = mtb_upload_primaries(h, n, primaries))
+      return rc;
+    dev_view = h->d_primaries.p;
+  }
+  if (int rc = launch_transport(h, n, dev_view, nullptr, seed, first_index, records != nullptr))
     return rc;
   if (int rc = sync_and_check(h))
     return rc;

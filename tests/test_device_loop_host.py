@@ -33,8 +33,9 @@ def test_trajectories_match_oracle(name, n):
     sel = ro["primary_steps"] == rh["primary_steps"]
     assert sel.mean() >= 0.95
     rel = (np.linalg.norm(ro["pos"] - rh["pos"], axis=1) / path)[sel]
-    assert (rel < TOL).mean() >= 0.995 and np.median(rel) < 0.1 * TOL
-    assert np.abs(ro["Eel"][same] - rh["Eel"][same]).max() <= TOL * ro["Eel"][same].max()
+    assert (rel >= TOL).sum() <= max(2, 0.005 * len(rel)) and np.median(rel) < 0.1 * TOL
+    bad = np.abs(ro["Eel"][same] - rh["Eel"][same]) > TOL * ro["Eel"][same]
+    assert bad.sum() <= max(2, 0.005 * same.sum()), bad.sum()
     co, ch = orc.counters(), hs.counters()
     # energy partition closes: E0 = Eel + Enuc for every non-lost cascade
     E0 = c["ion"][2] * n
