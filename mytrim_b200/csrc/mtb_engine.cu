@@ -298,6 +298,8 @@ struct mtb_handle
   DevBuf<ProjClass> d_pclass;
   DevBuf<PairM> d_pairm;
   DevBuf<PairE> d_paire;
+  DevBuf<int32_t> d_tclass_elem;
+  DevBuf<float4_t> d_custom_rows;
   bool fast = false;
   DevBuf<double> d_layer_cum, d_cl_xyzr;
   DevBuf<int32_t> d_layer_mat, d_cl_hash, d_cl_next;
@@ -349,6 +351,8 @@ build_tables(mtb_handle * h)
   P.pclass = h->d_pclass.p;
   P.pairm = h->d_pairm.p;
   P.paire = h->d_paire.p;
+  MTB_CUDA(h->d_tclass_elem.upload(T.tclass_elem.data(), T.tclass_elem.size(), h->stream));
+  P.tclass_elem = h->d_tclass_elem.p;
   if (P.n_layers)
   {
     MTB_CUDA(h->d_layer_cum.upload(T.layer_cum.data(), T.layer_cum.size(), h->stream));
@@ -396,7 +400,7 @@ build_tables(mtb_handle * h)
   h->smem_bytes = smem_layout(P).total;
   if (h->smem_bytes > 200 * 1024)
     return fail(MTB_EINVAL, "configuration tables do not fit in shared memory");
-  h->fast = fast_path_ok(P) && !h->host.custom_species;
+  h->fast = fast_path_ok(P);
   MTB_CUDA(cudaFuncSetAttribute(transport_kernel<TraitsGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   MTB_CUDA(cudaFuncSetAttribute(transport_kernel<TraitsFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   MTB_CUDA(cudaFuncSetAttribute(trim_one_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
@@ -449,9 +453,11 @@ launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, cons
   const unsigned blocks = (unsigned)std::min(max_blocks, want_blocks);
   MTB_CUDA(h->d_stacks.ensure((size_t)blocks * kBlock * MTB_STACK_DEPTH));
   P.stacks = h->d_stacks.p;
+  MTB_CUDA(h->d_custom_rows.ensure((size_t)blocks * kBlock * (size_t)(2 + P.n_materials + P.n_tclass)));
+  P.custom_rows = h->d_custom_rows.p;
   MTB_CUDA(cudaMemsetAsync(&P.u64[CNT_NEXT_PRIMARY], 0, sizeof(unsigned long long), h->stream));
   MTB_CUDA(cudaEventRecord(h->ev0, h->stream));
-  if (h->fast && fast_path_ok(P) && !h->host.custom_species)
+  if (h->fast && fast_path_ok(P))
     transport_kernel<TraitsFast><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
   else
     transport_kernel<TraitsGeneric><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
@@ -643,7 +649,7 @@ mtb_upload_primaries(mtb_handle * h, uint64_t n, const mtb_ion * primaries)
   if (n && !primaries)
     return fail(MTB_EINVAL, "null primaries");
   // species of the primaries get their own rows in the class tables
-  if (h->have_materials && register_primary_species(h->host, n, primaries))
+  if (h->have_materials && register_primary_species(h->host, std::min<uint64_t>(n, 64), primaries))
     h->dirty = true;
   if (int rc = ensure_ready(h))
     return rc;
@@ -717,7 +723,7 @@ mtb_run(mtb_handle * h, uint64_t n, const mtb_ion * primaries, uint64_t seed, ui
   }
   if (dev_view)
   {
-    if (h->have_materials && register_primary_species(h->host, n, primaries))
+    if (h->have_materials && register_primary_species(h->host, std::min<uint64_t>(n, 64), primaries))
       h->dirty = true;
     if (int rc = ensure_ready(h))
       return rc;
@@ -974,6 +980,8 @@ mtb_trim_one(mtb_handle * h, mtb_ion * ion, uint64_t seed, uint64_t uid, int32_t
   P.records = nullptr;
   P.events = h->d_events.p;
   P.events_cap = events ? capacity : 0;
+  MTB_CUDA(h->d_custom_rows.ensure((size_t)(2 + P.n_materials + P.n_tclass)));
+  P.custom_rows = h->d_custom_rows.p;
   P.tally_mask = 0; // hooks run on the host in this mode
   MTB_CUDA(cudaMemsetAsync(&P.u64[CNT_EVENTS_N], 0, sizeof(unsigned long long), h->stream));
   trim_one_kernel<<<1, 32, h->smem_bytes, h->stream>>>(P);

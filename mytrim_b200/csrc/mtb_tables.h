@@ -119,7 +119,6 @@ struct HostConfig
   std::vector<double> layer_thickness, cluster_xyzr;
   // (Z, m) of primaries seen so far that are not target atoms: they get projectile classes too
   std::vector<std::pair<int, double>> primary_species;
-  bool custom_species = false; // some primaries have no class (more distinct species than the cap)
 
   HostConfig()
   {
@@ -144,6 +143,7 @@ struct HostTables
   std::vector<ProjClass> pclass;
   std::vector<PairM> pairm;
   std::vector<PairE> paire;
+  std::vector<int32_t> tclass_elem;
   std::vector<double> layer_cum;
   std::vector<int32_t> layer_mat, cl_hash, cl_next;
 };
@@ -218,9 +218,10 @@ c_tmin(const HostConfig & H)
   return H.cfg.tmin;
 }
 
-// Registers the distinct (Z, m) of a batch of primaries as projectile classes (at most `cap`
-// beyond the target atoms; further species are handled by the on-the-fly path of the generic
-// kernel).  Returns true if the tables have to be rebuilt.
+// Registers the distinct (Z, m) among the first `n` primaries given as projectile classes (at most
+// `cap` beyond the target atoms).  This is only an optimisation for beams: a primary whose species
+// has no class builds its own rows on the device when it is fetched.  Returns true if the tables
+// have to be rebuilt.
 inline bool
 register_primary_species(HostConfig & H, uint64_t n, const mtb_ion * ions, size_t cap = 16)
 {
@@ -240,11 +241,7 @@ register_primary_species(HostConfig & H, uint64_t n, const mtb_ion * ions, size_
     if (known)
       continue;
     if (H.primary_species.size() >= cap)
-    {
-      changed = changed || !H.custom_species;
-      H.custom_species = true; // too many species: the rest stays "custom" (generic kernel only)
-      return changed;
-    }
+      return changed; // further species build their rows on the device
     if (key.first < 1 || key.first > MTB_NZ)
       continue;
     H.primary_species.push_back(key);
@@ -364,6 +361,9 @@ build_host_tables(const HostConfig & H, HostTables & T, LaunchParams & P, std::s
     T.elements[i].tcls = (int32_t)(it - classes.begin());
   }
   const size_t nt = classes.size();
+  T.tclass_elem.assign(nt, 0);
+  for (size_t i = H.elements.size(); i-- > 0;)
+    T.tclass_elem[T.elements[i].tcls] = (int32_t)i;
   for (const auto & sp : H.primary_species)
     if (std::find(classes.begin(), classes.end(), sp) == classes.end())
       classes.push_back(sp);

@@ -277,8 +277,7 @@ struct Lane
   uint64_t uid;
   uint32_t packed;
   int32_t tag;
-  int32_t pcls;    // projectile class of the ion in flight, -1: custom (generic kernels only)
-  ProjClass cust;  // constants of a custom projectile
+  int32_t pcls;    // projectile class of the ion in flight, -1: this lane's per-primary rows
   // current cascade
   uint64_t prim;
   int32_t prim_pcls;
@@ -288,24 +287,15 @@ struct Lane
   uint32_t casVac, casRepl, casSteps, casIons;
 };
 
-// Select the projectile class after L.packed changed (new primary, pop, hand-over to a recoil).
-template <class TR>
+// Select the projectile class after L.packed changed (pop, hand-over to a recoil).
 MTB_HD void
-set_species(const LaunchParams & P, Lane & L, const BlockCtx & S)
+set_species(Lane & L, const BlockCtx & S)
 {
   const uint32_t species = L.packed & SPECIES_MASK;
-  if (species == SPECIES_PRIMARY)
-  {
-    L.pcls = L.prim_pcls;
-    if (TR::kGeneric && L.pcls < 0)
-      L.cust = make_proj_class(S.ionz[L.pZ], L.pZ, L.pm);
-  }
-  else
-    L.pcls = S.elements[species - SPECIES_ELEMENT0].tcls;
-  (void)P;
+  L.pcls = species == SPECIES_PRIMARY ? L.prim_pcls : S.elements[species - SPECIES_ELEMENT0].tcls;
 }
 
-// Projectile class of a primary: a target class, a registered primary species, or -1 (custom).
+// Projectile class of a primary: a target class, a registered primary species, or -1.
 MTB_HD int
 find_class(const LaunchParams & P, const BlockCtx & S, int Z, float m)
 {
@@ -315,22 +305,72 @@ find_class(const LaunchParams & P, const BlockCtx & S, int Z, float m)
   return -1;
 }
 
-template <class TR>
-MTB_HD ProjClass
-current_class(const Lane & L, const BlockCtx & S)
+MTB_HD float4_t
+as_row(const PairM & v)
 {
-  if (TR::kGeneric && L.pcls < 0)
-    return L.cust;
-  return S.pclass[L.pcls];
+  float4_t r = {v.a, v.K, v.C2, v.pad};
+  return r;
+}
+MTB_HD float4_t
+as_row(const PairE & v)
+{
+  float4_t r = {v.my, v.ec, v.inv_ai, v.fi};
+  return r;
 }
 
-template <class TR>
-MTB_HD int
-current_Z(const Lane & L, const BlockCtx & S)
+// A primary whose (Z, m) has no class (e.g. a fission fragment with its own mass) gets private rows
+// [ProjClass | PairM per material | PairE per target class] in the lane's scratch area.
+MTB_HD void
+build_custom_rows(const LaunchParams & P, const BlockCtx & S, float4_t * rows, int Z, float m)
 {
-  if (TR::kGeneric && L.pcls < 0)
-    return L.cust.Z;
-  return S.pclass[L.pcls].Z;
+  const ProjClass c = make_proj_class(S.ionz[Z], Z, m);
+  float4_t r0 = {c.m2, c.inv_km, c.m, c.fz};
+  float4_t r1 = {c.z023, c.cbrt, c.lfctr, 0.0f};
+#if MTB_DEVICE_CODE
+  r1.w = __int_as_float(c.Z);
+#else
+  {
+    union { int32_t i; float f; } cv;
+    cv.i = c.Z;
+    r1.w = cv.f;
+  }
+#endif
+  rows[0] = r0;
+  rows[1] = r1;
+  for (int mi = 0; mi < P.n_materials; ++mi)
+    rows[2 + mi] = as_row(make_pair_m(c, S.materials[mi], P.tmin));
+  for (int tc = 0; tc < P.n_tclass; ++tc)
+    rows[2 + P.n_materials + tc] = as_row(make_pair_e(c, S.elements[P.tclass_elem[tc]]));
+}
+
+MTB_HD ProjClass
+row_class(const float4_t * rows)
+{
+  const float4_t r0 = rows[0], r1 = rows[1];
+  ProjClass c;
+  c.m2 = r0.x;
+  c.inv_km = r0.y;
+  c.m = r0.z;
+  c.fz = r0.w;
+  c.z023 = r1.x;
+  c.cbrt = r1.y;
+  c.lfctr = r1.z;
+#if MTB_DEVICE_CODE
+  c.Z = __float_as_int(r1.w);
+#else
+  {
+    union { int32_t i; float f; } cv;
+    cv.f = r1.w;
+    c.Z = cv.i;
+  }
+#endif
+  return c;
+}
+
+MTB_HD int
+current_Z(const Lane & L, const BlockCtx & S, const float4_t * rows)
+{
+  return L.pcls >= 0 ? S.pclass[L.pcls].Z : row_class(rows).Z;
 }
 
 MTB_HD void
@@ -426,7 +466,7 @@ log_birth(const LaunchParams & P, const Lane & L, int Z)
 // an ion has stopped (or left the sample): primary record + death half of the ion log
 template <class TR>
 MTB_HD void
-finish_ion(const LaunchParams & P, const BlockCtx & S, const Lane & L, int state)
+finish_ion(const LaunchParams & P, const BlockCtx & S, const Lane & L, const float4_t * rows, int state)
 {
   if ((L.packed & FLAG_PRIMARY) && P.records)
   {
@@ -440,7 +480,7 @@ finish_ion(const LaunchParams & P, const BlockCtx & S, const Lane & L, int state
   }
   if (tally_on<TR>(P, MTB_TALLY_IONLOG))
   {
-    const int Z = current_Z<TR>(L, S);
+    const int Z = current_Z(L, S, rows);
     if (P.ionlog_z && Z != P.ionlog_z)
       return;
     const unsigned long long i = MTB_ATOMIC_ADD(&P.u64[CNT_IONLOG_N], 1ull);
@@ -588,6 +628,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
   const int potential = TR::kGeneric ? P.potential : (int)MTB_POT_UNIVERSAL;
   Lane L;
   StackEntry * const stack = EVENTS ? nullptr : P.stacks + (size_t)lane_global * MTB_STACK_DEPTH;
+  float4_t * const rows = P.custom_rows + (size_t)lane_global * (size_t)(2 + P.n_materials + P.n_tclass);
   int sp = 0, sp_max = 0;
   bool active = false, open = false, started = false;
   unsigned long long n_events = 0;
@@ -604,7 +645,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       {
         --sp;
         stack_load(stack + sp, L);
-        set_species<TR>(P, L, S);
+        set_species(L, S);
       }
       else
       {
@@ -647,7 +688,9 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
         L.casIons = 1;
         open = true;
         L.prim_pcls = find_class(P, S, L.pZ, L.pm);
-        set_species<TR>(P, L, S);
+        if (L.prim_pcls < 0)
+          build_custom_rows(P, S, rows, L.pZ, L.pm);
+        L.pcls = L.prim_pcls;
         if (!EVENTS)
           log_birth<TR>(P, L, L.pZ);
       }
@@ -658,7 +701,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     if (!(L.Ecur > 0.0f))
     {
       // the reference would produce NaNs for a projectile without energy; park it instead
-      finish_ion<TR>(P, S, L, MTB_INTERSTITIAL);
+      finish_ion<TR>(P, S, L, rows, MTB_INTERSTITIAL);
       active = false;
       if (EVENTS)
         break;
@@ -672,7 +715,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       // vacuum: the reference breaks out with the state still MOVING (trim.C:80-82)
       MTB_ATOMIC_ADD(&S.blk_u64[CNT_LEFT], 1ull);
       --L.ic;
-      finish_ion<TR>(P, S, L, MTB_MOVING);
+      finish_ion<TR>(P, S, L, rows, MTB_MOVING);
       active = false;
       if (EVENTS)
         break;
@@ -699,14 +742,21 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     const float r1 = u01(w[3]);
 
     const float E0 = L.Ecur;
-    const ProjClass pc = current_class<TR>(L, S);
+    const bool custom = L.pcls < 0;
+    const ProjClass pc = custom ? row_class(rows) : S.pclass[L.pcls];
     const LowStop * const lowrow = S.lowstop + pc.Z * P.n_zslots;
 
     // free flight path and impact parameter — trim.C:88-94, 143-144 (constants of
     // MaterialBase::average from the (projectile class, material) table)
     PairM pm;
-    if (TR::kGeneric && L.pcls < 0)
-      pm = make_pair_m(pc, M, P.tmin);
+    if (custom)
+    {
+      const float4_t r = rows[2 + mi];
+      pm.a = r.x;
+      pm.K = r.y;
+      pm.C2 = r.z;
+      pm.pad = 0.0f;
+    }
     else
       pm = S.pairm[L.pcls * P.n_materials + mi];
     float ls;
@@ -727,8 +777,14 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
 
     // element part of MaterialBase::average — material.C:99-108
     PairE pe;
-    if (TR::kGeneric && L.pcls < 0)
-      pe = make_pair_e(pc, el);
+    if (custom)
+    {
+      const float4_t r = rows[2 + P.n_materials + el.tcls];
+      pe.my = r.x;
+      pe.ec = r.y;
+      pe.inv_ai = r.z;
+      pe.fi = r.w;
+    }
     else
       pe = S.paire[L.pcls * P.n_tclass + el.tcls];
     const float my = pe.my;
@@ -891,7 +947,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       ++n_events;
       if (state != MTB_MOVING)
       {
-        finish_ion<TR>(P, S, L, state);
+        finish_ion<TR>(P, S, L, rows, state);
         break;
       }
       continue;
@@ -914,7 +970,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           MTB_ATOMIC_ADD(&P.u64[CNT_ERROR], 1ull);
       }
       if (state != MTB_MOVING)
-        finish_ion<TR>(P, S, L, state);
+        finish_ion<TR>(P, S, L, rows, state);
       if (keep_projectile)
       {
         // suspend the recoil instead
@@ -954,7 +1010,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     }
     else if (state != MTB_MOVING)
     {
-      finish_ion<TR>(P, S, L, state);
+      finish_ion<TR>(P, S, L, rows, state);
       active = false;
     }
   }

@@ -150,6 +150,12 @@ enum
   CNT_COUNT = 16
 };
 
+// 16-byte row of the class tables (ProjClass = 2 rows, PairM = 1, PairE = 1)
+struct __attribute__((aligned(16))) float4_t
+{
+  float x, y, z, w;
+};
+
 struct RangeEntry
 {
   float x;
@@ -175,6 +181,8 @@ struct LaunchParams
   const PairM * pairm;      // [n_pclass][n_materials]
   const PairE * paire;      // [n_pclass][n_tclass]
   int32_t n_pclass, n_tclass;
+  const int32_t * tclass_elem; // [n_tclass]: one element index per target class
+  float4_t * custom_rows;      // [lanes][2 + n_materials + n_tclass]: class rows of per-primary species
   int32_t n_elements, n_materials;
   // geometry
   int32_t geom_kind;

@@ -31,6 +31,7 @@ struct hs_engine
   std::vector<StackEntry> stacks;
   std::vector<mtb_ion_log> ionlog;
   std::vector<RangeEntry> range;
+  std::vector<float4_t> custom_rows;
   std::string err;
   bool force_generic = false;
 };
@@ -66,6 +67,9 @@ hs_prepare(hs_engine * e)
   P.ionlog = e->ionlog.data();
   P.range = e->range.data();
   P.stacks = e->stacks.data();
+  P.tclass_elem = e->T.tclass_elem.data();
+  e->custom_rows.assign((size_t)(2 + P.n_materials + P.n_tclass), float4_t());
+  P.custom_rows = e->custom_rows.data();
   e->dirty = false;
   return MTB_OK;
 }
@@ -164,7 +168,7 @@ hs_set_geometry(hs_engine * e, const mtb_geometry * g)
 int
 hs_run(hs_engine * e, uint64_t n, const mtb_ion * primaries, uint64_t seed, uint64_t first_index, mtb_record * records)
 {
-  if (register_primary_species(e->host, n, primaries))
+  if (register_primary_species(e->host, std::min<uint64_t>(n, 64), primaries))
     e->dirty = true;
   if (int rc = hs_prepare(e))
     return rc;
@@ -177,7 +181,7 @@ hs_run(hs_engine * e, uint64_t n, const mtb_ion * primaries, uint64_t seed, uint
   P.records = records;
   P.u64[CNT_NEXT_PRIMARY] = 0;
   const BlockCtx S = hs_ctx(e);
-  if (fast_path_ok(P) && !e->force_generic && !e->host.custom_species)
+  if (fast_path_ok(P) && !e->force_generic)
     lane_loop<TraitsFast>(P, S, 0);
   else
     lane_loop<TraitsGeneric>(P, S, 0);

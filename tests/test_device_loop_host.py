@@ -2,6 +2,8 @@
 (tests/hostsim.cpp) against the double-precision oracle with the same Philox streams.  This checks
 the FP32 reformulations, the depth-first stack traversal and the tallies without a GPU; the GPU
 tests repeat it through the real kernels."""
+import os
+
 import numpy as np
 import pytest
 
@@ -105,3 +107,40 @@ def test_ion_log_and_events():
     assert np.abs(eo["pka_pos"] - eh["pka_pos"]).max() < 1e-5 * np.abs(eo["pka_pos"]).max()
     assert np.abs(eo["recoil_E"] - eh["recoil_E"]).max() <= 1e-5 * np.abs(eo["recoil_E"]).max()
     assert np.abs(fo["pos"] - fh["pos"]).max() < 1e-5 * np.abs(fo["pos"]).max()
+
+
+def _fission_like_primaries(n, seed=3):
+    """Heterogeneous primaries: every ion has its own (Z, m), like mytrim_uo2's fission fragments."""
+    rng = np.random.default_rng(seed)
+    ions = capi.make_ions(n, 1, 1.0, 1.0)
+    ions["Z"] = rng.integers(30, 62, n)
+    ions["m"] = np.round(ions["Z"] * 2.55 + rng.uniform(-3, 3, n), 3)
+    ions["E"] = rng.uniform(2e4, 2e5, n)
+    ions["pos"] = rng.uniform(0, 400, (n, 3))
+    d = rng.normal(size=(n, 3))
+    ions["dir"] = d / np.linalg.norm(d, axis=1)[:, None]
+    return ions
+
+
+def test_per_primary_species_and_clusters():
+    """More distinct primary species than the class table holds: the lane builds private rows.
+    Clusters geometry (tests/uo2: UO2 matrix, Xe bubbles) at the same time."""
+    cl = np.loadtxt(os.path.join(util.GOLDEN, "uo2_out.clcoor"))[:, :4]
+    cfg = dict(tally_mask=capi.TALLY_RECORDS | capi.TALLY_PHONON)
+    ions = _fission_like_primaries(48)
+    with util.OracleEngine(util.ORC_RNG_PHILOX, **cfg) as orc, util.HostSimEngine(**cfg) as hs:
+        for e in (orc, hs):
+            e.set_materials([util.UO2, util.XE_GAS])
+            e.set_geometry(capi.GEOM_CLUSTERS, (400.0, 400.0, 400.0), kn=(39, 39, 39), clusters=cl)
+        ro = orc.run(ions, seed=17, records=True)
+        rh = hs.run(ions, seed=17, records=True)
+        co, ch = orc.counters(), hs.counters()
+    same = (ro["vacancies"] == rh["vacancies"]) & (ro["steps"] == rh["steps"]) & (ro["ions"] == rh["ions"])
+    assert same.mean() >= 0.8, same.mean()
+    sel = ro["primary_steps"] == rh["primary_steps"]
+    path = np.maximum(np.linalg.norm(ro["pos"] - ions["pos"], axis=1), 1.0)
+    rel = (np.linalg.norm(ro["pos"] - rh["pos"], axis=1) / path)[sel]
+    assert (rel >= TOL).sum() <= 2 and np.median(rel) < 0.1 * TOL
+    E0 = ions["E"].sum()
+    assert abs(ch["EelTotal"] + ch["EnucTotal"] - E0) < 1e-6 * E0
+    assert abs(ch["steps"] - co["steps"]) <= 0.02 * co["steps"]

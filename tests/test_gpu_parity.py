@@ -223,3 +223,48 @@ def test_multi_gpu_allreduce_in_process():
         assert abs(c1["EelTotal"] - ca["EelTotal"]) <= 1e-9 * c1["EelTotal"]
         assert np.array_equal(one.vac_depth()[0], a.vac_depth()[0])
         assert np.array_equal(one.vac_depth()[1], b.vac_depth()[1])
+
+
+def test_per_primary_species_and_clusters():
+    """Heterogeneous primaries (own (Z, m) each, like fission fragments) in the tests/uo2 geometry."""
+    from tests.test_device_loop_host import _fission_like_primaries
+    cl = np.loadtxt(os.path.join(util.GOLDEN, "uo2_out.clcoor"))[:, :4]
+    cfg = dict(tally_mask=capi.TALLY_RECORDS | capi.TALLY_PHONON)
+    ions = _fission_like_primaries(400)
+    with util.OracleEngine(util.ORC_RNG_PHILOX, **cfg) as orc, capi.Engine(**cfg) as eng:
+        for e in (orc, eng):
+            e.set_materials([util.UO2, util.XE_GAS])
+            e.set_geometry(capi.GEOM_CLUSTERS, (400.0, 400.0, 400.0), kn=(39, 39, 39), clusters=cl)
+        ro = orc.run(ions, seed=17, records=True)
+        rg = eng.run(ions, seed=17, records=True)
+        co, cg = orc.counters(), eng.counters()
+    same = (ro["vacancies"] == rg["vacancies"]) & (ro["steps"] == rg["steps"]) & (ro["ions"] == rg["ions"])
+    assert same.mean() >= 0.8, same.mean()
+    sel = ro["primary_steps"] == rg["primary_steps"]
+    path = np.maximum(np.linalg.norm(ro["pos"] - ions["pos"], axis=1), 1.0)
+    rel = (np.linalg.norm(ro["pos"] - rg["pos"], axis=1) / path)[sel]
+    assert (rel >= TOL).sum() <= max(2, 0.005 * len(rel)) and np.median(rel) < 0.1 * TOL
+    E0 = ions["E"].sum()
+    assert abs(cg["EelTotal"] + cg["EnucTotal"] - E0) < 1e-6 * E0
+    assert abs(cg["steps"] - co["steps"]) <= 0.02 * co["steps"]
+
+
+def test_pinned_host_primaries_are_read_in_place():
+    """mtb_run with page-locked primaries (zero-copy) gives bit-identical records to the staged path."""
+    import torch
+    c = util.CONFIGS["cu_on_cu_10keV"]
+    n = 5000
+    ions = util.primaries_for(c, n)
+    pinned = torch.empty(n * capi.ION_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    view = np.frombuffer(pinned.numpy(), dtype=capi.ION_DTYPE)
+    view[:] = ions
+    cfg = dict(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS)
+    with capi.Engine(**cfg) as a, capi.Engine(**cfg) as b:
+        util.setup_engine(a, c)
+        util.setup_engine(b, c)
+        ra = a.run(ions, seed=8, records=True)
+        rb = np.zeros(n, dtype=capi.RECORD_DTYPE)
+        lib = capi.load_library()
+        assert lib.mtb_run(b._h, n, pinned.data_ptr(), 8, 0, rb.ctypes.data) == 0, lib.mtb_last_error()
+        for f in ra.dtype.names:
+            assert np.array_equal(ra[f], rb[f]), f
