@@ -300,6 +300,9 @@ struct mtb_handle
   DevBuf<PairE> d_paire;
   DevBuf<int32_t> d_tclass_elem;
   DevBuf<float4_t> d_custom_rows;
+  DevBuf<uint32_t> d_deferred;
+  bool deferred_pending = false;
+  float extra_ms = 0.f;
   bool fast = false;
   DevBuf<double> d_layer_cum, d_cl_xyzr;
   DevBuf<int32_t> d_layer_mat, d_cl_hash, d_cl_next;
@@ -455,15 +458,59 @@ launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, cons
   P.stacks = h->d_stacks.p;
   MTB_CUDA(h->d_custom_rows.ensure((size_t)blocks * kBlock * (size_t)(2 + P.n_materials + P.n_tclass)));
   P.custom_rows = h->d_custom_rows.p;
+  const bool fast = h->fast && fast_path_ok(P) && (primaries_dev || species_known(h->host, P.beam.Z, P.beam.m));
+  P.index_list = nullptr;
+  P.deferred = nullptr;
+  if (fast && primaries_dev)
+  {
+    if (n > 0xFFFFFFFFull)
+      return fail(MTB_EINVAL, "more than 2^32 primaries in one launch");
+    MTB_CUDA(h->d_deferred.ensure(n));
+    P.deferred = h->d_deferred.p;
+  }
   MTB_CUDA(cudaMemsetAsync(&P.u64[CNT_NEXT_PRIMARY], 0, sizeof(unsigned long long), h->stream));
+  MTB_CUDA(cudaMemsetAsync(&P.u64[CNT_DEFERRED], 0, sizeof(unsigned long long), h->stream));
   MTB_CUDA(cudaEventRecord(h->ev0, h->stream));
-  if (h->fast && fast_path_ok(P))
+  if (fast)
     transport_kernel<TraitsFast><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
   else
     transport_kernel<TraitsGeneric><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
   MTB_CUDA(cudaGetLastError());
   MTB_CUDA(cudaEventRecord(h->ev1, h->stream));
   h->timing_pending = true;
+  h->deferred_pending = fast && primaries_dev;
+  h->extra_ms = 0.f;
+  return MTB_OK;
+}
+
+// Primaries the fast kernel could not take (their species has no projectile class) run through the
+// generic kernel, which builds per-lane class rows for them.
+int
+run_deferred(mtb_handle * h)
+{
+  h->deferred_pending = false;
+  unsigned long long nd = 0;
+  MTB_CUDA(cudaMemcpy(&nd, h->d_u64.p + CNT_DEFERRED, sizeof(nd), cudaMemcpyDeviceToHost));
+  if (!nd)
+    return MTB_OK;
+  LaunchParams P = h->P;
+  P.index_list = h->d_deferred.p;
+  P.deferred = nullptr;
+  P.n_primaries = nd;
+  const uint64_t max_blocks = (uint64_t)h->sm_count * h->blocks_per_sm;
+  const unsigned blocks = (unsigned)std::min<uint64_t>(max_blocks, (nd + kBlock - 1) / kBlock);
+  MTB_CUDA(cudaMemsetAsync(&P.u64[CNT_NEXT_PRIMARY], 0, sizeof(unsigned long long), h->stream));
+  cudaEvent_t e0, e1;
+  MTB_CUDA(cudaEventCreate(&e0));
+  MTB_CUDA(cudaEventCreate(&e1));
+  MTB_CUDA(cudaEventRecord(e0, h->stream));
+  transport_kernel<TraitsGeneric><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+  MTB_CUDA(cudaGetLastError());
+  MTB_CUDA(cudaEventRecord(e1, h->stream));
+  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  MTB_CUDA(cudaEventElapsedTime(&h->extra_ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
   return MTB_OK;
 }
 
@@ -475,6 +522,12 @@ sync_and_check(mtb_handle * h)
   {
     MTB_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     h->timing_pending = false;
+  }
+  if (h->deferred_pending)
+  {
+    if (int rc = run_deferred(h))
+      return rc;
+    h->last_ms += h->extra_ms;
   }
   unsigned long long err = 0;
   MTB_CUDA(cudaMemcpy(&err, h->d_u64.p + CNT_ERROR, sizeof(err), cudaMemcpyDeviceToHost));

@@ -218,6 +218,18 @@ c_tmin(const HostConfig & H)
   return H.cfg.tmin;
 }
 
+inline bool
+species_known(const HostConfig & H, int Z, double m)
+{
+  const std::pair<int, double> key(Z, m);
+  if (std::find(H.primary_species.begin(), H.primary_species.end(), key) != H.primary_species.end())
+    return true;
+  for (const auto & e : H.elements)
+    if (e.Z == Z && e.m == m)
+      return true;
+  return false;
+}
+
 // Registers the distinct (Z, m) among the first `n` primaries given as projectile classes (at most
 // `cap` beyond the target atoms).  This is only an optimisation for beams: a primary whose species
 // has no class builds its own rows on the device when it is fetched.  Returns true if the tables

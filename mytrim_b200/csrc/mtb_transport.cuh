@@ -54,17 +54,18 @@ host_fetch_max(T * p, U v)
 // without CUT boundaries) so that the unused hook code is not even in the instruction cache.
 struct TraitsGeneric
 {
-  static constexpr bool kEvents = false, kGeneric = true;
+  static constexpr bool kEvents = false, kGeneric = true, kCustom = true;
   static constexpr uint32_t kTally = 0;
 };
 struct TraitsEvents
 {
-  static constexpr bool kEvents = true, kGeneric = true;
+  static constexpr bool kEvents = true, kGeneric = true, kCustom = true;
   static constexpr uint32_t kTally = 0;
 };
 struct TraitsFast
 {
-  static constexpr bool kEvents = false, kGeneric = false;
+  // kCustom = false: primaries whose species has no class are deferred to the generic kernel
+  static constexpr bool kEvents = false, kGeneric = false, kCustom = false;
   static constexpr uint32_t kTally = MTB_TALLY_VAC_DEPTH;
 };
 
@@ -370,7 +371,7 @@ row_class(const float4_t * rows)
 MTB_HD int
 current_Z(const Lane & L, const BlockCtx & S, const float4_t * rows)
 {
-  return L.pcls >= 0 ? S.pclass[L.pcls].Z : row_class(rows).Z;
+  return (L.pcls >= 0 || !rows) ? S.pclass[L.pcls].Z : row_class(rows).Z;
 }
 
 MTB_HD void
@@ -628,7 +629,8 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
   const int potential = TR::kGeneric ? P.potential : (int)MTB_POT_UNIVERSAL;
   Lane L;
   StackEntry * const stack = EVENTS ? nullptr : P.stacks + (size_t)lane_global * MTB_STACK_DEPTH;
-  float4_t * const rows = P.custom_rows + (size_t)lane_global * (size_t)(2 + P.n_materials + P.n_tclass);
+  float4_t * const rows =
+      TR::kCustom ? P.custom_rows + (size_t)lane_global * (size_t)(2 + P.n_materials + P.n_tclass) : nullptr;
   int sp = 0, sp_max = 0;
   bool active = false, open = false, started = false;
   unsigned long long n_events = 0;
@@ -666,7 +668,18 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
         started = true;
         if (idx >= P.n_primaries)
           break;
+        if (P.index_list)
+          idx = P.index_list[idx];
         const mtb_ion & src = P.primaries ? P.primaries[idx] : P.beam;
+        if (!TR::kCustom)
+        {
+          // species without a projectile class: hand the primary to the generic kernel
+          if (find_class(P, S, src.Z, (float)src.m) < 0)
+          {
+            P.deferred[MTB_ATOMIC_ADD(&P.u64[CNT_DEFERRED], 1ull)] = (uint32_t)idx;
+            continue;
+          }
+        }
         L.px = src.pos[0];
         L.py = src.pos[1];
         L.pz = src.pos[2];
@@ -688,7 +701,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
         L.casIons = 1;
         open = true;
         L.prim_pcls = find_class(P, S, L.pZ, L.pm);
-        if (L.prim_pcls < 0)
+        if (TR::kCustom && L.prim_pcls < 0)
           build_custom_rows(P, S, rows, L.pZ, L.pm);
         L.pcls = L.prim_pcls;
         if (!EVENTS)
@@ -742,7 +755,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     const float r1 = u01(w[3]);
 
     const float E0 = L.Ecur;
-    const bool custom = L.pcls < 0;
+    const bool custom = TR::kCustom && L.pcls < 0;
     const ProjClass pc = custom ? row_class(rows) : S.pclass[L.pcls];
     const LowStop * const lowrow = S.lowstop + pc.Z * P.n_zslots;
 

@@ -146,7 +146,7 @@ enum
   CNT_RANGE_N,
   CNT_ERROR,
   CNT_EVENTS_N,
-  CNT_RESERVED,
+  CNT_DEFERRED, // primaries the fast kernel handed to the generic kernel (per-primary species)
   CNT_COUNT = 16
 };
 
@@ -201,6 +201,8 @@ struct LaunchParams
   const mtb_ion * primaries;    // device copy, or null for beam mode
   mtb_ion beam;
   uint64_t n_primaries, first_index;
+  const uint32_t * index_list;  // optional: launch over primaries[index_list[k]], k < n_primaries
+  uint32_t * deferred;          // fast kernel: indices of primaries without a projectile class
   uint32_t key0, key1;
   // outputs
   unsigned long long * u64;     // counter + histogram block

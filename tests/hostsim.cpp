@@ -181,8 +181,26 @@ hs_run(hs_engine * e, uint64_t n, const mtb_ion * primaries, uint64_t seed, uint
   P.records = records;
   P.u64[CNT_NEXT_PRIMARY] = 0;
   const BlockCtx S = hs_ctx(e);
+  P.index_list = nullptr;
+  P.deferred = nullptr;
+  P.u64[CNT_DEFERRED] = 0;
   if (fast_path_ok(P) && !e->force_generic)
+  {
+    std::vector<uint32_t> deferred(n ? n : 1);
+    P.deferred = deferred.data();
     lane_loop<TraitsFast>(P, S, 0);
+    const unsigned long long nd = P.u64[CNT_DEFERRED];
+    if (nd)
+    {
+      // same hand-over as mtb_engine.cu::run_deferred
+      P.index_list = deferred.data();
+      P.deferred = nullptr;
+      P.n_primaries = nd;
+      P.u64[CNT_NEXT_PRIMARY] = 0;
+      lane_loop<TraitsGeneric>(P, S, 0);
+      P.index_list = nullptr;
+    }
+  }
   else
     lane_loop<TraitsGeneric>(P, S, 0);
   hs_flush(e);

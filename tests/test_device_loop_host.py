@@ -144,3 +144,26 @@ def test_per_primary_species_and_clusters():
     E0 = ions["E"].sum()
     assert abs(ch["EelTotal"] + ch["EnucTotal"] - E0) < 1e-6 * E0
     assert abs(ch["steps"] - co["steps"]) <= 0.02 * co["steps"]
+
+
+def test_fast_kernel_defers_unknown_species():
+    """Layered sample + TrimVacCount tallies selects the compile-time fast loop; primaries whose
+    species has no class are handed to the generic loop and the union equals a generic-only run."""
+    cfg = dict(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS)
+    ions = _fission_like_primaries(60)
+    ions["pos"] = (0.0, 50.0, 50.0)
+    ions["dir"] = (1.0, 0.0, 0.0)
+    ions[::3] = capi.make_ions(20, 29, 63.546, 1.0e4)   # every third primary is a plain Cu ion
+    with util.HostSimEngine(**cfg) as a, util.HostSimEngine(**cfg) as b:
+        for e in (a, b):
+            util.setup_engine(e, "cu_on_cu_10keV")
+        b._lib.hs_force_generic(b._h, 1)
+        ra = a.run(ions, seed=4, records=True)
+        rb = b.run(ions, seed=4, records=True)
+        for f in ra.dtype.names:
+            assert np.array_equal(ra[f], rb[f]), f
+        ca, cb = a.counters(), b.counters()
+        for k in ca:
+            if k not in ("stack_max",):
+                assert abs(ca[k] - cb[k]) <= 1e-12 * abs(cb[k]), k   # f64 totals: summation order differs
+        assert np.array_equal(a.vac_depth()[0], b.vac_depth()[0])

@@ -268,3 +268,26 @@ def test_pinned_host_primaries_are_read_in_place():
         assert lib.mtb_run(b._h, n, pinned.data_ptr(), 8, 0, rb.ctypes.data) == 0, lib.mtb_last_error()
         for f in ra.dtype.names:
             assert np.array_equal(ra[f], rb[f]), f
+
+
+def test_fast_kernel_defers_unknown_species():
+    """The compile-time fast kernel hands primaries without a projectile class to the generic kernel;
+    the union is bit-identical (per-primary records) to running everything through the generic kernel."""
+    from tests.test_device_loop_host import _fission_like_primaries
+    ions = _fission_like_primaries(3000)
+    ions["pos"] = (0.0, 50.0, 50.0)
+    ions["dir"] = (1.0, 0.0, 0.0)
+    ions[::3] = capi.make_ions(1000, 29, 63.546, 1.0e4)
+    fast = dict(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS)              # -> TraitsFast + deferral
+    generic = dict(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS | capi.TALLY_PHONON)  # -> TraitsGeneric
+    with capi.Engine(**fast) as a, capi.Engine(**generic) as b:
+        util.setup_engine(a, "cu_on_cu_10keV")
+        util.setup_engine(b, "cu_on_cu_10keV")
+        ra = a.run(ions, seed=4, records=True)
+        rb = b.run(ions, seed=4, records=True)
+        for f in ra.dtype.names:
+            if f != "Enuc":
+                assert np.array_equal(ra[f], rb[f]), f
+        ca, cb = a.counters(), b.counters()
+        assert ca["steps"] == cb["steps"] and ca["primaries"] == cb["primaries"] == len(ions)
+        assert np.array_equal(a.vac_depth()[0], b.vac_depth()[0])
