@@ -203,8 +203,7 @@ trim_one_kernel(const __grid_constant__ LaunchParams P)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   const BlockCtx S = stage_block(P, smem);
-  if (threadIdx.x == 0)
-    lane_loop<TraitsEvents>(P, S, 0);
+  lane_loop<TraitsEvents>(P, S, threadIdx.x); // lanes 1..31 only take part in the warp votes
   flush_block(P, S);
 }
 

@@ -26,7 +26,10 @@ namespace mtb
 #if MTB_DEVICE_CODE
 #define MTB_ATOMIC_ADD(ptr, val) atomicAdd((ptr), (val))
 #define MTB_ATOMIC_MAX(ptr, val) atomicMax((ptr), (val))
+// warp-uniform loop exit: all 32 lanes vote every iteration, which is also where the warp reconverges
+#define MTB_WARP_ALL(pred) __all_sync(0xffffffffu, (pred))
 #else
+#define MTB_WARP_ALL(pred) (pred)
 template <class T, class U>
 inline T
 host_fetch_add(T * p, U v)
@@ -632,22 +635,27 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
   float4_t * const rows =
       TR::kCustom ? P.custom_rows + (size_t)lane_global * (size_t)(2 + P.n_materials + P.n_tclass) : nullptr;
   int sp = 0, sp_max = 0;
-  bool active = false, open = false, started = false;
+  bool active = false, open = false, started = false, done = false;
   unsigned long long n_events = 0;
   L.prim = 0;
   L.casEel = L.casEnuc = 0.0;
   L.casVac = L.casRepl = L.casSteps = L.casIons = 0;
 
+  // Loop structure: [refill] -> [warp vote] -> [one collision].  No lane leaves the loop before the
+  // whole warp is out of work, and no `continue` jumps back to the loop head from divergent code, so
+  // the 32 lanes reconverge at the vote in every iteration (a lane-level early exit or continue lets
+  // the compiler split the warp for good — measured: 15 instead of 29 active threads).
   for (;;)
   {
     // ---------------- refill: next suspended ion, else next primary ----------------
-    if (!active)
+    if (!done && !active)
     {
       if (sp > 0)
       {
         --sp;
         stack_load(stack + sp, L);
         set_species(L, S);
+        active = true;
       }
       else
       {
@@ -656,69 +664,83 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           close_cascade(P, S, L);
           open = false;
         }
-        unsigned long long idx;
-        if (EVENTS)
+        for (;;)
         {
-          if (started || lane_global != 0)
-            break;
-          idx = 0;
-        }
-        else
-          idx = MTB_ATOMIC_ADD(&P.u64[CNT_NEXT_PRIMARY], 1ull);
-        started = true;
-        if (idx >= P.n_primaries)
-          break;
-        if (P.index_list)
-          idx = P.index_list[idx];
-        const mtb_ion & src = P.primaries ? P.primaries[idx] : P.beam;
-        if (!TR::kCustom)
-        {
-          // species without a projectile class: hand the primary to the generic kernel
-          if (find_class(P, S, src.Z, (float)src.m) < 0)
+          unsigned long long idx;
+          if (EVENTS)
           {
+            if (started || lane_global != 0)
+            {
+              done = true;
+              break;
+            }
+            idx = 0;
+          }
+          else
+            idx = MTB_ATOMIC_ADD(&P.u64[CNT_NEXT_PRIMARY], 1ull);
+          started = true;
+          if (idx >= P.n_primaries)
+          {
+            done = true;
+            break;
+          }
+          if (P.index_list)
+            idx = P.index_list[idx];
+          const mtb_ion & src = P.primaries ? P.primaries[idx] : P.beam;
+          const int src_Z = src.Z;
+          const float src_m = (float)src.m;
+          const int cls = find_class(P, S, src_Z, src_m);
+          if (!TR::kCustom && cls < 0)
+          {
+            // species without a projectile class: hand the primary to the generic kernel
             P.deferred[MTB_ATOMIC_ADD(&P.u64[CNT_DEFERRED], 1ull)] = (uint32_t)idx;
             continue;
           }
+          L.px = src.pos[0];
+          L.py = src.pos[1];
+          L.pz = src.pos[2];
+          L.dx = (float)src.dir[0];
+          L.dy = (float)src.dir[1];
+          L.dz = (float)src.dir[2];
+          L.E = src.E;
+          L.Ecur = (float)src.E;
+          L.ic = 0;
+          L.prim = P.first_index + idx;
+          L.uid = EVENTS ? P.single_uid : L.prim;
+          L.packed = SPECIES_PRIMARY | (((uint32_t)src.gen & GEN_MASK) << GEN_SHIFT) | FLAG_PRIMARY;
+          L.tag = src.tag;
+          L.pZ = src_Z;
+          L.pm = src_m;
+          L.Ef = (float)src.Ef;
+          L.casEel = L.casEnuc = 0.0;
+          L.casVac = L.casRepl = L.casSteps = 0;
+          L.casIons = 1;
+          open = true;
+          L.prim_pcls = cls;
+          if (TR::kCustom && cls < 0)
+            build_custom_rows(P, S, rows, src_Z, src_m);
+          L.pcls = cls;
+          if (!EVENTS)
+            log_birth<TR>(P, L, src_Z);
+          active = true;
+          break;
         }
-        L.px = src.pos[0];
-        L.py = src.pos[1];
-        L.pz = src.pos[2];
-        L.dx = (float)src.dir[0];
-        L.dy = (float)src.dir[1];
-        L.dz = (float)src.dir[2];
-        L.E = src.E;
-        L.Ecur = (float)src.E;
-        L.ic = 0;
-        L.prim = P.first_index + idx;
-        L.uid = EVENTS ? P.single_uid : L.prim;
-        L.packed = SPECIES_PRIMARY | (((uint32_t)src.gen & GEN_MASK) << GEN_SHIFT) | FLAG_PRIMARY;
-        L.tag = src.tag;
-        L.pZ = src.Z;
-        L.pm = (float)src.m;
-        L.Ef = (float)src.Ef;
-        L.casEel = L.casEnuc = 0.0;
-        L.casVac = L.casRepl = L.casSteps = 0;
-        L.casIons = 1;
-        open = true;
-        L.prim_pcls = find_class(P, S, L.pZ, L.pm);
-        if (TR::kCustom && L.prim_pcls < 0)
-          build_custom_rows(P, S, rows, L.pZ, L.pm);
-        L.pcls = L.prim_pcls;
-        if (!EVENTS)
-          log_birth<TR>(P, L, L.pZ);
       }
-      active = true;
     }
 
+    if (MTB_WARP_ALL(done))
+      break;
+
+    if (active)
+      do
+      {
     // ---------------- one collision: trim.C:74-424 ----------------
     if (!(L.Ecur > 0.0f))
     {
       // the reference would produce NaNs for a projectile without energy; park it instead
       finish_ion<TR>(P, S, L, rows, MTB_INTERSTITIAL);
       active = false;
-      if (EVENTS)
-        break;
-      continue;
+      break;
     }
     ++L.ic;
     int cluster;
@@ -730,9 +752,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       --L.ic;
       finish_ion<TR>(P, S, L, rows, MTB_MOVING);
       active = false;
-      if (EVENTS)
-        break;
-      continue;
+      break;
     }
     const DevMaterial & M = S.materials[mi];
     const int mtag = (TR::kGeneric && P.geom_kind == MTB_GEOM_CLUSTERS && mi == 1) ? cluster : M.tag;
@@ -961,9 +981,9 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       if (state != MTB_MOVING)
       {
         finish_ion<TR>(P, S, L, rows, state);
-        break;
+        active = false;
       }
-      continue;
+      break;
     }
 
     // ---------------- who flies next ----------------
@@ -1026,6 +1046,10 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       finish_ion<TR>(P, S, L, rows, state);
       active = false;
     }
+      } while (0);
+
+    if (EVENTS && !active)
+      done = true; // single-ion mode ends with the ion
   }
 
   if (!EVENTS)
