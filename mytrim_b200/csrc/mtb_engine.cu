@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -198,6 +199,16 @@ transport_kernel(const __grid_constant__ LaunchParams P)
   flush_block(P, S);
 }
 
+__global__ void
+pool_init_kernel(PoolSlot * pool, unsigned long long * ctl, uint32_t capacity)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < capacity)
+    pool[i].seq = i;
+  if (i < POOL_CTL_COUNT)
+    ctl[i] = 0ull;
+}
+
 __global__ void __launch_bounds__(32)
 trim_one_kernel(const __grid_constant__ LaunchParams P)
 {
@@ -300,6 +311,10 @@ struct mtb_handle
   DevBuf<int32_t> d_tclass_elem;
   DevBuf<float4_t> d_custom_rows;
   DevBuf<uint32_t> d_deferred;
+  DevBuf<PoolSlot> d_pool;
+  DevBuf<unsigned long long> d_pool_ctl;
+  bool pool_ready = false;
+  bool share_enabled = true;
   bool deferred_pending = false;
   float extra_ms = 0.f;
   bool fast = false;
@@ -405,6 +420,8 @@ build_tables(mtb_handle * h)
   h->fast = fast_path_ok(P);
   MTB_CUDA(cudaFuncSetAttribute(transport_kernel<TraitsGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   MTB_CUDA(cudaFuncSetAttribute(transport_kernel<TraitsFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  MTB_CUDA(cudaFuncSetAttribute(transport_kernel<TraitsGenericShare>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  MTB_CUDA(cudaFuncSetAttribute(transport_kernel<TraitsFastShare>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   MTB_CUDA(cudaFuncSetAttribute(trim_one_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   MTB_CUDA(cudaFuncSetAttribute(stopping_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   int bps = 0;
@@ -428,6 +445,41 @@ ensure_ready(mtb_handle * h)
   return MTB_OK;
 }
 
+constexpr uint32_t kPoolCapacity = 1u << 16;
+
+// Launches with few primaries per lane let idle lanes adopt suspended ions from a shared pool.
+int
+prepare_pool(mtb_handle * h, LaunchParams & P, unsigned lanes)
+{
+  if (!h->pool_ready)
+  {
+    MTB_CUDA(h->d_pool.ensure(kPoolCapacity));
+    MTB_CUDA(h->d_pool_ctl.ensure(POOL_CTL_COUNT));
+    pool_init_kernel<<<(kPoolCapacity + 255) / 256, 256, 0, h->stream>>>(h->d_pool.p, h->d_pool_ctl.p, kPoolCapacity);
+    MTB_CUDA(cudaGetLastError());
+    h->pool_ready = true;
+  }
+  P.pool = h->d_pool.p;
+  P.pool_ctl = h->d_pool_ctl.p;
+  P.pool_mask = kPoolCapacity - 1;
+  const unsigned long long init[2] = {(unsigned long long)lanes, 0ull}; // POOL_WORKING, POOL_IDLE
+  MTB_CUDA(cudaMemcpyAsync(h->d_pool_ctl.p + POOL_WORKING, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+  return MTB_OK;
+}
+
+void
+launch_kernel(mtb_handle * h, const LaunchParams & P, unsigned blocks, bool fast, bool share)
+{
+  if (fast && share)
+    transport_kernel<TraitsFastShare><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+  else if (fast)
+    transport_kernel<TraitsFast><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+  else if (share)
+    transport_kernel<TraitsGenericShare><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+  else
+    transport_kernel<TraitsGeneric><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+}
+
 int
 launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, const mtb_ion * beam, uint64_t seed,
                  uint64_t first_index, bool want_records)
@@ -445,6 +497,7 @@ launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, cons
   {
     MTB_CUDA(h->d_records.ensure(n));
     P.records = h->d_records.p;
+    MTB_CUDA(cudaMemsetAsync(h->d_records.p, 0, n * sizeof(mtb_record), h->stream)); // lanes accumulate into them
   }
   h->records_valid = want_records;
   h->last_n = n;
@@ -452,7 +505,12 @@ launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, cons
     return MTB_OK;
   const uint64_t max_blocks = (uint64_t)h->sm_count * h->blocks_per_sm;
   const uint64_t want_blocks = (n + kBlock - 1) / kBlock;
-  const unsigned blocks = (unsigned)std::min(max_blocks, want_blocks);
+  // fewer than ~8 cascades per lane: the last wave dominates, let lanes share suspended ions
+  const bool share = h->share_enabled && n < 8ull * max_blocks * kBlock;
+  const unsigned blocks = (unsigned)(share ? max_blocks : std::min(max_blocks, want_blocks));
+  if (share)
+    if (int rc = prepare_pool(h, P, blocks * kBlock))
+      return rc;
   MTB_CUDA(h->d_stacks.ensure((size_t)blocks * kBlock * MTB_STACK_DEPTH));
   P.stacks = h->d_stacks.p;
   MTB_CUDA(h->d_custom_rows.ensure((size_t)blocks * kBlock * (size_t)(2 + P.n_materials + P.n_tclass)));
@@ -470,10 +528,7 @@ launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, cons
   MTB_CUDA(cudaMemsetAsync(&P.u64[CNT_NEXT_PRIMARY], 0, sizeof(unsigned long long), h->stream));
   MTB_CUDA(cudaMemsetAsync(&P.u64[CNT_DEFERRED], 0, sizeof(unsigned long long), h->stream));
   MTB_CUDA(cudaEventRecord(h->ev0, h->stream));
-  if (fast)
-    transport_kernel<TraitsFast><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
-  else
-    transport_kernel<TraitsGeneric><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+  launch_kernel(h, P, blocks, fast, share);
   MTB_CUDA(cudaGetLastError());
   MTB_CUDA(cudaEventRecord(h->ev1, h->stream));
   h->timing_pending = true;
@@ -497,13 +552,21 @@ run_deferred(mtb_handle * h)
   P.deferred = nullptr;
   P.n_primaries = nd;
   const uint64_t max_blocks = (uint64_t)h->sm_count * h->blocks_per_sm;
-  const unsigned blocks = (unsigned)std::min<uint64_t>(max_blocks, (nd + kBlock - 1) / kBlock);
+  const bool share = h->share_enabled && nd < 8ull * max_blocks * kBlock;
+  const unsigned blocks = (unsigned)(share ? max_blocks : std::min<uint64_t>(max_blocks, (nd + kBlock - 1) / kBlock));
+  if (share)
+    if (int rc = prepare_pool(h, P, blocks * kBlock))
+      return rc;
+  MTB_CUDA(h->d_stacks.ensure((size_t)blocks * kBlock * MTB_STACK_DEPTH));
+  P.stacks = h->d_stacks.p;
+  MTB_CUDA(h->d_custom_rows.ensure((size_t)blocks * kBlock * (size_t)(2 + P.n_materials + P.n_tclass)));
+  P.custom_rows = h->d_custom_rows.p;
   MTB_CUDA(cudaMemsetAsync(&P.u64[CNT_NEXT_PRIMARY], 0, sizeof(unsigned long long), h->stream));
   cudaEvent_t e0, e1;
   MTB_CUDA(cudaEventCreate(&e0));
   MTB_CUDA(cudaEventCreate(&e1));
   MTB_CUDA(cudaEventRecord(e0, h->stream));
-  transport_kernel<TraitsGeneric><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+  launch_kernel(h, P, blocks, false, share);
   MTB_CUDA(cudaGetLastError());
   MTB_CUDA(cudaEventRecord(e1, h->stream));
   MTB_CUDA(cudaStreamSynchronize(h->stream));
@@ -590,6 +653,8 @@ mtb_create(const mtb_config * cfg, mtb_handle ** out)
     return fail(MTB_ENOMEM, "out of memory");
   h->host.cfg = *cfg;
   h->device = cfg->device;
+  if (const char * env = std::getenv("MYTRIM_B200_NO_SHARE"))
+    h->share_enabled = env[0] == '0';
   h->sm_count = prop.multiProcessorCount;
   cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess)

@@ -55,22 +55,29 @@ host_fetch_max(T * p, U v)
 // LaunchParams; the fast variant fixes the options of the north-star workload (UNIVERSAL
 // potential, follow ALL, vacancies_created++, TrimVacCount depth tallies, solid/layered sample
 // without CUT boundaries) so that the unused hook code is not even in the instruction cache.
-struct TraitsGeneric
+template <bool SHARE>
+struct TraitsGenericT
 {
-  static constexpr bool kEvents = false, kGeneric = true, kCustom = true;
+  static constexpr bool kEvents = false, kGeneric = true, kCustom = true, kShare = SHARE;
   static constexpr uint32_t kTally = 0;
 };
+typedef TraitsGenericT<false> TraitsGeneric;
+typedef TraitsGenericT<true> TraitsGenericShare;
 struct TraitsEvents
 {
-  static constexpr bool kEvents = true, kGeneric = true, kCustom = true;
+  static constexpr bool kEvents = true, kGeneric = true, kCustom = true, kShare = false;
   static constexpr uint32_t kTally = 0;
 };
-struct TraitsFast
+template <bool SHARE>
+struct TraitsFastT
 {
   // kCustom = false: primaries whose species has no class are deferred to the generic kernel
-  static constexpr bool kEvents = false, kGeneric = false, kCustom = false;
+  // kShare: lanes that run out of primaries adopt suspended ions other lanes donate to a global pool
+  static constexpr bool kEvents = false, kGeneric = false, kCustom = false, kShare = SHARE;
   static constexpr uint32_t kTally = MTB_TALLY_VAC_DEPTH;
 };
+typedef TraitsFastT<false> TraitsFast;
+typedef TraitsFastT<true> TraitsFastShare;
 
 template <class TR>
 MTB_HD bool
@@ -596,28 +603,118 @@ vacancy_creation(const LaunchParams & P, const BlockCtx & S, Lane & L, const Dev
   }
 }
 
-// close a cascade: per-primary record + block totals
+// close a subtree of a cascade (the whole cascade unless lanes shared it): per-primary record and
+// block totals.  Record counters are accumulated atomically because several lanes may have worked
+// on the same primary; records are zeroed before the launch.
 MTB_HD void
-close_cascade(const LaunchParams & P, const BlockCtx & S, Lane & L)
+close_subtree(const LaunchParams & P, const BlockCtx & S, Lane & L, uint32_t n_prim)
 {
   if (P.records)
   {
     mtb_record & r = P.records[L.prim - P.first_index];
-    r.Eel = L.casEel;
-    r.Enuc = L.casEnuc;
-    r.vacancies = L.casVac;
-    r.replacements = L.casRepl;
-    r.steps = L.casSteps;
-    r.ions = L.casIons;
+    MTB_ATOMIC_ADD(&r.Eel, L.casEel);
+    MTB_ATOMIC_ADD(&r.Enuc, L.casEnuc);
+    MTB_ATOMIC_ADD(&r.vacancies, L.casVac);
+    MTB_ATOMIC_ADD(&r.replacements, L.casRepl);
+    MTB_ATOMIC_ADD(&r.steps, L.casSteps);
+    MTB_ATOMIC_ADD(&r.ions, L.casIons);
   }
   MTB_ATOMIC_ADD(&S.blk_u64[CNT_VAC], (unsigned long long)L.casVac);
   MTB_ATOMIC_ADD(&S.blk_u64[CNT_REPL], (unsigned long long)L.casRepl);
   MTB_ATOMIC_ADD(&S.blk_u64[CNT_STEPS], (unsigned long long)L.casSteps);
   MTB_ATOMIC_ADD(&S.blk_u64[CNT_IONS], (unsigned long long)L.casIons);
-  MTB_ATOMIC_ADD(&S.blk_u64[CNT_QUEUED], (unsigned long long)(L.casIons - 1u));
-  MTB_ATOMIC_ADD(&S.blk_u64[CNT_PRIMARIES], 1ull);
+  MTB_ATOMIC_ADD(&S.blk_u64[CNT_QUEUED], (unsigned long long)(L.casIons - n_prim));
+  MTB_ATOMIC_ADD(&S.blk_u64[CNT_PRIMARIES], (unsigned long long)n_prim);
   MTB_ATOMIC_ADD(&S.blk_f64[0], L.casEel);
   MTB_ATOMIC_ADD(&S.blk_f64[1], L.casEnuc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// work-sharing pool (device only): bounded MPMC ring after D. Vyukov.  Both operations are
+// non-blocking attempts; a lane that fails simply keeps its ion / polls again next iteration.
+// ---------------------------------------------------------------------------------------------
+#if MTB_DEVICE_CODE
+MTB_D unsigned long long
+vload(const unsigned long long * p)
+{
+  return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+
+MTB_D bool
+pool_try_push(const LaunchParams & P, const Lane & ion, uint64_t prim)
+{
+  unsigned long long pos = vload(&P.pool_ctl[POOL_ENQ]);
+  for (int tries = 0; tries < 4; ++tries)
+  {
+    PoolSlot * slot = P.pool + (pos & P.pool_mask);
+    const long long dif = (long long)(vload(&slot->seq) - pos);
+    if (dif == 0)
+    {
+      const unsigned long long seen = atomicCAS(&P.pool_ctl[POOL_ENQ], pos, pos + 1);
+      if (seen == pos)
+      {
+        atomicAdd(&P.pool_ctl[POOL_WORKING], 1ull); // the entry counts as outstanding work from now on
+        slot->prim = prim;
+        stack_store(&slot->e, ion);
+        __threadfence();
+        *reinterpret_cast<volatile unsigned long long *>(&slot->seq) = pos + 1;
+        return true;
+      }
+      pos = seen;
+    }
+    else if (dif < 0)
+      return false; // full
+    else
+      pos = vload(&P.pool_ctl[POOL_ENQ]);
+  }
+  return false;
+}
+
+MTB_D bool
+pool_try_pop(const LaunchParams & P, Lane & ion, uint64_t * prim)
+{
+  unsigned long long pos = vload(&P.pool_ctl[POOL_DEQ]);
+  for (int tries = 0; tries < 4; ++tries)
+  {
+    PoolSlot * slot = P.pool + (pos & P.pool_mask);
+    const long long dif = (long long)(vload(&slot->seq) - (pos + 1));
+    if (dif == 0)
+    {
+      const unsigned long long seen = atomicCAS(&P.pool_ctl[POOL_DEQ], pos, pos + 1);
+      if (seen == pos)
+      {
+        __threadfence();
+        *prim = slot->prim;
+        stack_load(&slot->e, ion);
+        __threadfence();
+        *reinterpret_cast<volatile unsigned long long *>(&slot->seq) = pos + P.pool_mask + 1;
+        return true;
+      }
+      pos = seen;
+    }
+    else if (dif < 0)
+      return false; // empty
+    else
+      pos = vload(&P.pool_ctl[POOL_DEQ]);
+  }
+  return false;
+}
+#endif
+
+// Suspend an ion: on the lane's private stack, or — when lanes are idle — in the shared pool.
+template <class TR>
+MTB_HD void
+suspend_ion(const LaunchParams & P, StackEntry * stack, int & sp, const Lane & ion, uint64_t prim)
+{
+#if MTB_DEVICE_CODE
+  if (TR::kShare && vload(&P.pool_ctl[POOL_IDLE]) > 0 && pool_try_push(P, ion, prim))
+    return;
+#endif
+  (void)prim;
+  if (sp < MTB_STACK_DEPTH)
+    stack_store(stack + sp++, ion);
+  else
+    MTB_ATOMIC_ADD(&P.u64[CNT_ERROR], 1ull);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -635,7 +732,9 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
   float4_t * const rows =
       TR::kCustom ? P.custom_rows + (size_t)lane_global * (size_t)(2 + P.n_materials + P.n_tclass) : nullptr;
   int sp = 0, sp_max = 0;
-  bool active = false, open = false, started = false, done = false;
+  bool active = false, open = false, started = false, done = false, no_more = false, idle = false;
+  uint32_t cas_prim = 0;
+  unsigned long long idle_polls = 0;
   unsigned long long n_events = 0;
   L.prim = 0;
   L.casEel = L.casEnuc = 0.0;
@@ -661,17 +760,17 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       {
         if (open)
         {
-          close_cascade(P, S, L);
+          close_subtree(P, S, L, cas_prim);
           open = false;
         }
-        for (;;)
+        while (!no_more)
         {
           unsigned long long idx;
           if (EVENTS)
           {
             if (started || lane_global != 0)
             {
-              done = true;
+              no_more = true;
               break;
             }
             idx = 0;
@@ -681,7 +780,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           started = true;
           if (idx >= P.n_primaries)
           {
-            done = true;
+            no_more = true;
             break;
           }
           if (P.index_list)
@@ -715,6 +814,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           L.casEel = L.casEnuc = 0.0;
           L.casVac = L.casRepl = L.casSteps = 0;
           L.casIons = 1;
+          cas_prim = 1;
           open = true;
           L.prim_pcls = cls;
           if (TR::kCustom && cls < 0)
@@ -725,11 +825,60 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           active = true;
           break;
         }
+        if (!active)
+        {
+          // out of primaries: either done, or (work sharing) adopt what other lanes donate
+#if MTB_DEVICE_CODE
+          if (TR::kShare)
+          {
+            if (!idle)
+            {
+              idle = true;
+              atomicAdd(&P.pool_ctl[POOL_IDLE], 1ull);
+              atomicAdd(&P.pool_ctl[POOL_WORKING], (unsigned long long)-1ll);
+            }
+            uint64_t aprim;
+            if (pool_try_pop(P, L, &aprim))
+            {
+              // the entry carried its own count in POOL_WORKING; it now belongs to this lane
+              idle = false;
+              atomicAdd(&P.pool_ctl[POOL_IDLE], (unsigned long long)-1ll);
+              const mtb_ion & src = P.primaries ? P.primaries[aprim - P.first_index] : P.beam;
+              L.prim = aprim;
+              L.pZ = src.Z;
+              L.pm = (float)src.m;
+              L.Ef = (float)src.Ef;
+              L.prim_pcls = find_class(P, S, L.pZ, L.pm);
+              if (TR::kCustom && L.prim_pcls < 0)
+                build_custom_rows(P, S, rows, L.pZ, L.pm);
+              set_species(L, S);
+              L.casEel = L.casEnuc = 0.0;
+              L.casVac = L.casRepl = L.casSteps = L.casIons = 0;
+              cas_prim = 0;
+              open = true;
+              active = true;
+            }
+            else if (vload(&P.pool_ctl[POOL_WORKING]) == 0)
+              done = true;
+            else if (++idle_polls > (1ull << 26))
+            {
+              atomicAdd(&P.u64[CNT_ERROR], 1ull); // watchdog: never spin forever on an accounting bug
+              done = true;
+            }
+          }
+          else
+#endif
+            done = true;
+        }
       }
     }
 
     if (MTB_WARP_ALL(done))
       break;
+#if MTB_DEVICE_CODE
+    if (TR::kShare && MTB_WARP_ALL(!active))
+      __nanosleep(1000); // the whole warp is polling: back off
+#endif
 
     if (active)
       do
@@ -997,10 +1146,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       if (state == MTB_MOVING && !keep_projectile)
       {
         // both move on and the recoil has less energy: suspend the projectile, fly the recoil
-        if (sp < MTB_STACK_DEPTH)
-          stack_store(stack + sp++, L);
-        else
-          MTB_ATOMIC_ADD(&P.u64[CNT_ERROR], 1ull);
+        suspend_ion<TR>(P, stack, sp, L, L.prim);
       }
       if (state != MTB_MOVING)
         finish_ion<TR>(P, S, L, rows, state);
@@ -1020,10 +1166,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           R.prim = L.prim;
           log_birth<TR>(P, R, el.Z);
         }
-        if (sp < MTB_STACK_DEPTH)
-          stack_store(stack + sp++, R);
-        else
-          MTB_ATOMIC_ADD(&P.u64[CNT_ERROR], 1ull);
+        suspend_ion<TR>(P, stack, sp, R, L.prim);
       }
       else
       {

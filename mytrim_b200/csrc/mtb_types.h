@@ -156,6 +156,25 @@ struct __attribute__((aligned(16))) float4_t
   float x, y, z, w;
 };
 
+// Slot of the work-sharing pool (bounded multi-producer multi-consumer ring, D. Vyukov's scheme):
+// a suspended ion plus the primary it belongs to.
+struct __attribute__((aligned(16))) PoolSlot
+{
+  unsigned long long seq;
+  uint64_t prim;
+  StackEntry e;
+};
+static_assert(sizeof(PoolSlot) == 80, "PoolSlot layout");
+
+enum
+{
+  POOL_ENQ = 0,     // enqueue ticket
+  POOL_DEQ = 1,     // dequeue ticket
+  POOL_WORKING = 2, // lanes that hold work + entries in the pool; 0 <=> nothing left anywhere
+  POOL_IDLE = 3,    // lanes polling the pool
+  POOL_CTL_COUNT = 4
+};
+
 struct RangeEntry
 {
   float x;
@@ -215,6 +234,10 @@ struct LaunchParams
   RangeEntry * range;
   unsigned long long range_cap;
   StackEntry * stacks;          // [lanes][MTB_STACK_DEPTH]
+  // work sharing between lanes (launches with fewer primaries than lanes)
+  PoolSlot * pool;
+  unsigned long long * pool_ctl; // [POOL_CTL_COUNT]
+  uint32_t pool_mask;            // capacity - 1 (power of two)
   // single-ion event mode
   mtb_event * events;
   unsigned long long events_cap;
