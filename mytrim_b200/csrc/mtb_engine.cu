@@ -57,7 +57,7 @@ constexpr int kMinBlocks = MTB_MIN_BLOCKS;
 // ---------------------------------------------------------------------------------------------
 struct SmemLayout
 {
-  size_t elements, materials, ionz, lowstop, pclass, pairm, paire, layer_cum, layer_mat, hist_vac, hist_repl, blk_u64, blk_f64, total;
+  size_t elements, materials, ionz, lowstop, pclass, pairm, paire, layer_cum, layer_mat, hist_vac, hist_repl, blk_u64, blk_f64, pool, pool_ctl, total;
 };
 
 __host__ __device__ inline size_t
@@ -97,6 +97,10 @@ smem_layout(const LaunchParams & P)
   o += (size_t)P.smem_hist_bins * sizeof(unsigned int);
   L.hist_repl = o;
   o += (size_t)P.smem_hist_bins * sizeof(unsigned int);
+  L.pool = o = align_up(o, 16);
+  o += MTB_POOL_SLOTS * sizeof(PoolSlot);
+  L.pool_ctl = o;
+  o += POOL_CTL_COUNT * sizeof(unsigned long long);
   L.total = align_up(o, 16);
   return L;
 }
@@ -148,6 +152,12 @@ stage_block(const LaunchParams & P, unsigned char * smem)
     bu[threadIdx.x] = 0ull;
   if (threadIdx.x < 2)
     bf[threadIdx.x] = 0.0;
+  PoolSlot * pool = reinterpret_cast<PoolSlot *>(smem + L.pool);
+  unsigned long long * pctl = reinterpret_cast<unsigned long long *>(smem + L.pool_ctl);
+  if (threadIdx.x < MTB_POOL_SLOTS)
+    pool[threadIdx.x].seq = threadIdx.x;
+  if (threadIdx.x < POOL_CTL_COUNT)
+    pctl[threadIdx.x] = threadIdx.x == POOL_WORKING ? (unsigned long long)blockDim.x : 0ull;
   __syncthreads();
   S.elements = el;
   S.materials = mat;
@@ -162,6 +172,8 @@ stage_block(const LaunchParams & P, unsigned char * smem)
   S.hist_repl = hr;
   S.blk_u64 = bu;
   S.blk_f64 = bf;
+  S.pool = pool;
+  S.pool_ctl = pctl;
   return S;
 }
 
@@ -197,16 +209,6 @@ transport_kernel(const __grid_constant__ LaunchParams P)
   const BlockCtx S = stage_block(P, smem);
   lane_loop<TR>(P, S, blockIdx.x * blockDim.x + threadIdx.x);
   flush_block(P, S);
-}
-
-__global__ void
-pool_init_kernel(PoolSlot * pool, unsigned long long * ctl, uint32_t capacity)
-{
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < capacity)
-    pool[i].seq = i;
-  if (i < POOL_CTL_COUNT)
-    ctl[i] = 0ull;
 }
 
 __global__ void __launch_bounds__(32)
@@ -311,9 +313,6 @@ struct mtb_handle
   DevBuf<int32_t> d_tclass_elem;
   DevBuf<float4_t> d_custom_rows;
   DevBuf<uint32_t> d_deferred;
-  DevBuf<PoolSlot> d_pool;
-  DevBuf<unsigned long long> d_pool_ctl;
-  bool pool_ready = false;
   bool share_enabled = true;
   bool deferred_pending = false;
   float extra_ms = 0.f;
@@ -445,28 +444,6 @@ ensure_ready(mtb_handle * h)
   return MTB_OK;
 }
 
-constexpr uint32_t kPoolCapacity = 1u << 16;
-
-// Launches with few primaries per lane let idle lanes adopt suspended ions from a shared pool.
-int
-prepare_pool(mtb_handle * h, LaunchParams & P, unsigned lanes)
-{
-  if (!h->pool_ready)
-  {
-    MTB_CUDA(h->d_pool.ensure(kPoolCapacity));
-    MTB_CUDA(h->d_pool_ctl.ensure(POOL_CTL_COUNT));
-    pool_init_kernel<<<(kPoolCapacity + 255) / 256, 256, 0, h->stream>>>(h->d_pool.p, h->d_pool_ctl.p, kPoolCapacity);
-    MTB_CUDA(cudaGetLastError());
-    h->pool_ready = true;
-  }
-  P.pool = h->d_pool.p;
-  P.pool_ctl = h->d_pool_ctl.p;
-  P.pool_mask = kPoolCapacity - 1;
-  const unsigned long long init[2] = {(unsigned long long)lanes, 0ull}; // POOL_WORKING, POOL_IDLE
-  MTB_CUDA(cudaMemcpyAsync(h->d_pool_ctl.p + POOL_WORKING, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
-  return MTB_OK;
-}
-
 void
 launch_kernel(mtb_handle * h, const LaunchParams & P, unsigned blocks, bool fast, bool share)
 {
@@ -508,9 +485,6 @@ launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, cons
   // fewer than ~8 cascades per lane: the last wave dominates, let lanes share suspended ions
   const bool share = h->share_enabled && n < 8ull * max_blocks * kBlock;
   const unsigned blocks = (unsigned)(share ? max_blocks : std::min(max_blocks, want_blocks));
-  if (share)
-    if (int rc = prepare_pool(h, P, blocks * kBlock))
-      return rc;
   MTB_CUDA(h->d_stacks.ensure((size_t)blocks * kBlock * MTB_STACK_DEPTH));
   P.stacks = h->d_stacks.p;
   MTB_CUDA(h->d_custom_rows.ensure((size_t)blocks * kBlock * (size_t)(2 + P.n_materials + P.n_tclass)));
@@ -554,9 +528,6 @@ run_deferred(mtb_handle * h)
   const uint64_t max_blocks = (uint64_t)h->sm_count * h->blocks_per_sm;
   const bool share = h->share_enabled && nd < 8ull * max_blocks * kBlock;
   const unsigned blocks = (unsigned)(share ? max_blocks : std::min<uint64_t>(max_blocks, (nd + kBlock - 1) / kBlock));
-  if (share)
-    if (int rc = prepare_pool(h, P, blocks * kBlock))
-      return rc;
   MTB_CUDA(h->d_stacks.ensure((size_t)blocks * kBlock * MTB_STACK_DEPTH));
   P.stacks = h->d_stacks.p;
   MTB_CUDA(h->d_custom_rows.ensure((size_t)blocks * kBlock * (size_t)(2 + P.n_materials + P.n_tclass)));

@@ -112,6 +112,8 @@ struct BlockCtx
   unsigned int * hist_repl; // [smem_hist_bins] or null
   unsigned long long * blk_u64; // [CNT_COUNT]
   double * blk_f64;             // [2]
+  PoolSlot * pool;               // [MTB_POOL_SLOTS] work-sharing ring of this CTA (share kernels)
+  unsigned long long * pool_ctl; // [POOL_CTL_COUNT]
 };
 
 MTB_HD size_t
@@ -630,8 +632,12 @@ close_subtree(const LaunchParams & P, const BlockCtx & S, Lane & L, uint32_t n_p
 }
 
 // ---------------------------------------------------------------------------------------------
-// work-sharing pool (device only): bounded MPMC ring after D. Vyukov.  Both operations are
-// non-blocking attempts; a lane that fails simply keeps its ion / polls again next iteration.
+// work-sharing pool (device only): one bounded MPMC ring (after D. Vyukov) per CTA in shared memory.
+// When a launch has fewer primaries than lanes, lanes without work adopt suspended ions that busy
+// lanes of the same CTA donate instead of pushing them on their private stacks; a heavy cascade
+// fans out over the CTA within a few generations.  Both operations are non-blocking attempts.
+// (A single device-wide ring was measured first: 1e5 polling lanes on one L2 line made the kernel
+// 50x slower.  Shared memory has no such problem.)
 // ---------------------------------------------------------------------------------------------
 #if MTB_DEVICE_CODE
 MTB_D unsigned long long
@@ -641,22 +647,23 @@ vload(const unsigned long long * p)
 }
 
 MTB_D bool
-pool_try_push(const LaunchParams & P, const Lane & ion, uint64_t prim)
+pool_try_push(const BlockCtx & S, const Lane & ion, uint64_t prim)
 {
-  unsigned long long pos = vload(&P.pool_ctl[POOL_ENQ]);
+  const unsigned long long mask = MTB_POOL_SLOTS - 1;
+  unsigned long long pos = vload(&S.pool_ctl[POOL_ENQ]);
   for (int tries = 0; tries < 4; ++tries)
   {
-    PoolSlot * slot = P.pool + (pos & P.pool_mask);
+    PoolSlot * slot = S.pool + (pos & mask);
     const long long dif = (long long)(vload(&slot->seq) - pos);
     if (dif == 0)
     {
-      const unsigned long long seen = atomicCAS(&P.pool_ctl[POOL_ENQ], pos, pos + 1);
+      const unsigned long long seen = atomicCAS(&S.pool_ctl[POOL_ENQ], pos, pos + 1);
       if (seen == pos)
       {
-        atomicAdd(&P.pool_ctl[POOL_WORKING], 1ull); // the entry counts as outstanding work from now on
+        atomicAdd(&S.pool_ctl[POOL_WORKING], 1ull); // the entry counts as outstanding work from now on
         slot->prim = prim;
         stack_store(&slot->e, ion);
-        __threadfence();
+        __threadfence_block();
         *reinterpret_cast<volatile unsigned long long *>(&slot->seq) = pos + 1;
         return true;
       }
@@ -665,29 +672,30 @@ pool_try_push(const LaunchParams & P, const Lane & ion, uint64_t prim)
     else if (dif < 0)
       return false; // full
     else
-      pos = vload(&P.pool_ctl[POOL_ENQ]);
+      pos = vload(&S.pool_ctl[POOL_ENQ]);
   }
   return false;
 }
 
 MTB_D bool
-pool_try_pop(const LaunchParams & P, Lane & ion, uint64_t * prim)
+pool_try_pop(const BlockCtx & S, Lane & ion, uint64_t * prim)
 {
-  unsigned long long pos = vload(&P.pool_ctl[POOL_DEQ]);
+  const unsigned long long mask = MTB_POOL_SLOTS - 1;
+  unsigned long long pos = vload(&S.pool_ctl[POOL_DEQ]);
   for (int tries = 0; tries < 4; ++tries)
   {
-    PoolSlot * slot = P.pool + (pos & P.pool_mask);
+    PoolSlot * slot = S.pool + (pos & mask);
     const long long dif = (long long)(vload(&slot->seq) - (pos + 1));
     if (dif == 0)
     {
-      const unsigned long long seen = atomicCAS(&P.pool_ctl[POOL_DEQ], pos, pos + 1);
+      const unsigned long long seen = atomicCAS(&S.pool_ctl[POOL_DEQ], pos, pos + 1);
       if (seen == pos)
       {
-        __threadfence();
+        __threadfence_block();
         *prim = slot->prim;
         stack_load(&slot->e, ion);
-        __threadfence();
-        *reinterpret_cast<volatile unsigned long long *>(&slot->seq) = pos + P.pool_mask + 1;
+        __threadfence_block();
+        *reinterpret_cast<volatile unsigned long long *>(&slot->seq) = pos + mask + 1;
         return true;
       }
       pos = seen;
@@ -695,7 +703,7 @@ pool_try_pop(const LaunchParams & P, Lane & ion, uint64_t * prim)
     else if (dif < 0)
       return false; // empty
     else
-      pos = vload(&P.pool_ctl[POOL_DEQ]);
+      pos = vload(&S.pool_ctl[POOL_DEQ]);
   }
   return false;
 }
@@ -704,12 +712,13 @@ pool_try_pop(const LaunchParams & P, Lane & ion, uint64_t * prim)
 // Suspend an ion: on the lane's private stack, or — when lanes are idle — in the shared pool.
 template <class TR>
 MTB_HD void
-suspend_ion(const LaunchParams & P, StackEntry * stack, int & sp, const Lane & ion, uint64_t prim)
+suspend_ion(const LaunchParams & P, const BlockCtx & S, StackEntry * stack, int & sp, const Lane & ion, uint64_t prim)
 {
 #if MTB_DEVICE_CODE
-  if (TR::kShare && vload(&P.pool_ctl[POOL_IDLE]) > 0 && pool_try_push(P, ion, prim))
+  if (TR::kShare && vload(&S.pool_ctl[POOL_IDLE]) > 0 && pool_try_push(S, ion, prim))
     return;
 #endif
+  (void)S;
   (void)prim;
   if (sp < MTB_STACK_DEPTH)
     stack_store(stack + sp++, ion);
@@ -834,15 +843,15 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
             if (!idle)
             {
               idle = true;
-              atomicAdd(&P.pool_ctl[POOL_IDLE], 1ull);
-              atomicAdd(&P.pool_ctl[POOL_WORKING], (unsigned long long)-1ll);
+              atomicAdd(&S.pool_ctl[POOL_IDLE], 1ull);
+              atomicAdd(&S.pool_ctl[POOL_WORKING], (unsigned long long)-1ll);
             }
             uint64_t aprim;
-            if (pool_try_pop(P, L, &aprim))
+            if (pool_try_pop(S, L, &aprim))
             {
               // the entry carried its own count in POOL_WORKING; it now belongs to this lane
               idle = false;
-              atomicAdd(&P.pool_ctl[POOL_IDLE], (unsigned long long)-1ll);
+              atomicAdd(&S.pool_ctl[POOL_IDLE], (unsigned long long)-1ll);
               const mtb_ion & src = P.primaries ? P.primaries[aprim - P.first_index] : P.beam;
               L.prim = aprim;
               L.pZ = src.Z;
@@ -858,7 +867,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
               open = true;
               active = true;
             }
-            else if (vload(&P.pool_ctl[POOL_WORKING]) == 0)
+            else if (vload(&S.pool_ctl[POOL_WORKING]) == 0)
               done = true;
             else if (++idle_polls > (1ull << 26))
             {
@@ -877,7 +886,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       break;
 #if MTB_DEVICE_CODE
     if (TR::kShare && MTB_WARP_ALL(!active))
-      __nanosleep(1000); // the whole warp is polling: back off
+      __nanosleep(400); // the whole warp is polling: back off
 #endif
 
     if (active)
@@ -1146,7 +1155,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       if (state == MTB_MOVING && !keep_projectile)
       {
         // both move on and the recoil has less energy: suspend the projectile, fly the recoil
-        suspend_ion<TR>(P, stack, sp, L, L.prim);
+        suspend_ion<TR>(P, S, stack, sp, L, L.prim);
       }
       if (state != MTB_MOVING)
         finish_ion<TR>(P, S, L, rows, state);
@@ -1166,7 +1175,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           R.prim = L.prim;
           log_birth<TR>(P, R, el.Z);
         }
-        suspend_ion<TR>(P, stack, sp, R, L.prim);
+        suspend_ion<TR>(P, S, stack, sp, R, L.prim);
       }
       else
       {

@@ -156,8 +156,8 @@ struct __attribute__((aligned(16))) float4_t
   float x, y, z, w;
 };
 
-// Slot of the work-sharing pool (bounded multi-producer multi-consumer ring, D. Vyukov's scheme):
-// a suspended ion plus the primary it belongs to.
+// Slot of a CTA's work-sharing pool in shared memory (bounded multi-producer multi-consumer ring,
+// D. Vyukov's scheme): a suspended ion plus the primary it belongs to.
 struct __attribute__((aligned(16))) PoolSlot
 {
   unsigned long long seq;
@@ -174,6 +174,7 @@ enum
   POOL_IDLE = 3,    // lanes polling the pool
   POOL_CTL_COUNT = 4
 };
+#define MTB_POOL_SLOTS 32 // per CTA, power of two
 
 struct RangeEntry
 {
@@ -234,10 +235,6 @@ struct LaunchParams
   RangeEntry * range;
   unsigned long long range_cap;
   StackEntry * stacks;          // [lanes][MTB_STACK_DEPTH]
-  // work sharing between lanes (launches with fewer primaries than lanes)
-  PoolSlot * pool;
-  unsigned long long * pool_ctl; // [POOL_CTL_COUNT]
-  uint32_t pool_mask;            // capacity - 1 (power of two)
   // single-ion event mode
   mtb_event * events;
   unsigned long long events_cap;

@@ -91,6 +91,8 @@ hs_ctx(hs_engine * e)
   S.hist_repl = e->hist.data() + e->P.smem_hist_bins;
   S.blk_u64 = e->blk_u64;
   S.blk_f64 = e->blk_f64;
+  S.pool = nullptr;
+  S.pool_ctl = nullptr;
   std::memset(e->blk_u64, 0, sizeof(e->blk_u64));
   e->blk_f64[0] = e->blk_f64[1] = 0.0;
   std::fill(e->hist.begin(), e->hist.end(), 0u);

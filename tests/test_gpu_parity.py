@@ -285,18 +285,16 @@ def test_fast_kernel_defers_unknown_species():
         util.setup_engine(b, "cu_on_cu_10keV")
         ra = a.run(ions, seed=4, records=True)
         rb = b.run(ions, seed=4, records=True)
-        custom = np.ones(len(ions), dtype=bool)
-        custom[::3] = False
-        for f in ra.dtype.names:
-            if f != "Enuc":
-                # deferred primaries run through the same (generic) kernel in both engines: bit-identical
-                assert np.array_equal(ra[f][custom], rb[f][custom]), f
-        # the Cu primaries go through two different instantiations (FMA contraction differs): 1e-5
-        cu = ~custom
-        same = (ra["steps"][cu] == rb["steps"][cu]) & (ra["vacancies"][cu] == rb["vacancies"][cu])
-        assert same.mean() > 0.97
-        d = np.linalg.norm(ra["pos"][cu] - rb["pos"][cu], axis=1) / np.maximum(np.linalg.norm(ra["pos"][cu], axis=1), 1.0)
-        assert (d[ra["primary_steps"][cu] == rb["primary_steps"][cu]] >= TOL).sum() <= 5
+        # Primaries with a projectile class (the Cu ions and the first 16 distinct species, which the
+        # host registers) run in the fast instantiation in `a` and in the generic one in `b`; the rest
+        # are deferred to the generic kernel in `a`.  Different instantiations contract FMAs
+        # differently, so agreement is to the trajectory tolerance, not bitwise.
+        same = (ra["steps"] == rb["steps"]) & (ra["vacancies"] == rb["vacancies"]) & (ra["ions"] == rb["ions"])
+        assert same.mean() > 0.97, same.mean()
+        sel = ra["primary_steps"] == rb["primary_steps"]
+        d = np.linalg.norm(ra["pos"] - rb["pos"], axis=1) / np.maximum(np.linalg.norm(ra["pos"] - ions["pos"], axis=1), 1.0)
+        assert (d[sel] >= TOL).sum() <= 0.005 * len(ions) + 2
+        assert (ra["state"] == rb["state"]).mean() > 0.99
         ca, cb = a.counters(), b.counters()
         assert abs(ca["steps"] - cb["steps"]) <= 1e-3 * cb["steps"] and ca["primaries"] == cb["primaries"] == len(ions)
 
