@@ -100,7 +100,7 @@ smem_layout(const LaunchParams & P)
   L.pool = o = align_up(o, 16);
   o += MTB_POOL_SLOTS * sizeof(PoolSlot);
   L.pool_ctl = o;
-  o += POOL_CTL_COUNT * sizeof(unsigned long long);
+  o += (POOL_CTL_COUNT + 1) * sizeof(unsigned long long); // + the CTA-local primary counter
   L.total = align_up(o, 16);
   return L;
 }
@@ -156,7 +156,7 @@ stage_block(const LaunchParams & P, unsigned char * smem)
   unsigned long long * pctl = reinterpret_cast<unsigned long long *>(smem + L.pool_ctl);
   if (threadIdx.x < MTB_POOL_SLOTS)
     pool[threadIdx.x].seq = threadIdx.x;
-  if (threadIdx.x < POOL_CTL_COUNT)
+  if (threadIdx.x <= POOL_CTL_COUNT)
     pctl[threadIdx.x] = threadIdx.x == POOL_WORKING ? (unsigned long long)blockDim.x : 0ull;
   __syncthreads();
   S.elements = el;

@@ -292,7 +292,7 @@ struct Lane
   int32_t tag;
   int32_t pcls;    // projectile class of the ion in flight, -1: this lane's per-primary rows
   // current cascade
-  uint64_t prim;
+  uint32_t prim;   // index of the cascade's primary within this launch (global = first_index + prim)
   int32_t prim_pcls;
   int32_t pZ;
   float pm, Ef;
@@ -469,7 +469,7 @@ log_birth(const LaunchParams & P, const Lane & L, int Z)
   o.E0 = L.E;
   o.E1 = 0.0;
   o.uid = L.uid;
-  o.primary = L.prim;
+  o.primary = P.first_index + L.prim;
   o.Z = Z;
   o.gen = (int32_t)((L.packed >> GEN_SHIFT) & GEN_MASK);
   o.tag = L.tag;
@@ -483,7 +483,7 @@ finish_ion(const LaunchParams & P, const BlockCtx & S, const Lane & L, const flo
 {
   if ((L.packed & FLAG_PRIMARY) && P.records)
   {
-    mtb_record & r = P.records[L.prim - P.first_index];
+    mtb_record & r = P.records[L.prim];
     r.pos[0] = L.px;
     r.pos[1] = L.py;
     r.pos[2] = L.pz;
@@ -507,7 +507,7 @@ finish_ion(const LaunchParams & P, const BlockCtx & S, const Lane & L, const flo
     o.E0 = 0.0;
     o.E1 = L.E;
     o.uid = L.uid;
-    o.primary = L.prim;
+    o.primary = P.first_index + L.prim;
     o.Z = Z;
     o.gen = (int32_t)((L.packed >> GEN_SHIFT) & GEN_MASK);
     o.tag = L.tag;
@@ -613,7 +613,7 @@ close_subtree(const LaunchParams & P, const BlockCtx & S, Lane & L, uint32_t n_p
 {
   if (P.records)
   {
-    mtb_record & r = P.records[L.prim - P.first_index];
+    mtb_record & r = P.records[L.prim];
     MTB_ATOMIC_ADD(&r.Eel, L.casEel);
     MTB_ATOMIC_ADD(&r.Enuc, L.casEnuc);
     MTB_ATOMIC_ADD(&r.vacancies, L.casVac);
@@ -769,7 +769,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       {
         if (open)
         {
-          close_subtree(P, S, L, cas_prim);
+          close_subtree(P, S, L, TR::kShare ? cas_prim : 1u);
           open = false;
         }
         while (!no_more)
@@ -784,6 +784,14 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
             }
             idx = 0;
           }
+#if MTB_DEVICE_CODE
+          else if (TR::kShare)
+          {
+            // few primaries per lane: deal them round-robin over the CTAs (CTA-local counter) so that
+            // every CTA has something to share among its lanes
+            idx = (unsigned long long)blockIdx.x + (unsigned long long)gridDim.x * atomicAdd(&S.pool_ctl[POOL_CTL_COUNT], 1ull);
+          }
+#endif
           else
             idx = MTB_ATOMIC_ADD(&P.u64[CNT_NEXT_PRIMARY], 1ull);
           started = true;
@@ -813,8 +821,8 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           L.E = src.E;
           L.Ecur = (float)src.E;
           L.ic = 0;
-          L.prim = P.first_index + idx;
-          L.uid = EVENTS ? P.single_uid : L.prim;
+          L.prim = (uint32_t)idx;
+          L.uid = EVENTS ? P.single_uid : P.first_index + idx;
           L.packed = SPECIES_PRIMARY | (((uint32_t)src.gen & GEN_MASK) << GEN_SHIFT) | FLAG_PRIMARY;
           L.tag = src.tag;
           L.pZ = src_Z;
@@ -852,8 +860,8 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
               // the entry carried its own count in POOL_WORKING; it now belongs to this lane
               idle = false;
               atomicAdd(&S.pool_ctl[POOL_IDLE], (unsigned long long)-1ll);
-              const mtb_ion & src = P.primaries ? P.primaries[aprim - P.first_index] : P.beam;
-              L.prim = aprim;
+              const mtb_ion & src = P.primaries ? P.primaries[aprim] : P.beam;
+              L.prim = (uint32_t)aprim;
               L.pZ = src.Z;
               L.pm = (float)src.m;
               L.Ef = (float)src.Ef;
@@ -1190,8 +1198,8 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
         L.pcls = el.tcls;
         log_birth<TR>(P, L, el.Z);
       }
-      if (sp > sp_max)
-        sp_max = sp;
+      if (TR::kGeneric && sp > sp_max)
+        sp_max = sp; // diagnostic high-water mark (generic kernels only)
     }
     else if (state != MTB_MOVING)
     {
