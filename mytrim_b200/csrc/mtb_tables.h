@@ -32,7 +32,7 @@ builtin_zbl()
   return rows;
 }
 
-constexpr int kSmemHistMax = 4096;
+constexpr int kSmemHistMax = 2048; // depth bins mirrored per CTA in shared memory (2 x 8 KB)
 
 // ZBL proton stopping in double — MaterialBase::rpstop, material.C:133-158
 inline double

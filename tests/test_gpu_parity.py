@@ -84,8 +84,15 @@ def test_sharding_invariance():
         ra = a.run(ions, seed=77, records=True)
         rb = np.concatenate([b.run(ions[:1100], seed=77, first_index=0, records=True),
                              b.run(ions[1100:], seed=77, first_index=1100, records=True)])
-        for f in ra.dtype.names:
-            assert np.array_equal(ra[f], rb[f]), f
+
+        def same_records(x, y):
+            for f in x.dtype.names:
+                if f in ("Eel", "Enuc"):   # sums of per-lane partial sums: order of addition is not fixed
+                    assert np.allclose(x[f], y[f], rtol=1e-12, atol=0), f
+                else:
+                    assert np.array_equal(x[f], y[f]), f
+
+        same_records(ra, rb)
         va, _ = a.vac_depth()
         vb, _ = b.vac_depth()
         assert np.array_equal(va, vb)
@@ -94,8 +101,7 @@ def test_sharding_invariance():
         # beam mode (template ion) is the same thing without the per-primary host array
         b.reset_tallies()
         rc = b.run_beam(3000, ions[0], seed=77, records=True)
-        for f in ra.dtype.names:
-            assert np.array_equal(ra[f], rc[f]), f
+        same_records(ra, rc)
 
 
 def test_follow_policies_and_vacancy_models():
@@ -267,7 +273,10 @@ def test_pinned_host_primaries_are_read_in_place():
         lib = capi.load_library()
         assert lib.mtb_run(b._h, n, pinned.data_ptr(), 8, 0, rb.ctypes.data) == 0, lib.mtb_last_error()
         for f in ra.dtype.names:
-            assert np.array_equal(ra[f], rb[f]), f
+            if f in ("Eel", "Enuc"):
+                assert np.allclose(ra[f], rb[f], rtol=1e-12, atol=0), f
+            else:
+                assert np.array_equal(ra[f], rb[f]), f
 
 
 def test_fast_kernel_defers_unknown_species():
