@@ -201,8 +201,10 @@ flush_block(const LaunchParams & P, const BlockCtx & S)
     atomicAdd(&P.f64[threadIdx.x], S.blk_f64[threadIdx.x]);
 }
 
+// Share kernels run launches with few primaries per lane: they trade one CTA/SM of occupancy for
+// 96 registers (no spills in the donation/adoption paths).
 template <class TR>
-__global__ void __launch_bounds__(kBlock, kMinBlocks)
+__global__ void __launch_bounds__(kBlock, TR::kShare ? kMinBlocks - 1 : kMinBlocks)
 transport_kernel(const __grid_constant__ LaunchParams P)
 {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -297,7 +299,7 @@ struct mtb_handle
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int sm_count = 0, blocks_per_sm = 0;
+  int sm_count = 0, blocks_per_sm = 0, blocks_per_sm_share = 0;
 
   HostConfig host; // host copies of the configuration
   bool dirty = true, have_materials = false;
@@ -429,6 +431,11 @@ build_tables(mtb_handle * h)
   else
     MTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, transport_kernel<TraitsGeneric>, kBlock, h->smem_bytes));
   h->blocks_per_sm = std::max(bps, 1);
+  if (h->fast)
+    MTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, transport_kernel<TraitsFastShare>, kBlock, h->smem_bytes));
+  else
+    MTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, transport_kernel<TraitsGenericShare>, kBlock, h->smem_bytes));
+  h->blocks_per_sm_share = std::max(bps, 1);
   h->dirty = false;
   return MTB_OK;
 }
@@ -484,7 +491,8 @@ launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, cons
   const uint64_t want_blocks = (n + kBlock - 1) / kBlock;
   // fewer than ~8 cascades per lane: the last wave dominates, let lanes share suspended ions
   const bool share = h->share_enabled && n < 8ull * max_blocks * kBlock;
-  const unsigned blocks = (unsigned)(share ? max_blocks : std::min(max_blocks, want_blocks));
+  const unsigned blocks =
+      (unsigned)(share ? (uint64_t)h->sm_count * h->blocks_per_sm_share : std::min(max_blocks, want_blocks));
   MTB_CUDA(h->d_stacks.ensure((size_t)blocks * kBlock * MTB_STACK_DEPTH));
   P.stacks = h->d_stacks.p;
   MTB_CUDA(h->d_custom_rows.ensure((size_t)blocks * kBlock * (size_t)(2 + P.n_materials + P.n_tclass)));
@@ -527,7 +535,8 @@ run_deferred(mtb_handle * h)
   P.n_primaries = nd;
   const uint64_t max_blocks = (uint64_t)h->sm_count * h->blocks_per_sm;
   const bool share = h->share_enabled && nd < 8ull * max_blocks * kBlock;
-  const unsigned blocks = (unsigned)(share ? max_blocks : std::min<uint64_t>(max_blocks, (nd + kBlock - 1) / kBlock));
+  const unsigned blocks = (unsigned)(share ? (uint64_t)h->sm_count * h->blocks_per_sm_share
+                                           : std::min<uint64_t>(max_blocks, (nd + kBlock - 1) / kBlock));
   MTB_CUDA(h->d_stacks.ensure((size_t)blocks * kBlock * MTB_STACK_DEPTH));
   P.stacks = h->d_stacks.p;
   MTB_CUDA(h->d_custom_rows.ensure((size_t)blocks * kBlock * (size_t)(2 + P.n_materials + P.n_tclass)));
