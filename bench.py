@@ -216,6 +216,10 @@ def main():
         eng.launch_resident(MASTER_SEED, first_index(step_id))
         eng.synchronize()
         step_id += 1
+    if world > 1:
+        # warm-up of the collective itself (NCCL builds its communicator lazily on first use)
+        for _ in range(args.warmup):
+            mdist.reduce_tallies(torch.zeros_like(t_u64), torch.zeros_like(t_f64))
     eng.reset_tallies()
     sampler = ClockSampler(local_rank)
     barrier()
