@@ -345,6 +345,7 @@ struct DeviceHooks
   int vmap_z[3] = {-1, -1, -1};
   int ionlog_z = 0;
   int hist_bins = 0;
+  unsigned long long ionlog_capacity = 0; ///< entries (birth + death halves); 0 = engine default
 };
 
 class TrimBase

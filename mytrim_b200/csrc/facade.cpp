@@ -798,6 +798,7 @@ TrimBase::ensureEngine(bool batch)
       cfg.vmap_z[i] = h.vmap_z[i];
     cfg.ionlog_z = h.ionlog_z;
     cfg.hist_bins = h.hist_bins;
+    cfg.ionlog_capacity = h.ionlog_capacity;
   }
   if (mtb_create(&cfg, &_engine) != MTB_OK)
   {

@@ -136,3 +136,34 @@ def test_unmodified_reference_uo2_app_through_facade(tmp_path):
     assert 0.93 < eel / efiss < 0.98        # reference gold run: 1.75837e8 / 1.83473e8 = 0.958
     nrec = len(open(tmp_path / "out.Erec").read().strip().split("\n"))
     assert 0 <= nrec < 400                   # Xe recoils knocked out of the four bubbles (gold run: 21)
+
+
+def test_batched_mytrim_uo2_driver(tmp_path):
+    """apps/mytrim_uo2.cpp (all fission fragments in one GPU batch) against the oracle's restatement of
+    the reference experiment: identical bubble placement for the same seed, same energy partition and a
+    compatible yield of Xe recoils knocked out of the bubbles."""
+    import ctypes as C
+    apps = _apps()
+    env = dict(os.environ, MYTRIM_SEED="777")
+    nev = 400
+    out = subprocess.run([os.path.join(apps, "mytrim_uo2"), str(tmp_path / "gpu"), "10", "1.0", str(nev)],
+                         capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    eel, enuc, balance = (float(x) for x in out.stdout.strip().split("\n")[-3:])
+    frac_gpu = eel / (eel + enuc + balance)
+    n_gpu = len(open(tmp_path / "gpu.Erec").read().strip().split("\n")) / nev
+    dist_gpu = np.loadtxt(tmp_path / "gpu.dist", ndmin=2)
+
+    lib = C.CDLL(util.ORACLE_LIB)
+    lib.orc_uo2_experiment.argtypes = [C.c_char_p, C.c_double, C.c_double, C.c_int, C.c_uint32,
+                                       C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    e1, e2 = C.c_double(), C.c_double()
+    nev_ref = 6
+    assert lib.orc_uo2_experiment(str(tmp_path / "cpu").encode(), 10.0, 1.0, nev_ref, 777, C.byref(e1), C.byref(e2)) == 0
+    assert open(tmp_path / "gpu.clcoor").read() == open(tmp_path / "cpu.clcoor").read()
+    frac_cpu = e1.value / e2.value
+    assert abs(frac_gpu - frac_cpu) < 0.01, (frac_gpu, frac_cpu)
+    n_cpu = len(open(tmp_path / "cpu.Erec").read().strip().split("\n")) / nev_ref
+    assert 0.4 * n_cpu < n_gpu < 2.5 * n_cpu, (n_gpu, n_cpu)
+    # displacement of Xe recoils from their bubble centre: bubble radius is 10 A, most recoils stay near
+    assert dist_gpu.shape[1] == 5 and np.median(dist_gpu[:, 0]) < 60.0
