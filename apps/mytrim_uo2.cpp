@@ -109,90 +109,98 @@ main(int argc, char * argv[])
   material->prepare();
   sample->material.push_back(material);
 
-  // fission fragment pairs (mytrim_uo2.C:226-266)
+  char ename[400], dname[400];
+  std::snprintf(ename, sizeof(ename), "%s.Erec", argv[1]);
+  std::snprintf(dname, sizeof(dname), "%s.dist", argv[1]);
+  FILE * erec = std::fopen(ename, "wt");
+  FILE * rdist = std::fopen(dname, "wt");
+
+  // The ion log holds a birth and a death entry per Xe ion; events are processed in chunks so that
+  // it stays bounded however many events are requested.
+  const int chunk_events = 2048;
+  TrimXeLog trim(simconf, sample, 1ull << 22);
   MassInverter mass;
   EnergyInverter energy;
-  std::vector<IonBase *> primaries;
   Real Efiss = 0.0;
-  for (int n = 0; n < Nev; ++n)
+  std::vector<mtb_ion_log> log;
+  for (int first = 0; first < Nev; first += chunk_events)
   {
-    const Real A1 = mass.x(simconf->drand());
-    const Real A2 = 235.0 - A1;
-    energy.setMass(A1);
-    const Real Etot = energy.x(simconf->drand());
-    const Real E1 = Etot * A2 / (A1 + A2), E2 = Etot - E1;
-    const int Z1 = std::round((A1 * 92.0) / 235.0), Z2 = 92 - Z1;
-    IonMDTag * ff1 = new IonMDTag;
-    ff1->_gen = 0;
-    ff1->_tag = -1;
-    ff1->_Z = Z1;
-    ff1->_m = A1;
-    ff1->_E = E1 * 1.0e6;
-    Real norm;
-    do
+    // fission fragment pairs (mytrim_uo2.C:226-266)
+    std::vector<IonBase *> primaries;
+    for (int n = first; n < std::min(Nev, first + chunk_events); ++n)
     {
+      const Real A1 = mass.x(simconf->drand());
+      const Real A2 = 235.0 - A1;
+      energy.setMass(A1);
+      const Real Etot = energy.x(simconf->drand());
+      const Real E1 = Etot * A2 / (A1 + A2), E2 = Etot - E1;
+      const int Z1 = std::round((A1 * 92.0) / 235.0), Z2 = 92 - Z1;
+      IonMDTag * ff1 = new IonMDTag;
+      ff1->_gen = 0;
+      ff1->_tag = -1;
+      ff1->_Z = Z1;
+      ff1->_m = A1;
+      ff1->_E = E1 * 1.0e6;
+      Real norm;
+      do
+      {
+        for (int i = 0; i < 3; ++i)
+          ff1->_dir(i) = 2.0 * simconf->drand() - 1.0;
+        norm = ff1->_dir.norm_sq();
+      } while (norm <= 0.0001 || norm > 1.0);
+      ff1->_dir /= std::sqrt(norm);
       for (int i = 0; i < 3; ++i)
-        ff1->_dir(i) = 2.0 * simconf->drand() - 1.0;
-      norm = ff1->_dir.norm_sq();
-    } while (norm <= 0.0001 || norm > 1.0);
-    ff1->_dir /= std::sqrt(norm);
-    for (int i = 0; i < 3; ++i)
-      ff1->_pos(i) = simconf->drand() * sample->w[i];
-    ff1->setEf();
-    IonMDTag * ff2 = new IonMDTag(*ff1);
-    ff2->_dir = -ff2->_dir;
-    ff2->_Z = Z2;
-    ff2->_m = A2;
-    ff2->_E = E2 * 1.0e6;
-    ff2->setEf();
-    primaries.push_back(ff1);
-    primaries.push_back(ff2);
-    Efiss += ff1->_E + ff2->_E;
-  }
+        ff1->_pos(i) = simconf->drand() * sample->w[i];
+      ff1->setEf();
+      IonMDTag * ff2 = new IonMDTag(*ff1);
+      ff2->_dir = -ff2->_dir;
+      ff2->_Z = Z2;
+      ff2->_m = A2;
+      ff2->_E = E2 * 1.0e6;
+      ff2->setEf();
+      primaries.push_back(ff1);
+      primaries.push_back(ff2);
+      Efiss += ff1->_E + ff2->_E;
+    }
 
-  TrimXeLog trim(simconf, sample, 64ull * (unsigned long long)std::max(Nev, 1024));
-  if (!trim.trimBatch(primaries))
-  {
-    std::cerr << "ERROR: " << trim.lastError() << std::endl;
-    return 1;
-  }
+    if (!trim.trimBatch(primaries))
+    {
+      std::cerr << "ERROR: " << trim.lastError() << std::endl;
+      return 1;
+    }
+    for (auto * p : primaries)
+      delete p;
 
-  size_t n = 0;
-  mtb_get_ion_log(trim.engine(), nullptr, 0, &n);
-  std::vector<mtb_ion_log> log(n);
-  if (n)
-  {
-    const int rc = mtb_get_ion_log(trim.engine(), log.data(), n, &n);
-    if (rc != MTB_OK)
+    size_t n = 0;
+    mtb_get_ion_log(trim.engine(), nullptr, 0, &n);
+    log.resize(n);
+    if (n && mtb_get_ion_log(trim.engine(), log.data(), n, &n) != MTB_OK)
     {
       std::cerr << "ERROR: " << mtb_last_error() << std::endl;
       return 1;
     }
-  }
+    mtb_clear_lists(trim.engine());
 
-  std::snprintf(fname, sizeof(fname), "%s.Erec", argv[1]);
-  FILE * erec = std::fopen(fname, "wt");
-  std::snprintf(fname, sizeof(fname), "%s.dist", argv[1]);
-  FILE * rdist = std::fopen(fname, "wt");
-  for (const auto & l : log)
-  {
-    // mark ions born in the MD energy gap (mytrim_uo2.C:285-287)
-    const int md = (l.E0 > 200 && l.E0 < 12000) ? 1 : 0;
-    if (l.gen > 0)
-      std::fprintf(erec, "%f\t%d\t%d\n", l.E0, l.gen, md);
-    if (l.tag >= 0)
+    for (const auto & l : log)
     {
-      // displacement from the centre of the bubble of origin, minimum image (mytrim_uo2.C:296-337)
-      Real d2 = 0.0;
-      for (int i = 0; i < 3; ++i)
+      // mark ions born in the MD energy gap (mytrim_uo2.C:285-287)
+      const int md = (l.E0 > 200 && l.E0 < 12000) ? 1 : 0;
+      if (l.gen > 0)
+        std::fprintf(erec, "%f\t%d\t%d\n", l.E0, l.gen, md);
+      if (l.tag >= 0)
       {
-        Real dif = sample->c[i][l.tag] - l.pos0[i];
-        if (sample->bc[i] == SampleBase::PBC)
-          dif -= std::round(dif / sample->w[i]) * sample->w[i];
-        const Real centre = l.pos0[i] + dif;
-        d2 += (centre - l.pos1[i]) * (centre - l.pos1[i]);
+        // displacement from the centre of the bubble of origin, minimum image (mytrim_uo2.C:296-337)
+        Real d2 = 0.0;
+        for (int i = 0; i < 3; ++i)
+        {
+          Real dif = sample->c[i][l.tag] - l.pos0[i];
+          if (sample->bc[i] == SampleBase::PBC)
+            dif -= std::round(dif / sample->w[i]) * sample->w[i];
+          const Real centre = l.pos0[i] + dif;
+          d2 += (centre - l.pos1[i]) * (centre - l.pos1[i]);
+        }
+        std::fprintf(rdist, "%f %d %f %f %f\n", std::sqrt(d2), md, l.pos1[0], l.pos1[1], l.pos1[2]);
       }
-      std::fprintf(rdist, "%f %d %f %f %f\n", std::sqrt(d2), md, l.pos1[0], l.pos1[1], l.pos1[2]);
     }
   }
   std::fclose(erec);

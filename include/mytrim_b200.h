@@ -272,6 +272,8 @@ int mtb_get_vac_energy(mtb_handle * h, uint64_t * evac /*[rows][bins]*/, size_t 
 int mtb_get_vacmap(mtb_handle * h, uint64_t * vmap /*[20][20][3]*/);
 int mtb_get_range_list(mtb_handle * h, float * x, int32_t * Z, size_t capacity, size_t * n);
 int mtb_get_ion_log(mtb_handle * h, mtb_ion_log * out, size_t capacity, size_t * n);
+/* Empties the ion log and the range list (the other tallies keep accumulating). */
+int mtb_clear_lists(mtb_handle * h);
 int mtb_hist_bins(mtb_handle * h, size_t * bins, size_t * evac_rows);
 
 /* Raw device views of the additive tallies so a caller can reduce them across GPUs with

@@ -1038,6 +1038,17 @@ mtb_get_ion_log(mtb_handle * h, mtb_ion_log * out, size_t capacity, size_t * n)
 }
 
 int
+mtb_clear_lists(mtb_handle * h)
+{
+  if (int rc = ensure_ready(h))
+    return rc;
+  MTB_CUDA(cudaMemsetAsync(h->d_u64.p + CNT_IONLOG_N, 0, sizeof(unsigned long long), h->stream));
+  MTB_CUDA(cudaMemsetAsync(h->d_u64.p + CNT_RANGE_N, 0, sizeof(unsigned long long), h->stream));
+  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  return MTB_OK;
+}
+
+int
 mtb_tally_device_views(mtb_handle * h, void ** u64_dev, size_t * n_u64, void ** f64_dev, size_t * n_f64)
 {
   if (int rc = ensure_ready(h))
