@@ -298,9 +298,17 @@ def main():
         peak_src = "nominal 148 SM x 128 lanes x 2 x 1965 MHz (probe failed)"
     steps_per_s_gpu0 = counters["steps"] / (kernel_ms * 1e-3)
     achieved = steps_per_s_gpu0 * FLOP_PER_STEP / 1e12
+    # DRAM traffic of the kernel: bytes per cascade from the committed ncu --set full capture
+    # (profiles/traffic.json, written by tools/ncu_traffic.py), scaled to this launch size
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f)["dram_bytes_per_cascade"] * B
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {
         "bound": "fp32-issue", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved / tf.value,
-        "traffic": None, "kernel": "transport_kernel", "flop_per_collision_step": FLOP_PER_STEP,
+        "traffic": traffic, "kernel": "transport_kernel", "flop_per_collision_step": FLOP_PER_STEP,
         "collision_steps_per_launch": counters["steps"] / args.steps,
         "kernel_ms_per_launch": kernel_ms / args.steps, "peak_source": peak_src,
         "note": "no dense contraction on this path (SURVEY.md §8d): work = 930 FP32-equivalent flop per collision "

@@ -167,3 +167,30 @@ def test_fast_kernel_defers_unknown_species():
             if k not in ("stack_max",):
                 assert abs(ca[k] - cb[k]) <= 1e-12 * abs(cb[k]), k   # f64 totals: summation order differs
         assert np.array_equal(a.vac_depth()[0], b.vac_depth()[0])
+
+
+@pytest.mark.parametrize("opts", [dict(potential=capi.POT_MOLIERE), dict(potential=capi.POT_CKR),
+                                  dict(length_scale=10.0), dict(tmin=1.0, cw=0.01)])
+def test_options_potentials_and_scale(opts):
+    """MOLIERE / C-Kr potentials (trim.C:206-222, 247-259), SimconfType::setLengthScale, tmin/cw."""
+    cfg = dict(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS, **opts)
+    mat = {"rho": 8.92, "elements": [{"Z": 29, "m": 63.546, "t": 1.0, "Edisp": 30.0, "Elbind": 2.0}]}
+    scale = opts.get("length_scale", 1.0)
+    with util.OracleEngine(util.ORC_RNG_PHILOX, **cfg) as orc, util.HostSimEngine(**cfg) as hs:
+        for e in (orc, hs):
+            e.set_materials([mat])
+            e.set_layers([1000.0 / scale], wy=100.0 / scale, wz=100.0 / scale)
+        ions = capi.make_ions(150, 29, 63.546, 2.0e4, pos=(0.0, 50.0 / scale, 50.0 / scale), Ef=5.0)
+        ro = orc.run(ions, seed=21, records=True)
+        rh = hs.run(ions, seed=21, records=True)
+        co, ch = orc.counters(), hs.counters()
+    same = (ro["vacancies"] == rh["vacancies"]) & (ro["steps"] == rh["steps"]) & (ro["ions"] == rh["ions"])
+    assert same.mean() >= 0.9, same.mean()
+    sel = ro["primary_steps"] == rh["primary_steps"]
+    path = np.maximum(np.linalg.norm(ro["pos"] - ions["pos"], axis=1), 1.0 / scale)
+    rel = (np.linalg.norm(ro["pos"] - rh["pos"], axis=1) / path)[sel]
+    assert (rel >= TOL).sum() <= 2 and np.median(rel) < 0.1 * TOL
+    assert abs(co["vacancies_created"] - ch["vacancies_created"]) <= 0.01 * co["vacancies_created"]
+    if "length_scale" in opts:
+        # positions are in units of 10 A: the same physics lands in 10x fewer depth bins
+        assert ro["pos"][:, 0].mean() < 20.0

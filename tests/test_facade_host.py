@@ -1,0 +1,111 @@
+"""Host-only parts of the C++ plugin surface (include/mytrim) against the oracle / golden fixtures:
+runs everywhere, no GPU needed (no transport call is made)."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import util
+
+ROOT = util.ROOT
+
+
+@pytest.fixture(scope="module")
+def res():
+    exe = os.path.join(ROOT, "build", "facade_host_check")
+    src = os.path.join(ROOT, "tests", "facade_host_check.cpp")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", exe, src,
+                    "-L", os.path.join(ROOT, "mytrim_b200"), "-lmytrim_b200", "-Wl,-rpath," + os.path.join(ROOT, "mytrim_b200")],
+                   check=True)
+    env = dict(os.environ)
+    env.pop("MYTRIM_DATADIR", None)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True, env=env)
+    r = json.loads(out.stdout)
+    # the same program with the reference-format data directory (when oracle/_ref/data travelled along)
+    datadir = os.path.join(util.REF_DIR, "data")
+    r["_with_datadir"] = None
+    if os.path.exists(os.path.join(datadir, "SCOEF.95A")):
+        out2 = subprocess.run([exe], capture_output=True, text=True, check=True, env=dict(env, MYTRIM_DATADIR=datadir))
+        r["_with_datadir"] = json.loads(out2.stdout)
+    return r
+
+
+def test_simconf_rng_is_the_reference_rng(res):
+    lines = [l.split() for l in open(os.path.join(util.GOLDEN, "rng_mt19937.txt")) if not l.startswith("#")]
+    want_d = [float.fromhex(v) for k, v in lines[:8]]
+    assert res["drand"] == want_d
+    # irand() continues the same engine after 8 drand() calls: compare with the oracle's restatement
+    lib = C.CDLL(util.ORACLE_LIB)
+
+    class MT(C.Structure):
+        _fields_ = [("mt", C.c_uint32 * 624), ("idx", C.c_int)]
+
+    lib.orc_mt_drand.restype = C.c_double
+    lib.orc_mt_irand.restype = C.c_uint32
+    g = MT()
+    lib.orc_mt_seed(C.byref(g), C.c_uint32(39172))
+    for _ in range(8):
+        lib.orc_mt_drand(C.byref(g))
+    assert res["irand"] == [lib.orc_mt_irand(C.byref(g)) for _ in range(8)]
+
+
+def test_tables_builtin_equal_reference_data_files(res):
+    if res["_with_datadir"] is None:
+        pytest.skip("oracle/_ref/data not present")
+    assert res["scoef"] == res["_with_datadir"]["scoef"]
+    assert res["average"] == res["_with_datadir"]["average"]
+
+
+def test_material_average_matches_oracle(res):
+    mat = {"rho": 10.97, "elements": [{"Z": 92, "m": 238.03, "t": 1}, {"Z": 8, "m": 15.999, "t": 2}]}
+    with util.OracleEngine(util.ORC_RNG_MT19937) as orc:
+        orc.set_materials([mat])
+        want = orc.average(0, 54, 131.904, 2)
+    assert np.allclose(res["average"], want, rtol=1e-14, atol=0)
+    # SURVEY.md §8c known answers for Xe -> UO2
+    assert abs(res["average"][0] - 0.07339387767) < 1e-10 and abs(res["average"][3] - 0.09795086602) < 1e-10
+
+
+def test_cluster_placement_and_lookup(res):
+    gold = np.loadtxt(os.path.join(util.GOLDEN, "uo2_out.clcoor"))[:, :4]
+    assert np.allclose(np.array(res["clusters"]), gold, rtol=0, atol=5e-7)   # gold file has 6 decimals
+    from mytrim_b200 import capi
+    with util.OracleEngine(util.ORC_RNG_MT19937) as orc:
+        orc.set_materials([util.UO2, util.XE_GAS])
+        orc.set_geometry(capi.GEOM_CLUSTERS, (400.0, 400.0, 400.0), kn=(39, 39, 39), clusters=np.array(res["clusters"]))
+        orc._lib.orc_lookup_material.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        c0 = res["clusters"][0]
+        want = []
+        for i in range(400):
+            p = (C.c_double * 3)(c0[0] + 0.09 * (i % 20) * (i % 3 - 1) - 400.0 * (i % 2), c0[1] + 0.7 * (i // 20) - 6.0,
+                                 c0[2] + 0.05 * i - 8.0)
+            cl = C.c_int()
+            m = orc._lib.orc_lookup_material(orc._h, p, C.byref(cl))
+            want.append(cl.value if m == 1 else -1)
+    assert res["cluster_lookup"] == want
+    assert 0 in want and -1 in want
+
+
+def test_layer_and_wire_lookup(res):
+    assert res["layers"] == [0, 0, 0, 1, 1, 2, 2, 2, 2]           # sample_layers.C:26-49
+    assert res["wire"] == [[0, 0], [-1, 1], [0, 0], [0, 1], [0, -1], [-1, 1], [0, -1]]
+    assert res["bc"] == [2, 0, 1, 0]                               # CUT, PBC, INF, PBC
+
+
+def test_inverters_match_oracle(res):
+    lib = C.CDLL(util.ORACLE_LIB)
+    lib.orc_mass_inverter_x.restype = C.c_double
+    lib.orc_mass_inverter_x.argtypes = [C.c_double]
+    lib.orc_energy_inverter_x.restype = C.c_double
+    lib.orc_energy_inverter_x.argtypes = [C.c_double, C.c_double]
+    assert res["mass_x"] == [lib.orc_mass_inverter_x(0.1 * i) for i in range(1, 10)]
+    assert res["energy_x"] == [lib.orc_energy_inverter_x(96.0, 0.1 * i) for i in range(1, 10)]
+
+
+def test_ion_spawn_recoil_semantics(res):
+    # gen+1, position and Ef inherited, tag reset, IonMDTag type propagates with md = 0, state MOVING
+    assert res["ion"] == [4, 3.0, 7.0, -1, 0, 0]

@@ -336,3 +336,28 @@ def test_work_sharing_pool_is_result_neutral():
             assert c0[k] == c1[k], (name, k)
         assert np.array_equal(h0[0], h1[0]) and np.array_equal(h0[1], h1[1])
         print("%s n=%d: %.2f ms without sharing, %.2f ms with (x%.1f)" % (name, n, ms0, ms1, ms0 / ms1))
+
+
+@pytest.mark.parametrize("opts", [dict(potential=capi.POT_MOLIERE), dict(potential=capi.POT_CKR),
+                                  dict(length_scale=10.0), dict(tmin=1.0, cw=0.01)])
+def test_options_potentials_and_scale(opts):
+    """MOLIERE / C-Kr potentials (trim.C:206-222, 247-259), SimconfType::setLengthScale, tmin/cw, and
+    per-element Edisp/Elbind + a non-default final energy, against the oracle."""
+    cfg = dict(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS, **opts)
+    mat = {"rho": 8.92, "elements": [{"Z": 29, "m": 63.546, "t": 1.0, "Edisp": 30.0, "Elbind": 2.0}]}
+    scale = opts.get("length_scale", 1.0)
+    with util.OracleEngine(util.ORC_RNG_PHILOX, **cfg) as orc, capi.Engine(**cfg) as eng:
+        for e in (orc, eng):
+            e.set_materials([mat])
+            e.set_layers([1000.0 / scale], wy=100.0 / scale, wz=100.0 / scale)
+        ions = capi.make_ions(1500, 29, 63.546, 2.0e4, pos=(0.0, 50.0 / scale, 50.0 / scale), Ef=5.0)
+        ro = orc.run(ions, seed=21, records=True)
+        rg = eng.run(ions, seed=21, records=True)
+        co, cg = orc.counters(), eng.counters()
+    same = (ro["vacancies"] == rg["vacancies"]) & (ro["steps"] == rg["steps"]) & (ro["ions"] == rg["ions"])
+    assert same.mean() >= 0.9, same.mean()
+    sel = ro["primary_steps"] == rg["primary_steps"]
+    path = np.maximum(np.linalg.norm(ro["pos"] - ions["pos"], axis=1), 1.0 / scale)
+    rel = (np.linalg.norm(ro["pos"] - rg["pos"], axis=1) / path)[sel]
+    assert (rel >= TOL).sum() <= max(2, 0.005 * len(rel)) and np.median(rel) < 0.1 * TOL
+    assert abs(co["vacancies_created"] - cg["vacancies_created"]) <= 0.01 * co["vacancies_created"]
