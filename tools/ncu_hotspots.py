@@ -21,6 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ap = argparse.ArgumentParser()
 ap.add_argument("report")
 ap.add_argument("--kernel", default="transport_kernel")
+ap.add_argument("--sass-kernel", default="", help="substring of the mangled name in the cubin (default: --kernel)")
 ap.add_argument("--lib", default=os.path.join(ROOT, "mytrim_b200", "libmytrim_b200.so"))
 ap.add_argument("--top", type=int, default=40)
 ap.add_argument("--by", default="line", choices=["line", "file", "op"])
@@ -35,7 +36,7 @@ addr2line, addr2op = {}, {}
 inside, cur = False, ("?", 0)
 for l in dis.split("\n"):
     if l.startswith("\t.section\t.text."):
-        inside = args.kernel in l
+        inside = (args.sass_kernel or args.kernel) in l
         continue
     if not inside:
         continue

@@ -8,8 +8,10 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = sys.argv[1]
-kernel = sys.argv[2] if len(sys.argv) > 2 else "TraitsFast"
-out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_hotspots.py"), rep, "--kernel", kernel, "--top", "5000"],
+kernel = sys.argv[2] if len(sys.argv) > 2 else "TraitsFastT<(bool)0>"
+sass = sys.argv[3] if len(sys.argv) > 3 else "TraitsFastTILb0E"
+out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_hotspots.py"), rep, "--kernel", kernel, "--sass-kernel", sass,
+                      "--top", "5000"],
                      capture_output=True, text=True).stdout.split("\n")
 src = open(os.path.join(ROOT, "mytrim_b200", "csrc", "mtb_transport.cuh")).read().split("\n")
 psrc = open(os.path.join(ROOT, "mytrim_b200", "csrc", "mtb_physics.cuh")).read().split("\n")
