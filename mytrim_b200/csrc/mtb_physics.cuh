@@ -193,11 +193,11 @@ magic_scatter(int potential, float eps, float b)
     float sum, dsum; // sum = v*r, dsum = -(v + v1*r)
     if (potential == MTB_POT_UNIVERSAL)
     {
-      // c_i * exp(-d_i r) as c_i * 2^(-d_i log2(e) r)
-      const float ex1 = 0.18175f * fexp2(-4.6163355918f * r);
-      const float ex2 = 0.50986f * fexp2(-1.3594371101f * r);
-      const float ex3 = 0.28022f * fexp2(-0.58126183197f * r);
-      const float ex4 = 0.028171f * fexp2(-0.29087617414f * r);
+      // c_i * exp(-d_i r) = 2^(log2 c_i - d_i log2(e) r): one FFMA + one MUFU.EX2 per term
+      const float ex1 = fexp2(fmaf(-4.6163355918f, r, -2.4599727307f));
+      const float ex2 = fexp2(fmaf(-1.3594371101f, r, -0.9718269361f));
+      const float ex3 = fexp2(fmaf(-0.58126183197f, r, -1.8353681667f));
+      const float ex4 = fexp2(fmaf(-0.29087617414f, r, -5.1496454131f));
       sum = (ex1 + ex2) + (ex3 + ex4);
       dsum = (3.1998f * ex1 + 0.94229f * ex2) + (0.4029f * ex3 + 0.20162f * ex4);
     }
