@@ -361,3 +361,65 @@ def test_options_potentials_and_scale(opts):
     rel = (np.linalg.norm(ro["pos"] - rg["pos"], axis=1) / path)[sel]
     assert (rel >= TOL).sum() <= max(2, 0.005 * len(rel)) and np.median(rel) < 0.1 * TOL
     assert abs(co["vacancies_created"] - cg["vacancies_created"]) <= 0.01 * co["vacancies_created"]
+
+
+def test_published_vacancies_per_ion():
+    """The reference's only published numbers for this path: validation/vacancy_count/
+    vacancy_count_comparison.dat, "MyTRIM: exact" (full cascades) and "MyTRIM: KP" (TrimRange:
+    primaries only + NRT estimate), 1 and 10 keV rows (fixture: tests/golden/vacancy_count_published.json)."""
+    pub = json.load(open(os.path.join(util.GOLDEN, "vacancy_count_published.json")))
+    targets = {"cu_on_cu": (util.CU, (29, 63.546)),
+               "xe_on_u": ({"rho": 19.05, "elements": [{"Z": 92, "m": 238.03, "t": 1.0}]}, (54, 131.3)),
+               "si_on_c": ({"rho": 3.51, "elements": [{"Z": 6, "m": 12.011, "t": 1.0}]}, (14, 28.086))}
+    for key, (mat, (Z, m)) in targets.items():
+        for row in (0, 1):
+            E = pub["energy_keV"][row] * 1e3
+            n = 40000
+            for mode, cfg in (("exact", dict()),
+                              ("kp", dict(follow=capi.FOLLOW_NONE, vacancy_model=capi.VAC_NRT))):
+                with capi.Engine(**cfg) as eng:
+                    eng.set_materials([mat])
+                    eng.set_layers([100000.0])
+                    eng.run(capi.make_ions(n, Z, m, E), seed=31)
+                    vpi = eng.counters()["vacancies_created"] / n
+                want = pub["%s_%s" % (key, mode)][row]
+                # the published table was produced with unknown densities/masses for U and C: 4 %
+                assert abs(vpi - want) < 0.04 * want, (key, mode, E, vpi, want)
+
+
+def test_error_paths_return_status_codes():
+    """Nothing exits or throws across the C ABI: bad input comes back as a status + message."""
+    import ctypes as C
+    lib = capi.load_library()
+    with capi.Engine() as eng:
+        with pytest.raises(capi.MytrimError) as e:
+            eng.run(capi.make_ions(10, 29, 63.546, 1e4), seed=1)          # no materials yet
+        assert e.value.code == capi.EINVAL and "materials" in str(e.value)
+        with pytest.raises(capi.MytrimError):
+            eng.set_materials([{"rho": 8.92, "elements": [{"Z": 120, "m": 300.0, "t": 1.0}]}])  # Z > 92
+        with pytest.raises(capi.MytrimError):
+            eng.set_materials([{"rho": -1.0, "elements": [{"Z": 29, "m": 63.5, "t": 1.0}]}])
+        with pytest.raises(capi.MytrimError):
+            eng.set_geometry(capi.GEOM_LAYERS, (10.0, 10.0, 10.0))          # layers geometry without layers
+        with pytest.raises(capi.MytrimError):
+            eng.set_geometry(7, (10.0, 10.0, 10.0))
+        eng.set_materials([util.CU])
+        eng.set_layers([1000.0])
+        with pytest.raises(capi.MytrimError) as e:
+            eng.vac_energy()                                                 # tally not enabled
+        assert e.value.code == capi.EINVAL
+        with pytest.raises(capi.MytrimError) as e:
+            eng.stopping(3, [29], [63.5], [1e4])                             # material index out of range
+        assert e.value.code == capi.EINVAL
+        # an event buffer that is too small reports the needed size
+        ion = capi.make_ions(1, 29, 63.546, 1e4)
+        ev = np.zeros(2, dtype=capi.EVENT_DTYPE)
+        n = C.c_size_t()
+        st = C.c_int32()
+        rc = lib.mtb_trim_one(eng._h, ion.ctypes.data, 1, 1, C.byref(st), ev.ctypes.data, 2, C.byref(n))
+        assert rc == capi.ECAPACITY and n.value > 2
+    cfg = capi.default_config(potential=9)
+    h = C.c_void_p()
+    assert lib.mtb_create(C.byref(cfg), C.byref(h)) == capi.EINVAL
+    cfg = capi.default_config(device=99)
+    assert lib.mtb_create(C.byref(cfg), C.byref(h)) == capi.EINVAL
