@@ -646,6 +646,21 @@ vload(const unsigned long long * p)
   return *reinterpret_cast<const volatile unsigned long long *>(p);
 }
 
+// sequence numbers of the ring slots carry the hand-over of the payload: acquire / release at CTA scope
+MTB_D unsigned long long
+load_acquire(const unsigned long long * p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.cta.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+MTB_D void
+store_release(unsigned long long * p, unsigned long long v)
+{
+  asm volatile("st.release.cta.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 MTB_D bool
 pool_try_push(const BlockCtx & S, const Lane & ion, uint64_t prim)
 {
@@ -654,7 +669,7 @@ pool_try_push(const BlockCtx & S, const Lane & ion, uint64_t prim)
   for (int tries = 0; tries < 4; ++tries)
   {
     PoolSlot * slot = S.pool + (pos & mask);
-    const long long dif = (long long)(vload(&slot->seq) - pos);
+    const long long dif = (long long)(load_acquire(&slot->seq) - pos);
     if (dif == 0)
     {
       const unsigned long long seen = atomicCAS(&S.pool_ctl[POOL_ENQ], pos, pos + 1);
@@ -663,8 +678,7 @@ pool_try_push(const BlockCtx & S, const Lane & ion, uint64_t prim)
         atomicAdd(&S.pool_ctl[POOL_WORKING], 1ull); // the entry counts as outstanding work from now on
         slot->prim = prim;
         stack_store(&slot->e, ion);
-        __threadfence_block();
-        *reinterpret_cast<volatile unsigned long long *>(&slot->seq) = pos + 1;
+        store_release(&slot->seq, pos + 1); // publishes the payload
         return true;
       }
       pos = seen;
@@ -685,17 +699,15 @@ pool_try_pop(const BlockCtx & S, Lane & ion, uint64_t * prim)
   for (int tries = 0; tries < 4; ++tries)
   {
     PoolSlot * slot = S.pool + (pos & mask);
-    const long long dif = (long long)(vload(&slot->seq) - (pos + 1));
+    const long long dif = (long long)(load_acquire(&slot->seq) - (pos + 1));
     if (dif == 0)
     {
       const unsigned long long seen = atomicCAS(&S.pool_ctl[POOL_DEQ], pos, pos + 1);
       if (seen == pos)
       {
-        __threadfence_block();
         *prim = slot->prim;
         stack_load(&slot->e, ion);
-        __threadfence_block();
-        *reinterpret_cast<volatile unsigned long long *>(&slot->seq) = pos + mask + 1;
+        store_release(&slot->seq, pos + mask + 1); // hands the slot back to the producers
         return true;
       }
       pos = seen;
