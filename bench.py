@@ -324,6 +324,7 @@ def main():
         "steps_per_cascade": coll_steps / cascades,
         "vacancies_per_ion": total["vacancies_created"] / cascades,
         "ions_per_cascade": total["ions"] / cascades,
+        "recoils_per_s": (total["ions"] - total["primaries"]) / (job_ms * 1e-3),
         "wall_s_resident_arm": wall_resident,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "cascades/s", "h2d_bytes_per_step": int(B * capi.ION_DTYPE.itemsize),
@@ -335,7 +336,7 @@ def main():
         g.build_test_infrastructure()
         cores = os.cpu_count() or 1
         if util.have_reference():
-            n_ref = 500 * cores
+            n_ref = 2000 * cores   # ~2 s of wall time, ~30 core-seconds
             r = reference_cascades_per_s(n_ref, cores)
             line["cpu_baseline"] = {
                 "value": r["cascades_per_s"], "unit": "cascades/s", "cores": cores, "kind": "reference",
