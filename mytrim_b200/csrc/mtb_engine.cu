@@ -813,8 +813,13 @@ mtb_run(mtb_handle * h, uint64_t n, const mtb_ion * primaries, uint64_t seed, ui
   if (n)
   {
     cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, primaries) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
-      dev_view = static_cast<const mtb_ion *>(attr.devicePointer);
+    if (cudaPointerGetAttributes(&attr, primaries) == cudaSuccess)
+    {
+      if (attr.type == cudaMemoryTypeDevice)
+        return fail(MTB_EINVAL, "mtb_run takes host pointers (use mtb_upload_primaries + mtb_launch_resident)");
+      if (attr.type == cudaMemoryTypeHost && attr.devicePointer)
+        dev_view = static_cast<const mtb_ion *>(attr.devicePointer);
+    }
     else
       (void)cudaGetLastError();
   }
