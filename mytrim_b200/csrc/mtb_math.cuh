@@ -14,13 +14,9 @@
 #if defined(__CUDACC__)
 #define MTB_HD __host__ __device__ __forceinline__
 #define MTB_D __device__ __forceinline__
-// once-per-cascade code: a real call keeps it out of the hot loop (the compiler otherwise
-// if-converts it into predicated instructions that every passing lane pays for)
-#define MTB_HD_COLD __host__ __device__ __noinline__
 #else
 #define MTB_HD inline
 #define MTB_D inline
-#define MTB_HD_COLD inline
 #endif
 
 #if defined(__CUDA_ARCH__)

@@ -333,7 +333,7 @@ as_row(const PairE & v)
 
 // A primary whose (Z, m) has no class (e.g. a fission fragment with its own mass) gets private rows
 // [ProjClass | PairM per material | PairE per target class] in the lane's scratch area.
-MTB_HD_COLD void
+MTB_HD void
 build_custom_rows(const LaunchParams & P, const BlockCtx & S, float4_t * rows, int Z, float m)
 {
   const ProjClass c = make_proj_class(S.ionz[Z], Z, m);
@@ -477,24 +477,20 @@ log_birth(const LaunchParams & P, const Lane & L, int Z)
 }
 
 // an ion has stopped (or left the sample): primary record + death half of the ion log
-// the primary ion of a cascade has stopped: its final state goes into the per-primary record
-MTB_HD_COLD void
-record_primary(mtb_record * r, double px, double py, double pz, double E, int state, uint32_t ic)
-{
-  r->pos[0] = px;
-  r->pos[1] = py;
-  r->pos[2] = pz;
-  r->E = E;
-  r->state = state;
-  r->primary_steps = ic;
-}
-
 template <class TR>
 MTB_HD void
 finish_ion(const LaunchParams & P, const BlockCtx & S, const Lane & L, const float4_t * rows, int state)
 {
   if ((L.packed & FLAG_PRIMARY) && P.records)
-    record_primary(&P.records[L.prim], L.px, L.py, L.pz, L.E, state, L.ic);
+  {
+    mtb_record & r = P.records[L.prim];
+    r.pos[0] = L.px;
+    r.pos[1] = L.py;
+    r.pos[2] = L.pz;
+    r.E = L.E;
+    r.state = state;
+    r.primary_steps = L.ic;
+  }
   if (tally_on<TR>(P, MTB_TALLY_IONLOG))
   {
     const int Z = current_Z(L, S, rows);
@@ -612,34 +608,27 @@ vacancy_creation(const LaunchParams & P, const BlockCtx & S, Lane & L, const Dev
 // close a subtree of a cascade (the whole cascade unless lanes shared it): per-primary record and
 // block totals.  Record counters are accumulated atomically because several lanes may have worked
 // on the same primary; records are zeroed before the launch.
-MTB_HD_COLD void
-close_subtree_cold(mtb_record * r, unsigned long long * blk_u64, double * blk_f64, double Eel, double Enuc, uint32_t vac,
-                   uint32_t repl, uint32_t steps, uint32_t ions, uint32_t n_prim)
-{
-  if (r)
-  {
-    MTB_ATOMIC_ADD(&r->Eel, Eel);
-    MTB_ATOMIC_ADD(&r->Enuc, Enuc);
-    MTB_ATOMIC_ADD(&r->vacancies, vac);
-    MTB_ATOMIC_ADD(&r->replacements, repl);
-    MTB_ATOMIC_ADD(&r->steps, steps);
-    MTB_ATOMIC_ADD(&r->ions, ions);
-  }
-  MTB_ATOMIC_ADD(&blk_u64[CNT_VAC], (unsigned long long)vac);
-  MTB_ATOMIC_ADD(&blk_u64[CNT_REPL], (unsigned long long)repl);
-  MTB_ATOMIC_ADD(&blk_u64[CNT_STEPS], (unsigned long long)steps);
-  MTB_ATOMIC_ADD(&blk_u64[CNT_IONS], (unsigned long long)ions);
-  MTB_ATOMIC_ADD(&blk_u64[CNT_QUEUED], (unsigned long long)(ions - n_prim));
-  MTB_ATOMIC_ADD(&blk_u64[CNT_PRIMARIES], (unsigned long long)n_prim);
-  MTB_ATOMIC_ADD(&blk_f64[0], Eel);
-  MTB_ATOMIC_ADD(&blk_f64[1], Enuc);
-}
-
 MTB_HD void
 close_subtree(const LaunchParams & P, const BlockCtx & S, Lane & L, uint32_t n_prim)
 {
-  close_subtree_cold(P.records ? &P.records[L.prim] : nullptr, S.blk_u64, S.blk_f64, L.casEel, L.casEnuc, L.casVac,
-                     L.casRepl, L.casSteps, L.casIons, n_prim);
+  if (P.records)
+  {
+    mtb_record & r = P.records[L.prim];
+    MTB_ATOMIC_ADD(&r.Eel, L.casEel);
+    MTB_ATOMIC_ADD(&r.Enuc, L.casEnuc);
+    MTB_ATOMIC_ADD(&r.vacancies, L.casVac);
+    MTB_ATOMIC_ADD(&r.replacements, L.casRepl);
+    MTB_ATOMIC_ADD(&r.steps, L.casSteps);
+    MTB_ATOMIC_ADD(&r.ions, L.casIons);
+  }
+  MTB_ATOMIC_ADD(&S.blk_u64[CNT_VAC], (unsigned long long)L.casVac);
+  MTB_ATOMIC_ADD(&S.blk_u64[CNT_REPL], (unsigned long long)L.casRepl);
+  MTB_ATOMIC_ADD(&S.blk_u64[CNT_STEPS], (unsigned long long)L.casSteps);
+  MTB_ATOMIC_ADD(&S.blk_u64[CNT_IONS], (unsigned long long)L.casIons);
+  MTB_ATOMIC_ADD(&S.blk_u64[CNT_QUEUED], (unsigned long long)(L.casIons - n_prim));
+  MTB_ATOMIC_ADD(&S.blk_u64[CNT_PRIMARIES], (unsigned long long)n_prim);
+  MTB_ATOMIC_ADD(&S.blk_f64[0], L.casEel);
+  MTB_ATOMIC_ADD(&S.blk_f64[1], L.casEnuc);
 }
 
 // ---------------------------------------------------------------------------------------------
