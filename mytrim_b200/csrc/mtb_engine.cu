@@ -232,7 +232,8 @@ stopping_kernel(const __grid_constant__ LaunchParams P, int material, size_t n, 
   if (i < n)
   {
     const ProjClass pr = make_proj_class(S.ionz[Z1[i]], Z1[i], (float)m1[i]);
-    out[i] = (double)material_stopping(pr, S.lowstop + Z1[i] * P.n_zslots, S.materials[material], S.elements, (float)E[i]);
+    out[i] = (double)material_stopping(pr, S.lowstop + Z1[i] * P.n_zslots, S.materials[material], S.elements, (float)E[i],
+                                        fsqrt((float)E[i] * pr.inv_km));
   }
 }
 
@@ -431,6 +432,8 @@ build_tables(mtb_handle * h)
   else
     MTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, transport_kernel<TraitsGeneric>, kBlock, h->smem_bytes));
   h->blocks_per_sm = std::max(bps, 1);
+  if (const char * cap = std::getenv("MYTRIM_B200_BLOCKS_PER_SM")) // tuning knob: resident CTAs per SM
+    h->blocks_per_sm = std::max(1, std::min(h->blocks_per_sm, std::atoi(cap)));
   if (h->fast)
     MTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, transport_kernel<TraitsFastShare>, kBlock, h->smem_bytes));
   else
@@ -476,6 +479,7 @@ launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, cons
   P.first_index = first_index;
   P.key0 = (uint32_t)seed;
   P.key1 = (uint32_t)(seed >> 32);
+  philox_round_keys(P.key0, P.key1, P.rk);
   P.records = nullptr;
   if (want_records)
   {
@@ -1090,6 +1094,7 @@ mtb_trim_one(mtb_handle * h, mtb_ion * ion, uint64_t seed, uint64_t uid, int32_t
   P.single_uid = uid;
   P.key0 = (uint32_t)seed;
   P.key1 = (uint32_t)(seed >> 32);
+  philox_round_keys(P.key0, P.key1, P.rk);
   P.records = nullptr;
   P.events = h->d_events.p;
   P.events_cap = events ? capacity : 0;

@@ -116,6 +116,17 @@ fpow(float x, float y)
   return fexp2(y * flog2(x));
 }
 
+// Value barrier: the optimiser may not hoist or speculate anything computed from the result above
+// the point where this executes (keeps rarely-taken branches out of loop pre-headers).
+MTB_HD float
+opaque(float x)
+{
+#if MTB_DEVICE_CODE
+  asm volatile("" : "+f"(x));
+#endif
+  return x;
+}
+
 MTB_HD float
 fmax2(float a, float b)
 {
@@ -127,17 +138,56 @@ fmin2(float a, float b)
   return fminf(a, b);
 }
 
-// sin/cos of 2*pi*u, u in [0,1]
-MTB_HD void
-fsincos2pi(float u, float * s, float * c)
+MTB_HD uint32_t
+f2u(float f)
 {
 #if MTB_DEVICE_CODE
-  sincospif(2.0f * u, s, c);
+  return __float_as_uint(f);
 #else
-  const double a = 6.283185307179586476925 * (double)u;
-  *s = (float)sin(a);
-  *c = (float)cos(a);
+  union { uint32_t u; float f; } cvt;
+  cvt.f = f;
+  return cvt.u;
 #endif
+}
+
+MTB_HD float
+u2f(uint32_t u)
+{
+#if MTB_DEVICE_CODE
+  return __uint_as_float(u);
+#else
+  union { uint32_t u; float f; } cvt;
+  cvt.u = u;
+  return cvt.f;
+#endif
+}
+
+// (cos, sin) of 2*pi*u01(w) straight from the 32 random bits, on the FMA/ALU pipes only (sincospif
+// costs three conversion instructions on the SFU pipe, the busiest one of the transport kernel, and
+// ~30 issue slots).  u01(w) = (q + t)/4 with q = the top two bits and t = (the next 21 bits + 1/2)/2^21,
+// so the angle is q*90deg + 45deg + 90deg*a with a = t - 1/2 in (-1/2, 1/2): two degree-3 minimax
+// polynomials in a^2 (sqrt(1/2)*sin and sqrt(1/2)*cos of 90deg*a; |error| < 8e-8), one add and one subtract for
+// the 45deg rotation, and the quadrant as a swap plus sign-bit flips taken from w itself.
+MTB_HD void
+unit_circle(uint32_t w, float * s, float * c)
+{
+  const float f = u2f(0x3f800000u | ((w >> 7) & 0x007ffffcu)); // 1 + (21 bits)/2^21
+  const float a = f - 1.49999976158142089844f;                 // exact: t - 1/2
+  const float z = a * a;
+  float ps = -0.003254230599850416f, pc = -0.014430884271860123f;
+  ps = fmaf(ps, z, 0.05634243041276932f);
+  pc = fmaf(pc, z, 0.1793213188648224f);
+  ps = fmaf(ps, z, -0.45676514506340027f);
+  pc = fmaf(pc, z, -0.8723555207252502f);
+  ps = fmaf(ps, z, 1.1107207536697388f);
+  pc = fmaf(pc, z, 0.7071067690849304f);
+  ps *= a;
+  const float c0 = pc - ps, s0 = pc + ps; // cos, sin of 45deg + 90deg*a
+  const bool odd = (w & 0x40000000u) != 0u;
+  const uint32_t cb = f2u(odd ? s0 : c0) ^ ((w ^ (w << 1)) & 0x80000000u); // quadrants 1, 2: cos < 0
+  const uint32_t sb = f2u(odd ? c0 : s0) ^ (w & 0x80000000u);              // quadrants 2, 3: sin < 0
+  *c = u2f(cb);
+  *s = u2f(sb);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -174,22 +224,46 @@ philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, u
   out[3] = c3;
 }
 
+// The key schedule of philox4x32_10 depends only on the key: the host expands it once per launch and
+// the kernel reads the round keys as constant-bank operands (saves 18 uniform adds per collision).
+MTB_HD void
+philox_round_keys(uint32_t k0, uint32_t k1, uint32_t rk[20])
+{
+  for (int r = 0; r < 10; ++r)
+  {
+    rk[2 * r] = k0;
+    rk[2 * r + 1] = k1;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+MTB_HD void
+philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t * rk, uint32_t out[4])
+{
+#pragma unroll
+  for (int r = 0; r < 10; ++r)
+  {
+    const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ rk[2 * r];
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ rk[2 * r + 1];
+    c3 = lo0;
+  }
+  out[0] = c0;
+  out[1] = c1;
+  out[2] = c2;
+  out[3] = c3;
+}
+
 // 32 random bits -> uniform in (0,1): the top 23 bits become the mantissa of a float in [1,2),
 // minus 1, plus half a grid step.  Pure ALU/FMA-pipe work (an I2F conversion would occupy the SFU
 // pipe, the busiest one of the transport kernel), exactly the same on host and device.
 MTB_HD float
 u01(uint32_t x)
 {
-  const uint32_t bits = 0x3f800000u | (x >> 9);
-  float f;
-#if MTB_DEVICE_CODE
-  f = __uint_as_float(bits);
-#else
-  union { uint32_t u; float f; } cvt;
-  cvt.u = bits;
-  f = cvt.f;
-#endif
-  return (f - 1.0f) + 0x1p-24f;
+  return (u2f(0x3f800000u | (x >> 9)) - 1.0f) + 0x1p-24f;
 }
 
 // Stream id of a recoil: the spare word of the parent's Philox block of the collision that created

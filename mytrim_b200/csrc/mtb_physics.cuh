@@ -32,20 +32,14 @@ proton_stopping(const DevElement & el, float e)
   return sp;
 }
 
-// Electronic stopping cross-section of one target element — MaterialBase::rstop,
-// material.C:160-282.  E in eV.
+// MaterialBase::rstop outside the tabulated velocity-proportional regime — material.C:187-279.
+// e in keV/amu.  The inputs pass through opaque() so that none of this is hoisted out of the
+// element loop of material_stopping() into code every collision executes (for Cu->Cu the compiler
+// had moved ~30 instructions and 6 MUFU operations of this function in front of the loop).
 MTB_HD float
-element_stopping(const ProjClass & ion, const LowStop * lowrow, const DevElement & el, float E)
+element_stopping_general(const ProjClass & ion, const DevElement & el, float e_in)
 {
-  const float e = E * ion.inv_km; // keV/amu
-  if (ion.Z >= 3)
-  {
-    // velocity-proportional regime (material.C:259-273): rstop = coef(Z1,Z2) * e^power, with the
-    // (Z1, Z2)-only part tabulated in double on the host (mtb_tables.h)
-    const LowStop ls = lowrow[el.zslot];
-    if (e <= ls.e_max)
-      return ls.coef * (ls.power == 0.5f ? fsqrt(e) : fpow(e, ls.power));
-  }
+  const float e = opaque(e_in);
   float se;
   if (ion.Z == 1)
   {
@@ -70,6 +64,7 @@ element_stopping(const ProjClass & ion, const LowStop * lowrow, const DevElement
   else
   {
     // material.C:213-279
+    const float ifz = opaque(ion.fz);
     const float vfermi = el.vfermi;
     const float v = fsqrt(e * 0.04f) * frcp(vfermi);
     const float v2 = v * v;
@@ -79,7 +74,7 @@ element_stopping(const ProjClass & ion, const LowStop * lowrow, const DevElement
     else
       vr = (0.75f * vfermi) * (1.0f + v2 * (2.0f / 3.0f) - v2 * v2 * (1.0f / 15.0f));
 
-    const float cb = ion.cbrt;
+    const float cb = opaque(ion.cbrt);
     const float icb2 = frcp(cb * cb);
     const float ylow = fmax2(0.13f, icb2); // max(yrmin, vrmin / Z1^(2/3))
     const float yr = fmax2(ylow, vr * icb2);
@@ -88,10 +83,10 @@ element_stopping(const ProjClass & ion, const LowStop * lowrow, const DevElement
 
     const float q = fmin2(1.0f, fmax2(0.0f, 1.0f - fexp(-fmin2(a, 50.0f))));
     const float icb = frcp(cb);
-    const float b = fmin2(0.43f, fmax2(0.32f, 0.12f + 0.025f * ion.fz)) * icb;
-    const float l0 = (0.8f - q * fmin2(1.2f, 0.6f + ion.fz * (1.0f / 30.0f))) * icb;
-    const float qa = fmax2(0.0f, 0.9f - 0.025f * ion.fz);
-    const float z16 = 0.025f * fmin2(16.0f, ion.fz);
+    const float b = fmin2(0.43f, fmax2(0.32f, 0.12f + 0.025f * ifz)) * icb;
+    const float l0 = (0.8f - q * fmin2(1.2f, 0.6f + ifz * (1.0f / 30.0f))) * icb;
+    const float qa = fmax2(0.0f, 0.9f - 0.025f * ifz);
+    const float z16 = 0.025f * fmin2(16.0f, ifz);
     float l1;
     if (q < 0.2f)
       l1 = 0.0f;
@@ -110,10 +105,10 @@ element_stopping(const ProjClass & ion, const LowStop * lowrow, const DevElement
     if (e > 1.0f)
     {
       const float t = 7.6f - flog(e);
-      zeta *= 1.0f + fdiv(0.18f + 0.0015f * el.fz, ion.fz * ion.fz) * fexp(-(t * t));
+      zeta *= 1.0f + fdiv(0.18f + 0.0015f * el.fz, ifz * ifz) * fexp(-(t * t));
     }
 
-    const float zf = zeta * ion.fz;
+    const float zf = zeta * ifz;
     if (yr <= ylow)
     {
       // velocity-proportional stopping below yrmin
@@ -131,16 +126,34 @@ element_stopping(const ProjClass & ion, const LowStop * lowrow, const DevElement
   return se * 10.0f;
 }
 
+// Electronic stopping cross-section of one target element — MaterialBase::rstop,
+// material.C:160-282.  E in eV; sqrt_e = sqrt(e), e = E * ion.inv_km in keV/amu (the caller has it
+// from the free-flight computation).
+MTB_HD float
+element_stopping(const ProjClass & ion, const LowStop * lowrow, const DevElement & el, float E, float sqrt_e)
+{
+  const float e = E * ion.inv_km; // keV/amu
+  if (ion.Z >= 3)
+  {
+    // velocity-proportional regime (material.C:259-273): rstop = coef(Z1,Z2) * e^power, with the
+    // (Z1, Z2)-only part tabulated in double on the host (mtb_tables.h)
+    const LowStop ls = lowrow[el.zslot];
+    if (e <= ls.e_max)
+      return ls.coef * (ls.power == 0.5f ? sqrt_e : fpow(e, ls.power));
+  }
+  return element_stopping_general(ion, el, e);
+}
+
 // MaterialBase::getrstop — material.C:113-122 [eV/Ang]
 MTB_HD float
 material_stopping(const ProjClass & ion, const LowStop * lowrow, const DevMaterial & M, const DevElement * elements,
-                  float E)
+                  float E, float sqrt_e)
 {
   float se = 0.0f;
   for (int i = 0; i < M.n_elem; ++i)
   {
     const DevElement & el = elements[M.first_elem + i];
-    se += element_stopping(ion, lowrow, el, E) * el.t;
+    se += element_stopping(ion, lowrow, el, E, sqrt_e) * el.t;
   }
   return se * M.arho;
 }
@@ -152,14 +165,17 @@ struct Scatter
   float c2; // cos^2(theta/2)
 };
 
-// Biersack-Haggmark MAGIC scattering (trim.C:172-272) for reduced energy eps and reduced impact
-// parameter b.  The Newton iteration is the reference's (same start value, same map, same stop
-// test |q/r| <= 0.001) but carried in x = r - b so that distant collisions keep full relative
-// accuracy in single precision.
+// Biersack-Haggmark MAGIC scattering (trim.C:172-272) for reduced energy eps = sqe^2 and reduced
+// impact parameter b.  The Newton iteration is the reference's (same start value, same map, same
+// stop test |q/r| <= 0.001) but carried in x = r - b so that distant collisions keep full relative
+// accuracy in single precision.  Written for the SFU budget of the kernel: per Newton iteration two
+// reciprocals and the exponentials of the potential; after it one reciprocal for cc, b^cc, one
+// square root and ONE reciprocal for everything else (roc, ff, delta and co share a denominator).
 MTB_HD Scatter
-magic_scatter(int potential, float eps, float b)
+magic_scatter(int potential, float sqe, float b)
 {
   Scatter out;
+  const float eps = sqe * sqe;
   if (eps > 10.0f)
   {
     // Rutherford — trim.C:172-179
@@ -185,7 +201,7 @@ magic_scatter(int potential, float eps, float b)
   const float inv_eps = frcp(eps);
   const float b2 = b * b;
   float r, v, v1, q;
-  int guard = 0;
+  int guard = 64;
   do
   {
     r = b + x;
@@ -193,13 +209,13 @@ magic_scatter(int potential, float eps, float b)
     float sum, dsum; // sum = v*r, dsum = -(v + v1*r)
     if (potential == MTB_POT_UNIVERSAL)
     {
-      // c_i * exp(-d_i r) = 2^(log2 c_i - d_i log2(e) r): one FFMA + one MUFU.EX2 per term
-      const float ex1 = fexp2(fmaf(-4.6163355918f, r, -2.4599727307f));
-      const float ex2 = fexp2(fmaf(-1.3594371101f, r, -0.9718269361f));
-      const float ex3 = fexp2(fmaf(-0.58126183197f, r, -1.8353681667f));
-      const float ex4 = fexp2(fmaf(-0.29087617414f, r, -5.1496454131f));
-      sum = (ex1 + ex2) + (ex3 + ex4);
-      dsum = (3.1998f * ex1 + 0.94229f * ex2) + (0.4029f * ex3 + 0.20162f * ex4);
+      // sum c_i exp(-d_i r) and sum c_i d_i exp(-d_i r): the prefactors ride on the FMAs of the sums
+      const float ex1 = fexp2(-4.6163355918f * r);
+      const float ex2 = fexp2(-1.3594371101f * r);
+      const float ex3 = fexp2(-0.58126183197f * r);
+      const float ex4 = fexp2(-0.29087617414f * r);
+      sum = fmaf(0.18175f, ex1, fmaf(0.50986f, ex2, fmaf(0.28022f, ex3, 0.028171f * ex4)));
+      dsum = fmaf(0.58156365f, ex1, fmaf(0.4804359794f, ex2, fmaf(0.112900638f, ex3, 0.00567983702f * ex4)));
     }
     else if (potential == MTB_POT_MOLIERE)
     {
@@ -226,12 +242,11 @@ magic_scatter(int potential, float eps, float b)
     const float fr1 = -(b2 * inv_r * inv_r + 1.0f) - dsum * inv_eps;
     q = fdiv(fr, fr1);
     x -= q;
-  } while (fabsf(q) > 0.001f * fabsf(b + x) && ++guard < 64);
+    --guard; // the reference iterates without a bound; a lane must never spin forever
+  } while ((fabsf(q) > 0.001f * fabsf(b + x)) & (guard != 0));
   r = b + x;
 
   // trim.C:235-271 (v, v1 are those of the last evaluated r, as in the reference)
-  const float roc = fdiv(-2.0f * (eps - v), v1);
-  const float sqe = fsqrt(eps);
   float c_num, c_den, a_k, f_num, f_den;
   if (potential == MTB_POT_UNIVERSAL)
   {
@@ -246,12 +261,16 @@ magic_scatter(int potential, float eps, float b)
     c_num = 0.235809f; c_den = 0.126000f; a_k = 1.0144f; f_num = 6935.0f; f_den = 83550.0f;
   }
   const float cc = fdiv(c_num + sqe, c_den + sqe);
-  const float aa = 2.0f * eps * (1.0f + fdiv(a_k, sqe)) * fpow(b, cc);
-  // sqrt(aa^2+1) - aa == 1/(sqrt(aa^2+1) + aa), the latter does not cancel
-  const float ff = fdiv(f_num + eps, (f_den + eps) * (fsqrt(aa * aa + 1.0f) + aa));
-  const float g = fdiv(aa * ff, ff + 1.0f); // delta = (r - b) * g
-  // co = (b + delta + roc)/(r + roc)  =>  1 - co = (r - b - delta)/(r + roc)
-  const float omc = fdiv(x * (1.0f - g), r + roc);
+  // aa = 2 eps (1 + a_k/sqrt(eps)) b^cc = 2 (eps + a_k sqrt(eps)) b^cc
+  const float aa = 2.0f * fmaf(a_k, sqe, eps) * fpow(b, cc);
+  // ff = N/D with N = f_num + eps, D = (f_den + eps)(sqrt(aa^2+1) + aa)   [sqrt(aa^2+1) - aa in its
+  // non-cancelling reciprocal form];  delta = (r - b) g,  g = aa ff/(ff + 1) = aa N/(N + D);
+  // roc = -2 (eps - v)/v1  =>  r + roc = (r v1 - 2 (eps - v))/v1;
+  // 1 - co = (r - b - delta)/(r + roc) = x (N + D - aa N) v1 / ((N + D)(r v1 - 2 (eps - v)))
+  const float N = f_num + eps;
+  const float D = (f_den + eps) * (fsqrt(fmaf(aa, aa, 1.0f)) + aa);
+  const float ND = N + D;
+  const float omc = fdiv(x * fmaf(-aa, N, ND) * v1, ND * fmaf(r, v1, -2.0f * (eps - v)));
   const float co = 1.0f - omc;
   out.s2 = omc * (1.0f + co);
   out.c2 = co * co;
@@ -259,11 +278,12 @@ magic_scatter(int potential, float eps, float b)
 }
 
 // Free flight (trim.C:88-92) from the tabulated (projectile class, material) constants:
-// returns pmax and writes the mean free flight path ls.
+// returns pmax and writes the mean free flight path ls.  sqrtE = sqrt(E) is shared with the
+// stopping and the reduced energy of the same step.
 MTB_HD float
-flight_from_pair(const PairM & pm, float E, float * ls)
+flight_from_pair(const PairM & pm, float sqrtE, float * ls)
 {
-  const float eeg = pm.K * fsqrt(E);
+  const float eeg = pm.K * sqrtE;
   const float D = eeg + fsqrt(eeg) + 0.125f * fpow(eeg, 0.1f);
   *ls = pm.C2 * (D * D);
   return pm.a * frcp(D);
@@ -283,7 +303,7 @@ make_pair_m(const ProjClass & ion, const DevMaterial & M, float tmin)
   pm.a = a;
   pm.K = fsqrt(f * epsdg);
   pm.C2 = frcp(MTB_PI_F * M.arho * (a * a));
-  pm.pad = 0.0f;
+  pm.sk = fsqrt(ion.inv_km);
   return pm;
 }
 
@@ -296,7 +316,7 @@ make_pair_e(const ProjClass & ion, const DevElement & el)
   pe.ec = fdiv(4.0f * pe.my, opmy * opmy);
   const float ai = fdiv(MTB_SCREEN_K, ion.z023 + el.z023);
   pe.inv_ai = frcp(ai);
-  pe.fi = fdiv(ai * el.m, ion.fz * el.fz * 14.4f * (ion.m + el.m));
+  pe.sfi = fsqrt(fdiv(ai * el.m, ion.fz * el.fz * 14.4f * (ion.m + el.m)));
   return pe;
 }
 

@@ -418,7 +418,7 @@ build_host_tables(const HostConfig & H, HostTables & T, LaunchParams & P, std::s
       pm.a = (float)a;
       pm.K = (float)std::sqrt(f * epsdg);
       pm.C2 = (float)(1.0 / (3.14159265358979323846 * arho * a * a));
-      pm.pad = 0.f;
+      pm.sk = (float)std::sqrt(0.001 / m1);
     }
     for (size_t tc = 0; tc < nt; ++tc)
     {
@@ -430,7 +430,7 @@ build_host_tables(const HostConfig & H, HostTables & T, LaunchParams & P, std::s
       pe.my = (float)my;
       pe.ec = (float)(4.0 * my / ((1.0 + my) * (1.0 + my)));
       pe.inv_ai = (float)(1.0 / ai);
-      pe.fi = (float)(ai * m2 / ((double)z1 * (double)z2 * 14.4 * (m1 + m2)));
+      pe.sfi = (float)std::sqrt(ai * m2 / ((double)z1 * (double)z2 * 14.4 * (m1 + m2)));
     }
   }
   P.n_pclass = (int32_t)np;

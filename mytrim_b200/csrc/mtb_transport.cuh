@@ -321,13 +321,13 @@ find_class(const LaunchParams & P, const BlockCtx & S, int Z, float m)
 MTB_HD float4_t
 as_row(const PairM & v)
 {
-  float4_t r = {v.a, v.K, v.C2, v.pad};
+  float4_t r = {v.a, v.K, v.C2, v.sk};
   return r;
 }
 MTB_HD float4_t
 as_row(const PairE & v)
 {
-  float4_t r = {v.my, v.ec, v.inv_ai, v.fi};
+  float4_t r = {v.my, v.ec, v.inv_ai, v.sfi};
   return r;
 }
 
@@ -540,7 +540,6 @@ vacancy_creation(const LaunchParams & P, const BlockCtx & S, Lane & L, const Dev
   if (!TR::kGeneric)
   {
     L.casVac++;
-    depth_tally(P, S, S.hist_vac, off_vac(P), (int)rx);
     return;
   }
   switch (P.vacancy_model)
@@ -572,9 +571,7 @@ vacancy_creation(const LaunchParams & P, const BlockCtx & S, Lane & L, const Dev
     default:
       break;
   }
-  const int x = (int)rx; // truncation toward zero — TrimVacCount.C:35
-  if (P.tally_mask & MTB_TALLY_VAC_DEPTH)
-    depth_tally(P, S, S.hist_vac, off_vac(P), x);
+  const int x = (int)rx; // truncation toward zero — TrimVacCount.C:35 (the depth histogram itself: caller)
   if ((P.tally_mask & MTB_TALLY_VAC_ENERGY) && x >= 0) // TrimVacEnergyCount.C:31-53
   {
     int le = (int)flog(Erec);
@@ -830,6 +827,13 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           L.dx = (float)src.dir[0];
           L.dy = (float)src.dir[1];
           L.dz = (float)src.dir[2];
+          {
+            // v_norm(dir) of the first step (trim.C:85); later steps only trim the rounding drift
+            const float inv = frsqrt(L.dx * L.dx + L.dy * L.dy + L.dz * L.dz);
+            L.dx *= inv;
+            L.dy *= inv;
+            L.dz *= inv;
+          }
           L.E = src.E;
           L.Ecur = (float)src.E;
           L.ic = 0;
@@ -936,9 +940,11 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     const int mtag = (TR::kGeneric && P.geom_kind == MTB_GEOM_CLUSTERS && mi == 1) ? cluster : M.tag;
     L.casSteps++;
 
-    // v_norm(dir) — trim.C:85
+    // v_norm(dir) — trim.C:85.  Every ion enters the loop with a unit direction (primaries are
+    // normalised when they are loaded, recoils when they are created) and a rotation keeps the norm
+    // up to rounding, so 1/|d| = 1.5 - 0.5 |d|^2 is exact to O(1e-13): no MUFU.RSQ on the step path.
     {
-      const float inv = frsqrt(L.dx * L.dx + L.dy * L.dy + L.dz * L.dz);
+      const float inv = fmaf(-0.5f, L.dx * L.dx + L.dy * L.dy + L.dz * L.dz, 1.5f);
       L.dx *= inv;
       L.dy *= inv;
       L.dz *= inv;
@@ -946,10 +952,9 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
 
     // the four uniforms of this step: one Philox block
     uint32_t w[4];
-    philox4x32_10(L.ic, (uint32_t)L.uid, (uint32_t)(L.uid >> 32), 0u, P.key0, P.key1, w);
+    philox4x32_10_rk(L.ic, (uint32_t)L.uid, (uint32_t)(L.uid >> 32), 0u, P.rk, w);
     const float r2 = u01(w[0]);
     float hh = u01(w[1]);
-    const float uphi = u01(w[2]);
     const float r1 = u01(w[3]);
 
     const float E0 = L.Ecur;
@@ -966,12 +971,13 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       pm.a = r.x;
       pm.K = r.y;
       pm.C2 = r.z;
-      pm.pad = 0.0f;
+      pm.sk = r.w;
     }
     else
       pm = S.pairm[L.pcls * P.n_materials + mi];
     float ls;
-    const float pmax = flight_from_pair(pm, E0, &ls);
+    const float sqrtE0 = fsqrt(E0);
+    const float pmax = flight_from_pair(pm, sqrtE0, &ls);
     if (L.ic == 1)
       ls = r1 * fmin2(ls, P.cw);
     const float p = pmax * fsqrt(r2);
@@ -994,19 +1000,19 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       pe.my = r.x;
       pe.ec = r.y;
       pe.inv_ai = r.z;
-      pe.fi = r.w;
+      pe.sfi = r.w;
     }
     else
       pe = S.paire[L.pcls * P.n_tclass + el.tcls];
     const float my = pe.my;
 
-    const float eps = pe.fi * E0; // trim.C:159-160
+    const float sqe = pe.sfi * sqrtE0; // sqrt(eps), eps = fi E — trim.C:159-160
     const float b = p * pe.inv_ai;
 
-    const float see = material_stopping(pc, lowrow, M, S.elements, E0); // trim.C:166
+    const float see = material_stopping(pc, lowrow, M, S.elements, E0, sqrtE0 * pm.sk); // trim.C:166
     const float dee_f = ls * see;
 
-    const Scatter sc = magic_scatter(potential, eps, b);
+    const Scatter sc = magic_scatter(potential, sqe, b);
 
     // energy bookkeeping — trim.C:275-296.  The running energy is FP64; the float images used by
     // the physics are derived from it once per step.
@@ -1020,7 +1026,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     }
     L.E -= dee;
     L.casEel += dee;
-    const float p1 = fsqrt(pc.m2 * fmax2(E1, 0.0f));
+    const float E1p = fmax2(E1, 0.0f);
     double den = (double)den_f;
     float Erec_den = den_f;
     if (den > L.E)
@@ -1031,7 +1037,11 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     L.E -= den;
     const float E2 = (float)L.E;
     L.Ecur = E2;
-    const float p2 = fsqrt(pc.m2 * E2);
+    // recoil momentum p1 d - p2 d' with p = sqrt(2 m E) (trim.C:292-296, 311, 341).  Only its
+    // direction is used for a followed recoil, so the cascade kernels form sqrt(E1/2m) times it:
+    // E1 d - sqrt(E1 E2) d' (one square root instead of two); the event mode reports the momentum itself.
+    const float p1 = EVENTS ? fsqrt(pc.m2 * E1p) : E1p;
+    const float p2 = EVENTS ? fsqrt(pc.m2 * E2) : fsqrt(E1p * E2);
 
     // recoil is born at the previous collision site — trim.C:306-310
     const double rx = L.px, ry = L.py, rz = L.pz;
@@ -1047,7 +1057,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       const float a = -frcp(sg + L.dz);
       const float bb = L.dx * L.dy * a;
       float sphi, cphi;
-      fsincos2pi(uphi, &sphi, &cphi);
+      unit_circle(w[2], &sphi, &cphi);
       const float ex = cphi * (1.0f + sg * L.dx * L.dx * a) + sphi * bb;
       const float ey = cphi * (sg * bb) + sphi * (sg + L.dy * L.dy * a);
       const float ez = cphi * (-sg * L.dx) + sphi * (-L.dy);
@@ -1100,15 +1110,17 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           L.casEnuc += (double)el.Elbind; // TrimPhononOut::followRecoil
         follow = !EVENTS && (!TR::kGeneric || P.follow == MTB_FOLLOW_ALL ||
                              (P.follow == MTB_FOLLOW_GEN_LT && rec_gen < P.follow_max_gen));
-        if (E2 > el.Edisp)
+        const bool vacancy = E2 > el.Edisp;
+        if (vacancy)
           vacancy_creation<TR>(P, S, L, M, el, rx, ry, Erec, rec_gen);
         else
         {
           L.casRepl++;
-          if (tally_on<TR>(P, MTB_TALLY_VAC_DEPTH))
-            depth_tally(P, S, S.hist_repl, off_repl(P), (int)rx);
           state = (pc.Z == el.Z) ? MTB_REPLACEMENT : MTB_SUBSTITUTIONAL;
         }
+        // TrimVacCount::vacancyCreation / replacementCollision (TrimVacCount.C:31-53): one tally site
+        if (tally_on<TR>(P, MTB_TALLY_VAC_DEPTH))
+          depth_tally(P, S, vacancy ? S.hist_vac : S.hist_repl, vacancy ? off_vac(P) : off_repl(P), (int)rx);
       }
       else
       {

@@ -82,7 +82,7 @@ struct PairM
   float a;  // screening length
   float K;  // sqrt(f * epsdg)
   float C2; // 1 / (pi arho a^2)
-  float pad;
+  float sk; // sqrt(0.001 / m1): sqrt(E) * sk = sqrt(e), e in keV/amu (shares the sqrt(E) of the free flight)
 };
 
 // (projectile class, target class): collision constants (material.C:99-108)
@@ -91,7 +91,7 @@ struct PairE
   float my;     // m1 / m2
   float ec;     // 4 my / (1 + my)^2
   float inv_ai; // 1 / screening length
-  float fi;     // reduced-energy factor
+  float sfi;    // sqrt of the reduced-energy factor fi: sqrt(eps) = sfi * sqrt(E)
 };
 
 // Per projectile-Z constants (indexed by Z, entry 0 unused).
@@ -224,6 +224,7 @@ struct LaunchParams
   const uint32_t * index_list;  // optional: launch over primaries[index_list[k]], k < n_primaries
   uint32_t * deferred;          // fast kernel: indices of primaries without a projectile class
   uint32_t key0, key1;
+  uint32_t rk[20]; // Philox round keys (philox_round_keys): the key schedule is a launch constant
   // outputs
   unsigned long long * u64;     // counter + histogram block
   double * f64;                 // [0]=Eel, [1]=Enuc

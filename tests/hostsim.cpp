@@ -180,6 +180,7 @@ hs_run(hs_engine * e, uint64_t n, const mtb_ion * primaries, uint64_t seed, uint
   P.first_index = first_index;
   P.key0 = (uint32_t)seed;
   P.key1 = (uint32_t)(seed >> 32);
+  philox_round_keys(P.key0, P.key1, P.rk);
   P.records = records;
   P.u64[CNT_NEXT_PRIMARY] = 0;
   const BlockCtx S = hs_ctx(e);
@@ -343,6 +344,7 @@ hs_trim_one(hs_engine * e, mtb_ion * ion, uint64_t seed, uint64_t uid, int32_t *
   P.single_uid = uid;
   P.key0 = (uint32_t)seed;
   P.key1 = (uint32_t)(seed >> 32);
+  philox_round_keys(P.key0, P.key1, P.rk);
   P.records = nullptr;
   P.events = events;
   P.events_cap = capacity;
@@ -379,7 +381,7 @@ hs_stopping(hs_engine * e, int material, size_t n, const int32_t * Z1, const dou
   {
     const ProjClass pr = make_proj_class(S.ionz[Z1[i]], Z1[i], (float)m1[i]);
     out[i] = (double)material_stopping(pr, S.lowstop + Z1[i] * e->P.n_zslots, e->P.materials[material], e->P.elements,
-                                       (float)E[i]);
+                                       (float)E[i], fsqrt((float)E[i] * pr.inv_km));
   }
   return MTB_OK;
 }
