@@ -123,6 +123,8 @@ main(int argc, char * argv[])
   EnergyInverter energy;
   Real Efiss = 0.0;
   std::vector<mtb_ion_log> log;
+  double kernel_ms = 0.0; // device time of the transport launches (reported when MYTRIM_TIMING is set)
+  unsigned long long n_primaries = 0;
   for (int first = 0; first < Nev; first += chunk_events)
   {
     // fission fragment pairs (mytrim_uo2.C:226-266)
@@ -168,6 +170,12 @@ main(int argc, char * argv[])
       std::cerr << "ERROR: " << trim.lastError() << std::endl;
       return 1;
     }
+    {
+      float ms = 0.f;
+      if (mtb_last_kernel_ms(trim.engine(), &ms) == MTB_OK)
+        kernel_ms += ms;
+      n_primaries += primaries.size();
+    }
     for (auto * p : primaries)
       delete p;
 
@@ -205,6 +213,17 @@ main(int argc, char * argv[])
   }
   std::fclose(erec);
   std::fclose(rdist);
+
+  if (std::getenv("MYTRIM_TIMING"))
+  {
+    mtb_counters cnt;
+    if (mtb_get_counters(trim.engine(), &cnt) == MTB_OK && kernel_ms > 0.0)
+      std::fprintf(stderr,
+                   "{\"workload\": \"uo2_fission\", \"primaries\": %llu, \"collision_steps\": %llu, \"ions\": %llu, "
+                   "\"kernel_ms\": %.3f, \"primaries_per_s\": %.4g, \"collision_steps_per_s\": %.4g}\n",
+                   n_primaries, (unsigned long long)cnt.steps, (unsigned long long)cnt.ions, kernel_ms,
+                   n_primaries / (kernel_ms * 1e-3), cnt.steps / (kernel_ms * 1e-3));
+  }
 
   // energy accounting of the whole run (the reference prints it per event, mytrim_uo2.C:345-349)
   std::cout << simconf->EelTotal << std::endl;

@@ -47,10 +47,26 @@ fail(int code, const std::string & msg)
 #define MTB_BLOCK 128
 #endif
 constexpr int kBlock = MTB_BLOCK;
-#ifndef MTB_MIN_BLOCKS
-#define MTB_MIN_BLOCKS 6
+// resident CTAs per SM the register allocation of each kernel variant is bounded for (tuned on B200)
+#ifndef MTB_MIN_BLOCKS_FAST
+#define MTB_MIN_BLOCKS_FAST 7
 #endif
-constexpr int kMinBlocks = MTB_MIN_BLOCKS;
+#ifndef MTB_MIN_BLOCKS_GENERIC
+#define MTB_MIN_BLOCKS_GENERIC 6
+#endif
+#ifndef MTB_MIN_BLOCKS_FAST_SHARE
+#define MTB_MIN_BLOCKS_FAST_SHARE 5
+#endif
+#ifndef MTB_MIN_BLOCKS_GENERIC_SHARE
+#define MTB_MIN_BLOCKS_GENERIC_SHARE 5
+#endif
+template <class TR>
+constexpr int
+min_blocks()
+{
+  return TR::kGeneric ? (TR::kShare ? MTB_MIN_BLOCKS_GENERIC_SHARE : MTB_MIN_BLOCKS_GENERIC)
+                      : (TR::kShare ? MTB_MIN_BLOCKS_FAST_SHARE : MTB_MIN_BLOCKS_FAST);
+}
 
 // ---------------------------------------------------------------------------------------------
 // kernels
@@ -204,7 +220,7 @@ flush_block(const LaunchParams & P, const BlockCtx & S)
 // Share kernels run launches with few primaries per lane: they trade one CTA/SM of occupancy for
 // 96 registers (no spills in the donation/adoption paths).
 template <class TR>
-__global__ void __launch_bounds__(kBlock, TR::kShare ? kMinBlocks - 1 : kMinBlocks)
+__global__ void __launch_bounds__(kBlock, min_blocks<TR>())
 transport_kernel(const __grid_constant__ LaunchParams P)
 {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -317,11 +333,13 @@ struct mtb_handle
   DevBuf<float4_t> d_custom_rows;
   DevBuf<uint32_t> d_deferred;
   bool share_enabled = true;
+  uint64_t share_below = 4; // work sharing for launches with fewer primaries per lane than this
   bool deferred_pending = false;
   float extra_ms = 0.f;
   bool fast = false;
   DevBuf<double> d_layer_cum, d_cl_xyzr;
   DevBuf<int32_t> d_layer_mat, d_cl_hash, d_cl_next;
+  DevBuf<uint32_t> d_cl_near;
   // outputs
   DevBuf<unsigned long long> d_u64;
   DevBuf<double> d_f64;
@@ -387,6 +405,8 @@ build_tables(mtb_handle * h)
     P.cl_hash = h->d_cl_hash.p;
     P.cl_next = h->d_cl_next.p;
     P.cl_xyzr = h->d_cl_xyzr.p;
+    MTB_CUDA(h->d_cl_near.upload(T.cl_near.data(), T.cl_near.size(), h->stream));
+    P.cl_near = h->d_cl_near.p;
   }
   MTB_CUDA(cudaStreamSynchronize(h->stream)); // T goes out of scope
 
@@ -494,9 +514,11 @@ launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, cons
   const uint64_t max_blocks = (uint64_t)h->sm_count * h->blocks_per_sm;
   const uint64_t want_blocks = (n + kBlock - 1) / kBlock;
   // fewer than ~8 cascades per lane: the last wave dominates, let lanes share suspended ions
-  const bool share = h->share_enabled && n < 8ull * max_blocks * kBlock;
+  const bool share = h->share_enabled && n < h->share_below * max_blocks * kBlock;
   const unsigned blocks =
       (unsigned)(share ? (uint64_t)h->sm_count * h->blocks_per_sm_share : std::min(max_blocks, want_blocks));
+  if ((uint64_t)blocks * kBlock * MTB_STACK_DEPTH * sizeof(StackEntry) > 0xFFFFFFFFull)
+    return fail(MTB_EINVAL, "grid too large for 32-bit stack cursors");
   MTB_CUDA(h->d_stacks.ensure((size_t)blocks * kBlock * MTB_STACK_DEPTH));
   P.stacks = h->d_stacks.p;
   MTB_CUDA(h->d_custom_rows.ensure((size_t)blocks * kBlock * (size_t)(2 + P.n_materials + P.n_tclass)));
@@ -538,9 +560,11 @@ run_deferred(mtb_handle * h)
   P.deferred = nullptr;
   P.n_primaries = nd;
   const uint64_t max_blocks = (uint64_t)h->sm_count * h->blocks_per_sm;
-  const bool share = h->share_enabled && nd < 8ull * max_blocks * kBlock;
+  const bool share = h->share_enabled && nd < h->share_below * max_blocks * kBlock;
   const unsigned blocks = (unsigned)(share ? (uint64_t)h->sm_count * h->blocks_per_sm_share
                                            : std::min<uint64_t>(max_blocks, (nd + kBlock - 1) / kBlock));
+  if ((uint64_t)blocks * kBlock * MTB_STACK_DEPTH * sizeof(StackEntry) > 0xFFFFFFFFull)
+    return fail(MTB_EINVAL, "grid too large for 32-bit stack cursors");
   MTB_CUDA(h->d_stacks.ensure((size_t)blocks * kBlock * MTB_STACK_DEPTH));
   P.stacks = h->d_stacks.p;
   MTB_CUDA(h->d_custom_rows.ensure((size_t)blocks * kBlock * (size_t)(2 + P.n_materials + P.n_tclass)));
@@ -639,6 +663,8 @@ mtb_create(const mtb_config * cfg, mtb_handle ** out)
   h->device = cfg->device;
   if (const char * env = std::getenv("MYTRIM_B200_NO_SHARE"))
     h->share_enabled = env[0] == '0';
+  if (const char * env = std::getenv("MYTRIM_B200_SHARE_BELOW")) // tuning knob: primaries per lane
+    h->share_below = std::strtoull(env, nullptr, 10);
   h->sm_count = prop.multiProcessorCount;
   cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess)

@@ -146,6 +146,7 @@ struct HostTables
   std::vector<int32_t> tclass_elem;
   std::vector<double> layer_cum;
   std::vector<int32_t> layer_mat, cl_hash, cl_next;
+  std::vector<uint32_t> cl_near;
 };
 
 inline void
@@ -511,7 +512,37 @@ build_host_tables(const HostConfig & H, HostTables & T, LaunchParams & P, std::s
     {
       P.kn[i] = g.kn[i];
       P.kd[i] = g.w[i] / (double)g.kn[i];
+      P.kn_w[i] = (double)g.kn[i] / g.w[i];
       P.cl_ks[i] = (int)(cmr / P.kd[i]) + 1;
+    }
+    // Neighbourhood filter: lookupCluster scans the (2 ks + 1)^3 cells around the cell of the position
+    // (sample_clusters.C:83-131).  Bubbles are sparse (7e-7 per A^3 in the uo2 case: 4 in 59319
+    // cells), so almost every scan visits only empty cells.  Bit c says whether a scan centred on
+    // cell c can see a non-empty cell at all; the device tests it before it scans.
+    T.cl_near.assign((ncell + 31) / 32, 0u);
+    for (size_t cell = 0; cell < ncell; ++cell)
+    {
+      if (T.cl_hash[cell] < 0)
+        continue;
+      const int c[3] = {(int)(cell % g.kn[0]), (int)((cell / g.kn[0]) % g.kn[1]), (int)(cell / ((size_t)g.kn[0] * g.kn[1]))};
+      std::vector<int> centres[3];
+      for (int i = 0; i < 3; ++i)
+        for (int d = -P.cl_ks[i]; d <= P.cl_ks[i]; ++d)
+        {
+          int k = c[i] - d; // a scan centred on k reaches c = k + d
+          if (g.bc[i] == MTB_BC_PBC)
+            k = ((k % g.kn[i]) + g.kn[i]) % g.kn[i];
+          else if (k < 0 || k >= g.kn[i])
+            continue;
+          centres[i].push_back(k);
+        }
+      for (int k0 : centres[0])
+        for (int k1 : centres[1])
+          for (int k2 : centres[2])
+          {
+            const size_t cc = (size_t)k0 + (size_t)g.kn[0] * ((size_t)k1 + (size_t)g.kn[1] * (size_t)k2);
+            T.cl_near[cc >> 5] |= 1u << (cc & 31);
+          }
     }
   }
 

@@ -151,10 +151,16 @@ lookup_cluster(const LaunchParams & P, double px, double py, double pz)
 {
   // sampleClusters::lookupCluster(pos, 0) — sample_clusters.C:59-133
   const double pos[3] = {px, py, pz};
-  int k1[3], k2[3];
+  int kc[3], k1[3], k2[3];
   for (int i = 0; i < 3; ++i)
   {
-    int k = (int)floor((pos[i] * P.kn[i]) / P.w[i]);
+    // cell index floor((pos * kn) / w): a multiplication by kn/w unless the product sits within
+    // rounding distance of a cell boundary, where the reference expression decides
+    const double t = pos[i] * P.kn_w[i];
+    double fl = floor(t);
+    if (t - fl < 1e-9 * (fabs(t) + 1.0) || fl + 1.0 - t < 1e-9 * (fabs(t) + 1.0))
+      fl = floor((pos[i] * P.kn[i]) / P.w[i]);
+    int k = (int)fl;
     if (pos[i] < 0.0 || pos[i] >= P.w[i])
     {
       if (P.bc[i] == MTB_BC_CUT)
@@ -165,12 +171,29 @@ lookup_cluster(const LaunchParams & P, double px, double py, double pz)
       if (k < 0)
         k += P.kn[i];
     }
+    kc[i] = k;
     k1[i] = k - P.cl_ks[i];
     k2[i] = k + P.cl_ks[i];
     if (k1[i] < 0 && P.bc[i] != MTB_BC_PBC)
       k1[i] = 0;
     if (k2[i] >= P.kn[i] && P.bc[i] != MTB_BC_PBC)
       k2[i] = P.kn[i] - 1;
+  }
+  {
+    // neighbourhood filter (mtb_tables.h): nothing to find around this cell in almost every step.
+    // A position exactly on the upper face (pos == w under rounding) can index cell kn: scan then.
+    const int inside = (kc[0] < P.kn[0]) & (kc[1] < P.kn[1]) & (kc[2] < P.kn[2]) & (kc[0] >= 0) & (kc[1] >= 0) & (kc[2] >= 0);
+    if (inside)
+    {
+      const uint32_t cell = (uint32_t)kc[0] + (uint32_t)P.kn[0] * ((uint32_t)kc[1] + (uint32_t)P.kn[1] * (uint32_t)kc[2]);
+#if MTB_DEVICE_CODE
+      const uint32_t word = __ldg(P.cl_near + (cell >> 5));
+#else
+      const uint32_t word = P.cl_near[cell >> 5];
+#endif
+      if (!((word >> (cell & 31)) & 1u))
+        return -1;
+    }
   }
   for (int j0 = k1[0]; j0 <= k2[0]; ++j0)
   {
@@ -390,12 +413,14 @@ MTB_HD void
 stack_store(StackEntry * dst, const Lane & L)
 {
 #if MTB_DEVICE_CODE
-  // four 16-byte stores straight from registers (no local-memory staging)
+  // 8-byte stores for the doubles (they sit in aligned register pairs already: a 16-byte store would
+  // need four moves to line a quad up), 16-byte stores for the rest; no local-memory staging
+  double * dd = reinterpret_cast<double *>(dst);
+  dd[0] = L.px;
+  dd[1] = L.py;
+  dd[2] = L.pz;
+  dd[3] = L.E;
   uint4 * d = reinterpret_cast<uint4 *>(dst);
-  const unsigned long long x = (unsigned long long)__double_as_longlong(L.px), y = (unsigned long long)__double_as_longlong(L.py),
-                           z = (unsigned long long)__double_as_longlong(L.pz), e = (unsigned long long)__double_as_longlong(L.E);
-  d[0] = make_uint4((uint32_t)x, (uint32_t)(x >> 32), (uint32_t)y, (uint32_t)(y >> 32));
-  d[1] = make_uint4((uint32_t)z, (uint32_t)(z >> 32), (uint32_t)e, (uint32_t)(e >> 32));
   d[2] = make_uint4(__float_as_uint(L.dx), __float_as_uint(L.dy), __float_as_uint(L.dz), L.ic);
   d[3] = make_uint4((uint32_t)L.uid, (uint32_t)(L.uid >> 32), L.packed, (uint32_t)L.tag);
 #else
@@ -718,10 +743,29 @@ pool_try_pop(const BlockCtx & S, Lane & ion, uint64_t * prim)
 }
 #endif
 
+// Stack cursor of a lane: the byte offset, within P.stacks, of its next free entry.  A lane owns
+// MTB_STACK_DEPTH consecutive 64-byte entries, so bits 6.. of the cursor hold lane * MTB_STACK_DEPTH +
+// depth: the depth needs no register of its own and an entry address is one 32 x 64-bit add.
+// (Depth MTB_STACK_DEPTH itself would carry into the lane index: a stack is full at MTB_STACK_DEPTH - 1.)
+static_assert(sizeof(StackEntry) == 64 && (MTB_STACK_DEPTH & (MTB_STACK_DEPTH - 1)) == 0, "stack cursor encoding");
+#define MTB_STACK_DEPTH_BITS ((uint32_t)(MTB_STACK_DEPTH - 1) << 6)
+
+MTB_HD StackEntry *
+stack_entry(const LaunchParams & P, uint32_t cursor)
+{
+  return reinterpret_cast<StackEntry *>(reinterpret_cast<unsigned char *>(P.stacks) + cursor);
+}
+
+MTB_HD int
+stack_depth(uint32_t cursor)
+{
+  return (int)((cursor & MTB_STACK_DEPTH_BITS) >> 6);
+}
+
 // Suspend an ion: on the lane's private stack, or — when lanes are idle — in the shared pool.
 template <class TR>
 MTB_HD void
-suspend_ion(const LaunchParams & P, const BlockCtx & S, StackEntry * stack, int & sp, const Lane & ion, uint64_t prim)
+suspend_ion(const LaunchParams & P, const BlockCtx & S, uint32_t & sp, const Lane & ion, uint64_t prim)
 {
 #if MTB_DEVICE_CODE
   if (TR::kShare && vload(&S.pool_ctl[POOL_IDLE]) > 0 && pool_try_push(S, ion, prim))
@@ -729,8 +773,11 @@ suspend_ion(const LaunchParams & P, const BlockCtx & S, StackEntry * stack, int 
 #endif
   (void)S;
   (void)prim;
-  if (sp < MTB_STACK_DEPTH)
-    stack_store(stack + sp++, ion);
+  if ((sp & MTB_STACK_DEPTH_BITS) != MTB_STACK_DEPTH_BITS)
+  {
+    stack_store(stack_entry(P, sp), ion);
+    sp += (uint32_t)sizeof(StackEntry);
+  }
   else
     MTB_ATOMIC_ADD(&P.u64[CNT_ERROR], 1ull);
 }
@@ -746,10 +793,10 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
   constexpr bool EVENTS = TR::kEvents;
   const int potential = TR::kGeneric ? P.potential : (int)MTB_POT_UNIVERSAL;
   Lane L;
-  StackEntry * const stack = EVENTS ? nullptr : P.stacks + (size_t)lane_global * MTB_STACK_DEPTH;
   float4_t * const rows =
       TR::kCustom ? P.custom_rows + (size_t)lane_global * (size_t)(2 + P.n_materials + P.n_tclass) : nullptr;
-  int sp = 0, sp_max = 0;
+  uint32_t sp = lane_global * (uint32_t)(MTB_STACK_DEPTH * sizeof(StackEntry)); // stack cursor, see stack_entry()
+  int sp_max = 0;
   bool active = false, open = false, started = false, done = false, no_more = false, idle = false;
   uint32_t cas_prim = 0;
   unsigned long long idle_polls = 0;
@@ -767,10 +814,10 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     // ---------------- refill: next suspended ion, else next primary ----------------
     if (!done && !active)
     {
-      if (sp > 0)
+      if (sp & MTB_STACK_DEPTH_BITS)
       {
-        --sp;
-        stack_load(stack + sp, L);
+        sp -= (uint32_t)sizeof(StackEntry);
+        stack_load(stack_entry(P, sp), L);
         set_species(L, S);
         active = true;
       }
@@ -1187,7 +1234,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       if (state == MTB_MOVING && !keep_projectile)
       {
         // both move on and the recoil has less energy: suspend the projectile, fly the recoil
-        suspend_ion<TR>(P, S, stack, sp, L, L.prim);
+        suspend_ion<TR>(P, S, sp, L, L.prim);
       }
       if (state != MTB_MOVING)
         finish_ion<TR>(P, S, L, rows, state);
@@ -1207,7 +1254,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           R.prim = L.prim;
           log_birth<TR>(P, R, el.Z);
         }
-        suspend_ion<TR>(P, S, stack, sp, R, L.prim);
+        suspend_ion<TR>(P, S, sp, R, L.prim);
       }
       else
       {
@@ -1222,8 +1269,8 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
         L.pcls = el.tcls;
         log_birth<TR>(P, L, el.Z);
       }
-      if (TR::kGeneric && sp > sp_max)
-        sp_max = sp; // diagnostic high-water mark (generic kernels only)
+      if (TR::kGeneric && stack_depth(sp) > sp_max)
+        sp_max = stack_depth(sp); // diagnostic high-water mark (generic kernels only)
     }
     else if (state != MTB_MOVING)
     {

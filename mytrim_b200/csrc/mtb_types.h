@@ -217,6 +217,8 @@ struct LaunchParams
   const int32_t * cl_next;      // cl[]
   const double * cl_xyzr;       // 4 per cluster
   double kd[3];
+  double kn_w[3];               // kn / w: cell index without a division (exact path on near-ties)
+  const uint32_t * cl_near;     // one bit per hash cell: some cell of its scan neighbourhood holds a cluster
   // primaries
   const mtb_ion * primaries;    // device copy, or null for beam mode
   mtb_ion beam;

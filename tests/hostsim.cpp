@@ -55,6 +55,7 @@ hs_prepare(hs_engine * e)
   P.layer_mat = e->T.layer_mat.data();
   P.cl_hash = e->T.cl_hash.data();
   P.cl_next = e->T.cl_next.data();
+  P.cl_near = e->T.cl_near.data();
   P.cl_xyzr = e->host.cluster_xyzr.data();
   e->u64.assign(u64_block_size(P), 0ull);
   e->f64[0] = e->f64[1] = 0.0;

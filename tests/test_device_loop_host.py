@@ -147,6 +147,38 @@ def test_per_primary_species_and_clusters():
     assert abs(ch["steps"] - co["steps"]) <= 0.02 * co["steps"]
 
 
+@pytest.mark.parametrize("bc", [(capi.BC_PBC,) * 3, (capi.BC_CUT, capi.BC_PBC, capi.BC_INF)])
+def test_dense_clusters_neighbourhood_filter(bc):
+    """300 bubbles in a 20^3 hash (scan neighbourhoods overlap, chains form, the box faces matter):
+    the neighbourhood bitmap in front of the 27-cell scan must not change a single lookup."""
+    rng = np.random.default_rng(11)
+    cl = np.column_stack([rng.uniform(0, 400, (300, 3)), rng.uniform(6.0, 19.0, 300)])
+    cfg = dict(tally_mask=capi.TALLY_RECORDS | capi.TALLY_PHONON)
+    n = 160
+    ions = capi.make_ions(n, 54, 131.0, 4.0e4)
+    ions["pos"] = rng.uniform(0, 400, (n, 3))
+    ions["pos"][:40] = cl[:40, :3] + rng.uniform(-3, 3, (40, 3))   # some start inside a bubble
+    d = rng.normal(size=(n, 3))
+    ions["dir"] = d / np.linalg.norm(d, axis=1)[:, None]
+    with util.OracleEngine(util.ORC_RNG_PHILOX, **cfg) as orc, util.HostSimEngine(**cfg) as hs:
+        for e in (orc, hs):
+            e.set_materials([util.UO2, util.XE_GAS])
+            e.set_geometry(capi.GEOM_CLUSTERS, (400.0, 400.0, 400.0), bc=bc, kn=(20, 20, 20), clusters=cl)
+        ro = orc.run(ions, seed=5, records=True)
+        rh = hs.run(ions, seed=5, records=True)
+        co, ch = orc.counters(), hs.counters()
+    same = (ro["vacancies"] == rh["vacancies"]) & (ro["steps"] == rh["steps"]) & (ro["ions"] == rh["ions"])
+    assert same.mean() >= 0.8, same.mean()
+    assert np.array_equal(ro["state"], rh["state"]) or (ro["state"] != rh["state"]).sum() <= 2
+    sel = ro["primary_steps"] == rh["primary_steps"]
+    assert sel.mean() >= 0.95
+    path = np.maximum(np.linalg.norm(ro["pos"] - ions["pos"], axis=1), 1.0)
+    rel = (np.linalg.norm(ro["pos"] - rh["pos"], axis=1) / path)[sel]
+    assert (rel >= TOL).sum() <= 2 and np.median(rel) < 0.1 * TOL
+    assert abs(ch["steps"] - co["steps"]) <= 0.02 * co["steps"]
+    assert abs(ch["left_sample"] - co["left_sample"]) <= 2 and abs(ch["lost"] - co["lost"]) <= 2
+
+
 def test_fast_kernel_defers_unknown_species():
     """Layered sample + TrimVacCount tallies selects the compile-time fast loop; primaries whose
     species has no class are handed to the generic loop and the union equals a generic-only run."""
