@@ -7,6 +7,7 @@
 // Difference from the reference driver: all 2*Nev fragments are generated first (host mt19937, same
 // inverse-CDF sampling) and followed in ONE batch on the GPU; the per-ion pre/post analysis of
 // mytrim_uo2.C:281-338 runs afterwards on the engine's ion log.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -117,7 +118,7 @@ main(int argc, char * argv[])
 
   // The ion log holds a birth and a death entry per Xe ion; events are processed in chunks so that
   // it stays bounded however many events are requested.
-  const int chunk_events = 2048;
+  const int chunk_events = std::getenv("MYTRIM_UO2_CHUNK") ? std::max(1, std::atoi(std::getenv("MYTRIM_UO2_CHUNK"))) : 32768;
   TrimXeLog trim(simconf, sample, 1ull << 22);
   MassInverter mass;
   EnergyInverter energy;

@@ -51,11 +51,17 @@ constexpr int kBlock = MTB_BLOCK;
 #ifndef MTB_MIN_BLOCKS_FAST
 #define MTB_MIN_BLOCKS_FAST 7
 #endif
+#ifndef MTB_MIN_BLOCKS_CLUSTERS
+#define MTB_MIN_BLOCKS_CLUSTERS 6
+#endif
 #ifndef MTB_MIN_BLOCKS_GENERIC
 #define MTB_MIN_BLOCKS_GENERIC 6
 #endif
 #ifndef MTB_MIN_BLOCKS_FAST_SHARE
 #define MTB_MIN_BLOCKS_FAST_SHARE 5
+#endif
+#ifndef MTB_MIN_BLOCKS_CLUSTERS_SHARE
+#define MTB_MIN_BLOCKS_CLUSTERS_SHARE 5
 #endif
 #ifndef MTB_MIN_BLOCKS_GENERIC_SHARE
 #define MTB_MIN_BLOCKS_GENERIC_SHARE 5
@@ -64,8 +70,9 @@ template <class TR>
 constexpr int
 min_blocks()
 {
-  return TR::kGeneric ? (TR::kShare ? MTB_MIN_BLOCKS_GENERIC_SHARE : MTB_MIN_BLOCKS_GENERIC)
-                      : (TR::kShare ? MTB_MIN_BLOCKS_FAST_SHARE : MTB_MIN_BLOCKS_FAST);
+  return TR::kF & F_GEOM_ANY ? (TR::kShare ? MTB_MIN_BLOCKS_GENERIC_SHARE : MTB_MIN_BLOCKS_GENERIC)
+         : TR::kF & F_CLUSTERS ? (TR::kShare ? MTB_MIN_BLOCKS_CLUSTERS_SHARE : MTB_MIN_BLOCKS_CLUSTERS)
+                               : (TR::kShare ? MTB_MIN_BLOCKS_FAST_SHARE : MTB_MIN_BLOCKS_FAST);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -316,7 +323,9 @@ struct mtb_handle
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int sm_count = 0, blocks_per_sm = 0, blocks_per_sm_share = 0;
+  int sm_count = 0;
+  int bps[3][2] = {{1, 1}, {1, 1}, {1, 1}}; // resident CTAs per SM: [variant][share]
+  Variant variant = VARIANT_GENERIC, variant_custom = VARIANT_GENERIC; // pick_variant(P, false / true)
 
   HostConfig host; // host copies of the configuration
   bool dirty = true, have_materials = false;
@@ -333,13 +342,14 @@ struct mtb_handle
   DevBuf<float4_t> d_custom_rows;
   DevBuf<uint32_t> d_deferred;
   bool share_enabled = true;
-  uint64_t share_below = 4; // work sharing for launches with fewer primaries per lane than this
+  uint64_t share_below = 4;  // work sharing for launches with fewer primaries per lane than this
+  float share_min_E = 0.f;   // eV, see suspend_ion()
   bool deferred_pending = false;
   float extra_ms = 0.f;
   bool fast = false;
   DevBuf<double> d_layer_cum, d_cl_xyzr;
   DevBuf<int32_t> d_layer_mat, d_cl_hash, d_cl_next;
-  DevBuf<uint32_t> d_cl_near;
+  DevBuf<uint8_t> d_cl_dist;
   // outputs
   DevBuf<unsigned long long> d_u64;
   DevBuf<double> d_f64;
@@ -405,8 +415,8 @@ build_tables(mtb_handle * h)
     P.cl_hash = h->d_cl_hash.p;
     P.cl_next = h->d_cl_next.p;
     P.cl_xyzr = h->d_cl_xyzr.p;
-    MTB_CUDA(h->d_cl_near.upload(T.cl_near.data(), T.cl_near.size(), h->stream));
-    P.cl_near = h->d_cl_near.p;
+    MTB_CUDA(h->d_cl_dist.upload(T.cl_dist.data(), T.cl_dist.size(), h->stream));
+    P.cl_dist = h->d_cl_dist.p;
   }
   MTB_CUDA(cudaStreamSynchronize(h->stream)); // T goes out of scope
 
@@ -440,25 +450,24 @@ build_tables(mtb_handle * h)
   if (h->smem_bytes > 200 * 1024)
     return fail(MTB_EINVAL, "configuration tables do not fit in shared memory");
   h->fast = fast_path_ok(P);
-  MTB_CUDA(cudaFuncSetAttribute(transport_kernel<TraitsGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  MTB_CUDA(cudaFuncSetAttribute(transport_kernel<TraitsFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  MTB_CUDA(cudaFuncSetAttribute(transport_kernel<TraitsGenericShare>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  MTB_CUDA(cudaFuncSetAttribute(transport_kernel<TraitsFastShare>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  h->variant = pick_variant(P, false);
+  h->variant_custom = pick_variant(P, true);
+#define MTB_SETUP_KERNEL(TRAITS, V, SH)                                                                                     \
+  MTB_CUDA(cudaFuncSetAttribute(transport_kernel<TRAITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)); \
+  MTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->bps[V][SH], transport_kernel<TRAITS>, kBlock, h->smem_bytes));  \
+  h->bps[V][SH] = std::max(h->bps[V][SH], 1);
+  MTB_SETUP_KERNEL(TraitsFast, VARIANT_FAST, 0)
+  MTB_SETUP_KERNEL(TraitsFastShare, VARIANT_FAST, 1)
+  MTB_SETUP_KERNEL(TraitsClusters, VARIANT_CLUSTERS, 0)
+  MTB_SETUP_KERNEL(TraitsClustersShare, VARIANT_CLUSTERS, 1)
+  MTB_SETUP_KERNEL(TraitsGeneric, VARIANT_GENERIC, 0)
+  MTB_SETUP_KERNEL(TraitsGenericShare, VARIANT_GENERIC, 1)
+#undef MTB_SETUP_KERNEL
   MTB_CUDA(cudaFuncSetAttribute(trim_one_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   MTB_CUDA(cudaFuncSetAttribute(stopping_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  int bps = 0;
-  if (h->fast)
-    MTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, transport_kernel<TraitsFast>, kBlock, h->smem_bytes));
-  else
-    MTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, transport_kernel<TraitsGeneric>, kBlock, h->smem_bytes));
-  h->blocks_per_sm = std::max(bps, 1);
   if (const char * cap = std::getenv("MYTRIM_B200_BLOCKS_PER_SM")) // tuning knob: resident CTAs per SM
-    h->blocks_per_sm = std::max(1, std::min(h->blocks_per_sm, std::atoi(cap)));
-  if (h->fast)
-    MTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, transport_kernel<TraitsFastShare>, kBlock, h->smem_bytes));
-  else
-    MTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, transport_kernel<TraitsGenericShare>, kBlock, h->smem_bytes));
-  h->blocks_per_sm_share = std::max(bps, 1);
+    for (int v = 0; v < 3; ++v)
+      h->bps[v][0] = std::max(1, std::min(h->bps[v][0], std::atoi(cap)));
   h->dirty = false;
   return MTB_OK;
 }
@@ -475,16 +484,38 @@ ensure_ready(mtb_handle * h)
 }
 
 void
-launch_kernel(mtb_handle * h, const LaunchParams & P, unsigned blocks, bool fast, bool share)
+launch_kernel(mtb_handle * h, const LaunchParams & P, unsigned blocks, Variant v, bool share)
 {
-  if (fast && share)
-    transport_kernel<TraitsFastShare><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
-  else if (fast)
-    transport_kernel<TraitsFast><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
-  else if (share)
-    transport_kernel<TraitsGenericShare><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
-  else
-    transport_kernel<TraitsGeneric><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+  switch (v)
+  {
+    case VARIANT_FAST:
+      if (share)
+        transport_kernel<TraitsFastShare><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+      else
+        transport_kernel<TraitsFast><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+      break;
+    case VARIANT_CLUSTERS:
+      if (share)
+        transport_kernel<TraitsClustersShare><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+      else
+        transport_kernel<TraitsClusters><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+      break;
+    default:
+      if (share)
+        transport_kernel<TraitsGenericShare><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+      else
+        transport_kernel<TraitsGeneric><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+  }
+}
+
+// grid of a launch of n primaries with variant v: resident CTAs only; work sharing below share_below
+// primaries per lane
+unsigned
+launch_grid(const mtb_handle * h, Variant v, uint64_t n, bool * share)
+{
+  const uint64_t max_blocks = (uint64_t)h->sm_count * h->bps[v][0];
+  *share = h->share_enabled && n < h->share_below * max_blocks * kBlock;
+  return (unsigned)(*share ? (uint64_t)h->sm_count * h->bps[v][1] : std::min<uint64_t>(max_blocks, (n + kBlock - 1) / kBlock));
 }
 
 int
@@ -500,6 +531,7 @@ launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, cons
   P.key0 = (uint32_t)seed;
   P.key1 = (uint32_t)(seed >> 32);
   philox_round_keys(P.key0, P.key1, P.rk);
+  P.share_min_E = h->share_min_E;
   P.records = nullptr;
   if (want_records)
   {
@@ -511,22 +543,20 @@ launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, cons
   h->last_n = n;
   if (!n)
     return MTB_OK;
-  const uint64_t max_blocks = (uint64_t)h->sm_count * h->blocks_per_sm;
-  const uint64_t want_blocks = (n + kBlock - 1) / kBlock;
-  // fewer than ~8 cascades per lane: the last wave dominates, let lanes share suspended ions
-  const bool share = h->share_enabled && n < h->share_below * max_blocks * kBlock;
-  const unsigned blocks =
-      (unsigned)(share ? (uint64_t)h->sm_count * h->blocks_per_sm_share : std::min(max_blocks, want_blocks));
+  // beam mode with a species that has no projectile class cannot defer: take a variant with F_CUSTOM
+  const Variant v = (primaries_dev || species_known(h->host, P.beam.Z, P.beam.m)) ? h->variant : h->variant_custom;
+  bool share;
+  const unsigned blocks = launch_grid(h, v, n, &share);
   if ((uint64_t)blocks * kBlock * MTB_STACK_DEPTH * sizeof(StackEntry) > 0xFFFFFFFFull)
     return fail(MTB_EINVAL, "grid too large for 32-bit stack cursors");
   MTB_CUDA(h->d_stacks.ensure((size_t)blocks * kBlock * MTB_STACK_DEPTH));
   P.stacks = h->d_stacks.p;
   MTB_CUDA(h->d_custom_rows.ensure((size_t)blocks * kBlock * (size_t)(2 + P.n_materials + P.n_tclass)));
   P.custom_rows = h->d_custom_rows.p;
-  const bool fast = h->fast && fast_path_ok(P) && (primaries_dev || species_known(h->host, P.beam.Z, P.beam.m));
+  const bool defers = v == VARIANT_FAST && primaries_dev != nullptr; // class-less primaries go to a second launch
   P.index_list = nullptr;
   P.deferred = nullptr;
-  if (fast && primaries_dev)
+  if (defers)
   {
     if (n > 0xFFFFFFFFull)
       return fail(MTB_EINVAL, "more than 2^32 primaries in one launch");
@@ -536,11 +566,11 @@ launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, cons
   MTB_CUDA(cudaMemsetAsync(&P.u64[CNT_NEXT_PRIMARY], 0, sizeof(unsigned long long), h->stream));
   MTB_CUDA(cudaMemsetAsync(&P.u64[CNT_DEFERRED], 0, sizeof(unsigned long long), h->stream));
   MTB_CUDA(cudaEventRecord(h->ev0, h->stream));
-  launch_kernel(h, P, blocks, fast, share);
+  launch_kernel(h, P, blocks, v, share);
   MTB_CUDA(cudaGetLastError());
   MTB_CUDA(cudaEventRecord(h->ev1, h->stream));
   h->timing_pending = true;
-  h->deferred_pending = fast && primaries_dev;
+  h->deferred_pending = defers;
   h->extra_ms = 0.f;
   return MTB_OK;
 }
@@ -559,10 +589,8 @@ run_deferred(mtb_handle * h)
   P.index_list = h->d_deferred.p;
   P.deferred = nullptr;
   P.n_primaries = nd;
-  const uint64_t max_blocks = (uint64_t)h->sm_count * h->blocks_per_sm;
-  const bool share = h->share_enabled && nd < h->share_below * max_blocks * kBlock;
-  const unsigned blocks = (unsigned)(share ? (uint64_t)h->sm_count * h->blocks_per_sm_share
-                                           : std::min<uint64_t>(max_blocks, (nd + kBlock - 1) / kBlock));
+  bool share;
+  const unsigned blocks = launch_grid(h, h->variant_custom, nd, &share);
   if ((uint64_t)blocks * kBlock * MTB_STACK_DEPTH * sizeof(StackEntry) > 0xFFFFFFFFull)
     return fail(MTB_EINVAL, "grid too large for 32-bit stack cursors");
   MTB_CUDA(h->d_stacks.ensure((size_t)blocks * kBlock * MTB_STACK_DEPTH));
@@ -574,7 +602,7 @@ run_deferred(mtb_handle * h)
   MTB_CUDA(cudaEventCreate(&e0));
   MTB_CUDA(cudaEventCreate(&e1));
   MTB_CUDA(cudaEventRecord(e0, h->stream));
-  launch_kernel(h, P, blocks, false, share);
+  launch_kernel(h, P, blocks, h->variant_custom, share);
   MTB_CUDA(cudaGetLastError());
   MTB_CUDA(cudaEventRecord(e1, h->stream));
   MTB_CUDA(cudaStreamSynchronize(h->stream));
@@ -663,6 +691,8 @@ mtb_create(const mtb_config * cfg, mtb_handle ** out)
   h->device = cfg->device;
   if (const char * env = std::getenv("MYTRIM_B200_NO_SHARE"))
     h->share_enabled = env[0] == '0';
+  if (const char * env = std::getenv("MYTRIM_B200_SHARE_MIN_E")) // tuning knob: eV
+    h->share_min_E = (float)std::atof(env);
   if (const char * env = std::getenv("MYTRIM_B200_SHARE_BELOW")) // tuning knob: primaries per lane
     h->share_below = std::strtoull(env, nullptr, 10);
   h->sm_count = prop.multiProcessorCount;
@@ -1121,6 +1151,7 @@ mtb_trim_one(mtb_handle * h, mtb_ion * ion, uint64_t seed, uint64_t uid, int32_t
   P.key0 = (uint32_t)seed;
   P.key1 = (uint32_t)(seed >> 32);
   philox_round_keys(P.key0, P.key1, P.rk);
+  P.share_min_E = h->share_min_E;
   P.records = nullptr;
   P.events = h->d_events.p;
   P.events_cap = events ? capacity : 0;

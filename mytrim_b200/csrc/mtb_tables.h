@@ -146,7 +146,7 @@ struct HostTables
   std::vector<int32_t> tclass_elem;
   std::vector<double> layer_cum;
   std::vector<int32_t> layer_mat, cl_hash, cl_next;
-  std::vector<uint32_t> cl_near;
+  std::vector<uint8_t> cl_dist;
 };
 
 inline void
@@ -513,13 +513,17 @@ build_host_tables(const HostConfig & H, HostTables & T, LaunchParams & P, std::s
       P.kn[i] = g.kn[i];
       P.kd[i] = g.w[i] / (double)g.kn[i];
       P.kn_w[i] = (double)g.kn[i] / g.w[i];
+      P.inv_kn[i] = 1.0 / (double)g.kn[i];
       P.cl_ks[i] = (int)(cmr / P.kd[i]) + 1;
     }
-    // Neighbourhood filter: lookupCluster scans the (2 ks + 1)^3 cells around the cell of the position
-    // (sample_clusters.C:83-131).  Bubbles are sparse (7e-7 per A^3 in the uo2 case: 4 in 59319
-    // cells), so almost every scan visits only empty cells.  Bit c says whether a scan centred on
-    // cell c can see a non-empty cell at all; the device tests it before it scans.
-    T.cl_near.assign((ncell + 31) / 32, 0u);
+    // Distance map in front of the scan.  lookupCluster scans the (2 ks + 1)^3 cells around the cell of
+    // the position (sample_clusters.C:83-131).  Bubbles are sparse (7e-7 per A^3 in the uo2 case: 4 in
+    // 59319 cells), so almost every scan visits only empty cells.  cl_dist[c] = 0 where a scan centred on
+    // cell c can see a non-empty cell; elsewhere the chessboard distance (26-neighbourhood BFS, periodic
+    // where the box is) to the nearest such cell.  The device scans only in cells with distance 0 and,
+    // in a fully periodic box, lets an ion travel (distance - 1) cell edges before it looks again.
+    T.cl_dist.assign(ncell, 255);
+    std::vector<uint32_t> frontier, next;
     for (size_t cell = 0; cell < ncell; ++cell)
     {
       if (T.cl_hash[cell] < 0)
@@ -541,9 +545,50 @@ build_host_tables(const HostConfig & H, HostTables & T, LaunchParams & P, std::s
           for (int k2 : centres[2])
           {
             const size_t cc = (size_t)k0 + (size_t)g.kn[0] * ((size_t)k1 + (size_t)g.kn[1] * (size_t)k2);
-            T.cl_near[cc >> 5] |= 1u << (cc & 31);
+            if (T.cl_dist[cc])
+            {
+              T.cl_dist[cc] = 0;
+              frontier.push_back((uint32_t)cc);
+            }
           }
     }
+    for (int level = 1; level < 255 && !frontier.empty(); ++level)
+    {
+      next.clear();
+      for (uint32_t cell : frontier)
+      {
+        const int c[3] = {(int)(cell % g.kn[0]), (int)((cell / g.kn[0]) % g.kn[1]), (int)(cell / ((size_t)g.kn[0] * g.kn[1]))};
+        for (int d0 = -1; d0 <= 1; ++d0)
+          for (int d1 = -1; d1 <= 1; ++d1)
+            for (int d2 = -1; d2 <= 1; ++d2)
+            {
+              int k[3] = {c[0] + d0, c[1] + d1, c[2] + d2};
+              bool ok = true;
+              for (int i = 0; i < 3; ++i)
+              {
+                if (g.bc[i] == MTB_BC_PBC)
+                  k[i] = (k[i] + g.kn[i]) % g.kn[i];
+                else if (k[i] < 0 || k[i] >= g.kn[i])
+                  ok = false;
+              }
+              if (!ok)
+                continue;
+              const size_t cc = (size_t)k[0] + (size_t)g.kn[0] * ((size_t)k[1] + (size_t)g.kn[1] * (size_t)k[2]);
+              if (T.cl_dist[cc] > level)
+              {
+                T.cl_dist[cc] = (uint8_t)level;
+                next.push_back((uint32_t)cc);
+              }
+            }
+      }
+      frontier.swap(next);
+    }
+    // A path of length s changes the cell index by at most floor(s / kd) + 1 per axis, so an ion that
+    // starts in a cell with distance n and travels less than (n - 1) kd_min ends in a cell with distance
+    // >= 1: the lookup it skips would have returned the matrix.  Leaving a non-periodic box must be
+    // seen by the lookup, so skipping is for fully periodic boxes only.
+    const bool periodic = g.bc[0] == MTB_BC_PBC && g.bc[1] == MTB_BC_PBC && g.bc[2] == MTB_BC_PBC;
+    P.cl_safe_unit = periodic ? (float)(0.999 * std::min(P.kd[0], std::min(P.kd[1], P.kd[2]))) : 0.f;
   }
 
   // tally sizes

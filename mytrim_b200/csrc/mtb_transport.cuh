@@ -51,49 +51,135 @@ host_fetch_max(T * p, U v)
 #define MTB_ATOMIC_MAX(ptr, val) ::mtb::host_fetch_max((ptr), (val))
 #endif
 
-// Compile-time specialisation of the lane loop.  The generic variant reads every option from
-// LaunchParams; the fast variant fixes the options of the north-star workload (UNIVERSAL
-// potential, follow ALL, vacancies_created++, TrimVacCount depth tallies, solid/layered sample
-// without CUT boundaries) so that the unused hook code is not even in the instruction cache.
-template <bool SHARE>
-struct TraitsGenericT
+// Add to a 64-bit block accumulator in shared memory.  Shared memory has no native 64-bit add (the
+// compiler emits a compare-and-swap loop of a dozen instructions per site); two native 32-bit adds
+// with a carry do the same.  The accumulators are only read after the CTA has synchronised.
+MTB_HD void
+block_add(unsigned long long * acc, uint32_t v)
 {
-  static constexpr bool kEvents = false, kGeneric = true, kCustom = true, kShare = SHARE;
-  static constexpr uint32_t kTally = 0;
-};
-typedef TraitsGenericT<false> TraitsGeneric;
-typedef TraitsGenericT<true> TraitsGenericShare;
-struct TraitsEvents
+#if MTB_DEVICE_CODE
+  unsigned int * w = reinterpret_cast<unsigned int *>(acc);
+  const unsigned int old = atomicAdd(w, v);
+  if (old + v < old)
+    atomicAdd(w + 1, 1u);
+#else
+  *acc += v;
+#endif
+}
+
+// Compile-time specialisation of the lane loop.  A variant is a set of features (which run-time
+// options it reads from LaunchParams) plus the tallies it can produce; everything outside the set is
+// not even compiled in.  That matters twice: fewer instructions per collision, and a collision loop
+// that fits the instruction cache (the all-features loop spills out of the 32 KB L1.5 on the uo2
+// workload: "no instruction" was its top stall reason).  pick_variant() chooses the leanest variant
+// that covers a configuration:
+//   FAST      north-star options: UNIVERSAL potential, follow ALL, vacancies_created++, TrimVacCount depth
+//             tallies, solid/layered sample, no CUT boundaries, projectile classes only
+//   CLUSTERS  the tests/uo2 shape: sampleClusters geometry, per-primary species (fission fragments),
+//             ion log / energy partition, otherwise the north-star options
+//   GENERIC   every option at run time
+enum Feature : uint32_t
 {
-  static constexpr bool kEvents = true, kGeneric = true, kCustom = true, kShare = false;
-  static constexpr uint32_t kTally = 0;
+  F_EVENTS = 1u << 0,    // single-ion mode behind mtb_trim_one: every collision is reported, no recoil is followed
+  F_SHARE = 1u << 1,     // lanes without work adopt suspended ions of other lanes of the CTA
+  F_CUSTOM = 1u << 2,    // primaries whose (Z, m) has no projectile class build private table rows
+  F_CLUSTERS = 1u << 3,  // sampleClusters geometry
+  F_GEOM_ANY = 1u << 4,  // SampleWire, SampleBurriedWire
+  F_CUT = 1u << 5,       // CUT boundary conditions (trim.C:344-352)
+  F_POTENTIAL = 1u << 6, // potential chosen at run time (else UNIVERSAL)
+  F_FOLLOW = 1u << 7,    // follow policy chosen at run time (else ALL)
+  F_VACMODEL = 1u << 8,  // vacancy model chosen at run time (else vacancies_created++)
+  F_TALLY_RT = 1u << 9,  // tallies switched at run time within kTally (else exactly kTally)
+  F_DIAG = 1u << 10      // stack high-water mark
 };
-template <bool SHARE>
-struct TraitsFastT
+
+template <uint32_t F, uint32_t TALLY>
+struct TraitsT
 {
-  // kCustom = false: primaries whose species has no class are deferred to the generic kernel
-  // kShare: lanes that run out of primaries adopt suspended ions other lanes donate to a global pool
-  static constexpr bool kEvents = false, kGeneric = false, kCustom = false, kShare = SHARE;
-  static constexpr uint32_t kTally = MTB_TALLY_VAC_DEPTH;
+  static constexpr uint32_t kF = F, kTally = TALLY;
+  static constexpr bool kEvents = (F & F_EVENTS) != 0, kShare = (F & F_SHARE) != 0, kCustom = (F & F_CUSTOM) != 0;
+  static constexpr bool has(uint32_t f) { return (F & f) != 0; }
 };
-typedef TraitsFastT<false> TraitsFast;
-typedef TraitsFastT<true> TraitsFastShare;
+
+constexpr uint32_t kFeatFast = 0;
+constexpr uint32_t kTallyFast = MTB_TALLY_VAC_DEPTH;
+constexpr uint32_t kFeatClusters = F_CUSTOM | F_CLUSTERS | F_TALLY_RT;
+constexpr uint32_t kTallyClusters = MTB_TALLY_IONLOG | MTB_TALLY_PHONON;
+constexpr uint32_t kFeatGeneric =
+    F_CUSTOM | F_CLUSTERS | F_GEOM_ANY | F_CUT | F_POTENTIAL | F_FOLLOW | F_VACMODEL | F_TALLY_RT | F_DIAG;
+constexpr uint32_t kTallyAll = 0xffffffffu;
+
+typedef TraitsT<kFeatFast, kTallyFast> TraitsFast;
+typedef TraitsT<kFeatFast | F_SHARE, kTallyFast> TraitsFastShare;
+typedef TraitsT<kFeatClusters, kTallyClusters> TraitsClusters;
+typedef TraitsT<kFeatClusters | F_SHARE, kTallyClusters> TraitsClustersShare;
+typedef TraitsT<kFeatGeneric, kTallyAll> TraitsGeneric;
+typedef TraitsT<kFeatGeneric | F_SHARE, kTallyAll> TraitsGenericShare;
+typedef TraitsT<kFeatGeneric | F_EVENTS, kTallyAll> TraitsEvents;
 
 template <class TR>
 MTB_HD bool
 tally_on(const LaunchParams & P, uint32_t bit)
 {
-  return TR::kGeneric ? (P.tally_mask & bit) != 0 : (TR::kTally & bit) != 0;
+  return (TR::kTally & bit) != 0 && (!TR::has(F_TALLY_RT) || (P.tally_mask & bit) != 0);
+}
+
+enum Variant
+{
+  VARIANT_FAST = 0,
+  VARIANT_CLUSTERS,
+  VARIANT_GENERIC
+};
+
+// Features a configuration needs (F_CUSTOM is decided per primary: variants without it hand
+// class-less primaries to a second launch of a variant that has it).
+inline uint32_t
+needed_features(const LaunchParams & P)
+{
+  uint32_t f = 0;
+  if (P.geom_kind == MTB_GEOM_CLUSTERS)
+    f |= F_CLUSTERS;
+  else if (P.geom_kind != MTB_GEOM_SOLID && P.geom_kind != MTB_GEOM_LAYERS)
+    f |= F_GEOM_ANY;
+  if (P.bc[0] == MTB_BC_CUT || P.bc[1] == MTB_BC_CUT || P.bc[2] == MTB_BC_CUT)
+    f |= F_CUT;
+  // outside a non-periodic clusters box the lookup returns vacuum: same code path as CUT-less generic
+  if (P.potential != MTB_POT_UNIVERSAL)
+    f |= F_POTENTIAL;
+  if (P.follow != MTB_FOLLOW_ALL)
+    f |= F_FOLLOW;
+  if (P.vacancy_model != MTB_VAC_COUNT)
+    f |= F_VACMODEL;
+  return f;
+}
+
+inline bool
+variant_covers(uint32_t feat, uint32_t tally, const LaunchParams & P)
+{
+  const uint32_t want = P.tally_mask & ~(uint32_t)MTB_TALLY_RECORDS;
+  if (needed_features(P) & ~feat)
+    return false;
+  return (feat & F_TALLY_RT) ? (want & ~tally) == 0 : want == tally;
+}
+
+// The leanest variant that covers the configuration; `custom` = the launch may contain primaries
+// without a projectile class and cannot defer them (second launch of a deferral, beam mode).
+inline Variant
+pick_variant(const LaunchParams & P, bool custom)
+{
+  if (!custom && variant_covers(kFeatFast, kTallyFast, P))
+    return VARIANT_FAST;
+  if (variant_covers(kFeatClusters, kTallyClusters, P))
+    return VARIANT_CLUSTERS;
+  return VARIANT_GENERIC;
 }
 
 // Does this configuration qualify for TraitsFast?  (The launcher additionally requires that every
-// primary species has a projectile class; per-primary masses go through the generic kernel.)
+// primary species has a projectile class; per-primary masses go through a variant with F_CUSTOM.)
 inline bool
 fast_path_ok(const LaunchParams & P)
 {
-  return P.potential == MTB_POT_UNIVERSAL && P.follow == MTB_FOLLOW_ALL && P.vacancy_model == MTB_VAC_COUNT &&
-         (P.tally_mask & ~(uint32_t)MTB_TALLY_RECORDS) == MTB_TALLY_VAC_DEPTH && (P.geom_kind == MTB_GEOM_SOLID || P.geom_kind == MTB_GEOM_LAYERS) &&
-         P.bc[0] != MTB_BC_CUT && P.bc[1] != MTB_BC_CUT && P.bc[2] != MTB_BC_CUT;
+  return variant_covers(kFeatFast, kTallyFast, P);
 }
 
 // Block-local views: the small tables staged in shared memory plus block accumulators.
@@ -146,9 +232,28 @@ u64_block_size(const LaunchParams & P)
 // geometry: the lookupMaterial() family.  Returns the de-duplicated
 // material id, or -1 for vacuum; *cluster receives the cluster index (clusters geometry).
 // ---------------------------------------------------------------------------------------------
+// j mod kn for a cell index at most one period outside [0, kn) (the scan range is [k - ks, k + ks]
+// with 0 <= k < kn); the general modulo only when the neighbourhood is wider than the hash itself
 MTB_HD int
-lookup_cluster(const LaunchParams & P, double px, double py, double pz)
+wrap_cell(int j, int kn)
 {
+  if (j < 0)
+    j += kn;
+  else if (j >= kn)
+    j -= kn;
+  if (j < 0 || j >= kn)
+  {
+    j %= kn;
+    if (j < 0)
+      j += kn;
+  }
+  return j;
+}
+
+MTB_HD_COLD int
+lookup_cluster(const LaunchParams & P, double px, double py, double pz, float * safe)
+{
+  *safe = 0.0f;
   // sampleClusters::lookupCluster(pos, 0) — sample_clusters.C:59-133
   const double pos[3] = {px, py, pz};
   int kc[3], k1[3], k2[3];
@@ -167,9 +272,16 @@ lookup_cluster(const LaunchParams & P, double px, double py, double pz)
         return -2;
       if (P.bc[i] == MTB_BC_INF)
         return -1;
-      k = k % P.kn[i];
-      if (k < 0)
-        k += P.kn[i];
+      // k mod kn in floating point (all values are integers far below 2^53: exact; an integer
+      // modulo by a run-time divisor is a 25-instruction sequence and this branch is the common case
+      // for ions that left the periodic box)
+      const double kn = (double)P.kn[i];
+      double r = fl - kn * floor(fl * P.inv_kn[i]);
+      if (r < 0.0)
+        r += kn;
+      else if (r >= kn)
+        r -= kn;
+      k = (int)r;
     }
     kc[i] = k;
     k1[i] = k - P.cl_ks[i];
@@ -180,36 +292,34 @@ lookup_cluster(const LaunchParams & P, double px, double py, double pz)
       k2[i] = P.kn[i] - 1;
   }
   {
-    // neighbourhood filter (mtb_tables.h): nothing to find around this cell in almost every step.
+    // distance map (mtb_tables.h): nothing to find around this cell in almost every lookup, and in a
+    // periodic box nothing within *safe of path length either.
     // A position exactly on the upper face (pos == w under rounding) can index cell kn: scan then.
     const int inside = (kc[0] < P.kn[0]) & (kc[1] < P.kn[1]) & (kc[2] < P.kn[2]) & (kc[0] >= 0) & (kc[1] >= 0) & (kc[2] >= 0);
     if (inside)
     {
       const uint32_t cell = (uint32_t)kc[0] + (uint32_t)P.kn[0] * ((uint32_t)kc[1] + (uint32_t)P.kn[1] * (uint32_t)kc[2]);
 #if MTB_DEVICE_CODE
-      const uint32_t word = __ldg(P.cl_near + (cell >> 5));
+      const uint32_t n = __ldg(P.cl_dist + cell);
 #else
-      const uint32_t word = P.cl_near[cell >> 5];
+      const uint32_t n = P.cl_dist[cell];
 #endif
-      if (!((word >> (cell & 31)) & 1u))
+      if (n)
+      {
+        *safe = (float)(n - 1u) * P.cl_safe_unit;
         return -1;
+      }
     }
   }
   for (int j0 = k1[0]; j0 <= k2[0]; ++j0)
   {
-    int c0 = j0 % P.kn[0];
-    if (c0 < 0)
-      c0 += P.kn[0];
+    const int c0 = wrap_cell(j0, P.kn[0]);
     for (int j1 = k1[1]; j1 <= k2[1]; ++j1)
     {
-      int c1 = j1 % P.kn[1];
-      if (c1 < 0)
-        c1 += P.kn[1];
+      const int c1 = wrap_cell(j1, P.kn[1]);
       for (int j2 = k1[2]; j2 <= k2[2]; ++j2)
       {
-        int c2 = j2 % P.kn[2];
-        if (c2 < 0)
-          c2 += P.kn[2];
+        const int c2 = wrap_cell(j2, P.kn[2]);
         int l = P.cl_hash[c0 + P.kn[0] * (c1 + P.kn[1] * c2)];
         while (l >= 0)
         {
@@ -234,49 +344,29 @@ lookup_cluster(const LaunchParams & P, double px, double py, double pz)
 
 template <class TR>
 MTB_HD int
-lookup_material(const LaunchParams & P, const BlockCtx & S, double px, double py, double pz, int * cluster)
+lookup_material(const LaunchParams & P, const BlockCtx & S, double px, double py, double pz, int * cluster, float * safe)
 {
   *cluster = -1;
-  if (!TR::kGeneric)
+  *safe = 0.0f;
+  if (TR::has(F_CLUSTERS) && P.geom_kind == MTB_GEOM_CLUSTERS) // sample_clusters.C:43-55
   {
-    if (P.geom_kind == MTB_GEOM_SOLID || P.n_layers == 1)
+    const int l = lookup_cluster(P, px, py, pz, safe);
+    if (l == -2)
+      return -1;
+    if (l == -1)
       return 0;
-    int lo = 0, hi = P.n_layers - 1;
-    while (lo < hi)
-    {
-      const int mid = (lo + hi) >> 1;
-      if (px < S.layer_cum[mid])
-        hi = mid;
-      else
-        lo = mid + 1;
-    }
-    return S.layer_mat[lo];
+    *cluster = l;
+    return 1;
   }
-  switch (P.geom_kind)
+  if (TR::has(F_GEOM_ANY))
   {
-    case MTB_GEOM_SOLID: // sample_solid.C:25-29
-      return 0;
-    case MTB_GEOM_LAYERS: // sample_layers.C:26-49
-    {
-      // first layer whose cumulative thickness exceeds x; beyond the stack -> last layer
-      int lo = 0, hi = P.n_layers - 1;
-      while (lo < hi)
-      {
-        const int mid = (lo + hi) >> 1;
-        if (px < S.layer_cum[mid])
-          hi = mid;
-        else
-          lo = mid + 1;
-      }
-      return S.layer_mat[lo];
-    }
-    case MTB_GEOM_WIRE: // sample_wire.C:37-46
+    if (P.geom_kind == MTB_GEOM_WIRE) // sample_wire.C:37-46
     {
       const double x = (px / P.w[0]) * 2.0 - 1.0;
       const double y = (py / P.w[1]) * 2.0 - 1.0;
       return (x * x + y * y) > 1.0 ? -1 : 0;
     }
-    case MTB_GEOM_BURIED_WIRE: // sample_burried_wire.C:38-55
+    if (P.geom_kind == MTB_GEOM_BURIED_WIRE) // sample_burried_wire.C:38-55
     {
       if (pz < 0.0 && pz >= -250.0)
         return 1;
@@ -286,18 +376,21 @@ lookup_material(const LaunchParams & P, const BlockCtx & S, double px, double py
       const double y = (py / P.w[1]) * 2.0 - 1.0;
       return (x * x + y * y) > 1.0 ? 1 : 0;
     }
-    case MTB_GEOM_CLUSTERS: // sample_clusters.C:43-55
-    {
-      const int l = lookup_cluster(P, px, py, pz);
-      if (l == -2)
-        return -1;
-      if (l == -1)
-        return 0;
-      *cluster = l;
-      return 1;
-    }
   }
-  return -1;
+  // sample_solid.C:25-29, sample_layers.C:26-49: the first layer whose cumulative thickness exceeds x;
+  // beyond the stack -> last layer
+  if (P.geom_kind == MTB_GEOM_SOLID || P.n_layers == 1)
+    return 0;
+  int lo = 0, hi = P.n_layers - 1;
+  while (lo < hi)
+  {
+    const int mid = (lo + hi) >> 1;
+    if (px < S.layer_cum[mid])
+      hi = mid;
+    else
+      lo = mid + 1;
+  }
+  return S.layer_mat[lo];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -314,6 +407,7 @@ struct Lane
   uint32_t packed;
   int32_t tag;
   int32_t pcls;    // projectile class of the ion in flight, -1: this lane's per-primary rows
+  float dsafe;     // clusters geometry: path length left before the next lookup can matter (cl_dist)
   // current cascade
   uint32_t prim;   // index of the cascade's primary within this launch (global = first_index + prim)
   int32_t prim_pcls;
@@ -356,7 +450,7 @@ as_row(const PairE & v)
 
 // A primary whose (Z, m) has no class (e.g. a fission fragment with its own mass) gets private rows
 // [ProjClass | PairM per material | PairE per target class] in the lane's scratch area.
-MTB_HD void
+MTB_HD_COLD void
 build_custom_rows(const LaunchParams & P, const BlockCtx & S, float4_t * rows, int Z, float m)
 {
   const ProjClass c = make_proj_class(S.ionz[Z], Z, m);
@@ -451,6 +545,7 @@ stack_load(const StackEntry * src, Lane & L)
   L.pz = __longlong_as_double((long long)(((unsigned long long)b.y << 32) | b.x));
   L.E = __longlong_as_double((long long)(((unsigned long long)b.w << 32) | b.z));
   L.Ecur = (float)L.E;
+  L.dsafe = 0.0f;
   L.dx = __uint_as_float(c.x);
   L.dy = __uint_as_float(c.y);
   L.dz = __uint_as_float(c.z);
@@ -465,6 +560,7 @@ stack_load(const StackEntry * src, Lane & L)
   L.pz = e.pos[2];
   L.E = e.E;
   L.Ecur = (float)e.E;
+  L.dsafe = 0.0f;
   L.dx = e.dir[0];
   L.dy = e.dir[1];
   L.dz = e.dir[2];
@@ -475,6 +571,33 @@ stack_load(const StackEntry * src, Lane & L)
 #endif
 }
 
+// One half of an ion-log entry (birth: state = -1, position/energy at birth; death: final state,
+// position and energy); mtb_get_ion_log joins the halves by uid.
+MTB_HD_COLD void
+ionlog_append(const LaunchParams & P, double x, double y, double z, double E, uint64_t uid, uint32_t prim, int Z, uint32_t packed,
+              int32_t tag, int state)
+{
+  const unsigned long long i = MTB_ATOMIC_ADD(&P.u64[CNT_IONLOG_N], 1ull);
+  if (i >= P.ionlog_cap)
+    return;
+  mtb_ion_log & o = P.ionlog[i];
+  const bool birth = state < 0;
+  o.pos0[0] = birth ? x : 0.0;
+  o.pos0[1] = birth ? y : 0.0;
+  o.pos0[2] = birth ? z : 0.0;
+  o.pos1[0] = birth ? 0.0 : x;
+  o.pos1[1] = birth ? 0.0 : y;
+  o.pos1[2] = birth ? 0.0 : z;
+  o.E0 = birth ? E : 0.0;
+  o.E1 = birth ? 0.0 : E;
+  o.uid = uid;
+  o.primary = P.first_index + prim;
+  o.Z = Z;
+  o.gen = (int32_t)((packed >> GEN_SHIFT) & GEN_MASK);
+  o.tag = tag;
+  o.state = state;
+}
+
 template <class TR>
 MTB_HD void
 log_birth(const LaunchParams & P, const Lane & L, int Z)
@@ -483,22 +606,7 @@ log_birth(const LaunchParams & P, const Lane & L, int Z)
     return;
   if (P.ionlog_z && Z != P.ionlog_z)
     return;
-  const unsigned long long i = MTB_ATOMIC_ADD(&P.u64[CNT_IONLOG_N], 1ull);
-  if (i >= P.ionlog_cap)
-    return;
-  mtb_ion_log & o = P.ionlog[i];
-  o.pos0[0] = L.px;
-  o.pos0[1] = L.py;
-  o.pos0[2] = L.pz;
-  o.pos1[0] = o.pos1[1] = o.pos1[2] = 0.0;
-  o.E0 = L.E;
-  o.E1 = 0.0;
-  o.uid = L.uid;
-  o.primary = P.first_index + L.prim;
-  o.Z = Z;
-  o.gen = (int32_t)((L.packed >> GEN_SHIFT) & GEN_MASK);
-  o.tag = L.tag;
-  o.state = -1; // birth half; mtb_get_ion_log joins it with the death half
+  ionlog_append(P, L.px, L.py, L.pz, L.E, L.uid, L.prim, Z, L.packed, L.tag, -1);
 }
 
 // an ion has stopped (or left the sample): primary record + death half of the ion log
@@ -521,22 +629,7 @@ finish_ion(const LaunchParams & P, const BlockCtx & S, const Lane & L, const flo
     const int Z = current_Z(L, S, rows);
     if (P.ionlog_z && Z != P.ionlog_z)
       return;
-    const unsigned long long i = MTB_ATOMIC_ADD(&P.u64[CNT_IONLOG_N], 1ull);
-    if (i >= P.ionlog_cap)
-      return;
-    mtb_ion_log & o = P.ionlog[i];
-    o.pos0[0] = o.pos0[1] = o.pos0[2] = 0.0;
-    o.pos1[0] = L.px;
-    o.pos1[1] = L.py;
-    o.pos1[2] = L.pz;
-    o.E0 = 0.0;
-    o.E1 = L.E;
-    o.uid = L.uid;
-    o.primary = P.first_index + L.prim;
-    o.Z = Z;
-    o.gen = (int32_t)((L.packed >> GEN_SHIFT) & GEN_MASK);
-    o.tag = L.tag;
-    o.state = state;
+    ionlog_append(P, L.px, L.py, L.pz, L.E, L.uid, L.prim, Z, L.packed, L.tag, state);
   }
 }
 
@@ -547,7 +640,7 @@ depth_tally(const LaunchParams & P, const BlockCtx & S, unsigned int * smem_hist
     return;
   if (x >= P.hist_bins)
   {
-    MTB_ATOMIC_ADD(&S.blk_u64[CNT_CLAMPED], 1ull);
+    block_add(&S.blk_u64[CNT_CLAMPED], 1u);
     x = P.hist_bins - 1;
   }
   if (x < P.smem_hist_bins)
@@ -562,12 +655,7 @@ MTB_HD void
 vacancy_creation(const LaunchParams & P, const BlockCtx & S, Lane & L, const DevMaterial & M,
                  const DevElement & el, double rx, double ry, float Erec, int rec_gen)
 {
-  if (!TR::kGeneric)
-  {
-    L.casVac++;
-    return;
-  }
-  switch (P.vacancy_model)
+  switch (TR::has(F_VACMODEL) ? P.vacancy_model : (int)MTB_VAC_COUNT)
   {
     case MTB_VAC_COUNT: // trim.C:439-443
       L.casVac++;
@@ -597,19 +685,19 @@ vacancy_creation(const LaunchParams & P, const BlockCtx & S, Lane & L, const Dev
       break;
   }
   const int x = (int)rx; // truncation toward zero — TrimVacCount.C:35 (the depth histogram itself: caller)
-  if ((P.tally_mask & MTB_TALLY_VAC_ENERGY) && x >= 0) // TrimVacEnergyCount.C:31-53
+  if (tally_on<TR>(P, MTB_TALLY_VAC_ENERGY) && x >= 0) // TrimVacEnergyCount.C:31-53
   {
     int le = (int)flog(Erec);
     le = le < 0 ? 0 : (le >= P.evac_rows ? P.evac_rows - 1 : le);
     int xb = x;
     if (xb >= P.hist_bins)
     {
-      MTB_ATOMIC_ADD(&S.blk_u64[CNT_CLAMPED], 1ull);
+      block_add(&S.blk_u64[CNT_CLAMPED], 1u);
       xb = P.hist_bins - 1;
     }
     MTB_ATOMIC_ADD(&P.u64[off_evac(P) + (size_t)le * (size_t)P.hist_bins + (size_t)xb], 1ull);
   }
-  if (P.tally_mask & MTB_TALLY_VACMAP) // TrimVacMap::vacancyCreation — trim.C:483-501
+  if (tally_on<TR>(P, MTB_TALLY_VACMAP)) // TrimVacMap::vacancyCreation — trim.C:483-501
   {
     int vx = (int)((rx * MTB_VMAP_NX) / P.w[0]);
     int vy = (int)((ry * MTB_VMAP_NY) / P.w[1]);
@@ -643,12 +731,12 @@ close_subtree(const LaunchParams & P, const BlockCtx & S, Lane & L, uint32_t n_p
     MTB_ATOMIC_ADD(&r.steps, L.casSteps);
     MTB_ATOMIC_ADD(&r.ions, L.casIons);
   }
-  MTB_ATOMIC_ADD(&S.blk_u64[CNT_VAC], (unsigned long long)L.casVac);
-  MTB_ATOMIC_ADD(&S.blk_u64[CNT_REPL], (unsigned long long)L.casRepl);
-  MTB_ATOMIC_ADD(&S.blk_u64[CNT_STEPS], (unsigned long long)L.casSteps);
-  MTB_ATOMIC_ADD(&S.blk_u64[CNT_IONS], (unsigned long long)L.casIons);
-  MTB_ATOMIC_ADD(&S.blk_u64[CNT_QUEUED], (unsigned long long)(L.casIons - n_prim));
-  MTB_ATOMIC_ADD(&S.blk_u64[CNT_PRIMARIES], (unsigned long long)n_prim);
+  block_add(&S.blk_u64[CNT_VAC], L.casVac);
+  block_add(&S.blk_u64[CNT_REPL], L.casRepl);
+  block_add(&S.blk_u64[CNT_STEPS], L.casSteps);
+  block_add(&S.blk_u64[CNT_IONS], L.casIons);
+  block_add(&S.blk_u64[CNT_QUEUED], L.casIons - n_prim);
+  block_add(&S.blk_u64[CNT_PRIMARIES], n_prim);
   MTB_ATOMIC_ADD(&S.blk_f64[0], L.casEel);
   MTB_ATOMIC_ADD(&S.blk_f64[1], L.casEnuc);
 }
@@ -765,10 +853,13 @@ stack_depth(uint32_t cursor)
 // Suspend an ion: on the lane's private stack, or — when lanes are idle — in the shared pool.
 template <class TR>
 MTB_HD void
-suspend_ion(const LaunchParams & P, const BlockCtx & S, uint32_t & sp, const Lane & ion, uint64_t prim)
+suspend_ion(const LaunchParams & P, const BlockCtx & S, uint32_t & sp, const Lane & ion, uint64_t prim, float e_small)
 {
 #if MTB_DEVICE_CODE
-  if (TR::kShare && vload(&S.pool_ctl[POOL_IDLE]) > 0 && pool_try_push(S, ion, prim))
+  // Donate only when BOTH ions of the pair carry a subtree worth a hand-over (e_small = the smaller of
+  // the two energies): a lane that gives its big ion away and keeps a 30 eV recoil is idle itself
+  // three steps later, and every adoption costs a few hundred instructions at one active lane.
+  if (TR::kShare && e_small >= P.share_min_E && vload(&S.pool_ctl[POOL_IDLE]) > 0 && pool_try_push(S, ion, prim))
     return;
 #endif
   (void)S;
@@ -791,7 +882,7 @@ MTB_HD void
 lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
 {
   constexpr bool EVENTS = TR::kEvents;
-  const int potential = TR::kGeneric ? P.potential : (int)MTB_POT_UNIVERSAL;
+  const int potential = TR::has(F_POTENTIAL) ? P.potential : (int)MTB_POT_UNIVERSAL;
   Lane L;
   float4_t * const rows =
       TR::kCustom ? P.custom_rows + (size_t)lane_global * (size_t)(2 + P.n_materials + P.n_tclass) : nullptr;
@@ -843,9 +934,15 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
 #if MTB_DEVICE_CODE
           else if (TR::kShare)
           {
-            // few primaries per lane: deal them round-robin over the CTAs (CTA-local counter) so that
-            // every CTA has something to share among its lanes
-            idx = (unsigned long long)blockIdx.x + (unsigned long long)gridDim.x * atomicAdd(&S.pool_ctl[POOL_CTL_COUNT], 1ull);
+            // The first primary of every lane is dealt round-robin over the CTAs (CTA-local counter), so
+            // that a launch with fewer primaries than lanes gives every CTA something to share among
+            // its lanes; the rest comes from the device-wide counter like in the plain kernels (a
+            // static split of ALL primaries over the CTAs cost 10 % at 16 primaries per lane).
+            const unsigned long long k = atomicAdd(&S.pool_ctl[POOL_CTL_COUNT], 1ull);
+            if (k < (unsigned long long)blockDim.x)
+              idx = (unsigned long long)blockIdx.x + (unsigned long long)gridDim.x * k;
+            else
+              idx = (unsigned long long)gridDim.x * blockDim.x + atomicAdd(&P.u64[CNT_NEXT_PRIMARY], 1ull);
           }
 #endif
           else
@@ -883,6 +980,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           }
           L.E = src.E;
           L.Ecur = (float)src.E;
+          L.dsafe = 0.0f;
           L.ic = 0;
           L.prim = (uint32_t)idx;
           L.uid = EVENTS ? P.single_uid : P.first_index + idx;
@@ -925,12 +1023,18 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
               atomicAdd(&S.pool_ctl[POOL_IDLE], (unsigned long long)-1ll);
               const mtb_ion & src = P.primaries ? P.primaries[aprim] : P.beam;
               L.prim = (uint32_t)aprim;
-              L.pZ = src.Z;
-              L.pm = (float)src.m;
               L.Ef = (float)src.Ef;
-              L.prim_pcls = find_class(P, S, L.pZ, L.pm);
-              if (TR::kCustom && L.prim_pcls < 0)
-                build_custom_rows(P, S, rows, L.pZ, L.pm);
+              L.prim_pcls = 0;
+              if ((L.packed & SPECIES_MASK) == SPECIES_PRIMARY)
+              {
+                // only the primary itself flies as its own species: a recoil subtree needs neither the
+                // class of the primary nor (per-primary masses) its private rows
+                const int aZ = src.Z;
+                const float am = (float)src.m;
+                L.prim_pcls = find_class(P, S, aZ, am);
+                if (TR::kCustom && L.prim_pcls < 0)
+                  build_custom_rows(P, S, rows, aZ, am);
+              }
               set_species(L, S);
               L.casEel = L.casEnuc = 0.0;
               L.casVac = L.casRepl = L.casSteps = L.casIons = 0;
@@ -972,19 +1076,25 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       break;
     }
     ++L.ic;
-    int cluster;
-    const int mi = lookup_material<TR>(P, S, L.px, L.py, L.pz, &cluster);
+    int cluster = -1;
+    int mi = 0;
+    if (!(TR::has(F_CLUSTERS) && L.dsafe > 0.0f)) // else: clusters geometry, still provably in the matrix
+    {
+      float safe;
+      mi = lookup_material<TR>(P, S, L.px, L.py, L.pz, &cluster, &safe);
+      L.dsafe = safe;
+    }
     if (mi < 0)
     {
       // vacuum: the reference breaks out with the state still MOVING (trim.C:80-82)
-      MTB_ATOMIC_ADD(&S.blk_u64[CNT_LEFT], 1ull);
+      block_add(&S.blk_u64[CNT_LEFT], 1u);
       --L.ic;
       finish_ion<TR>(P, S, L, rows, MTB_MOVING);
       active = false;
       break;
     }
     const DevMaterial & M = S.materials[mi];
-    const int mtag = (TR::kGeneric && P.geom_kind == MTB_GEOM_CLUSTERS && mi == 1) ? cluster : M.tag;
+    const int mtag = (TR::has(F_CLUSTERS) && P.geom_kind == MTB_GEOM_CLUSTERS && mi == 1) ? cluster : M.tag;
     L.casSteps++;
 
     // v_norm(dir) — trim.C:85.  Every ion enters the loop with a unit direction (primaries are
@@ -1093,6 +1203,8 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     // recoil is born at the previous collision site — trim.C:306-310
     const double rx = L.px, ry = L.py, rz = L.pz;
     const float flight = (ls - P.tau) * P.inv_scale;
+    const float dsafe_here = L.dsafe; // of the collision site: a recoil starts there
+    L.dsafe -= fabsf(flight);
     L.px += (double)(L.dx * flight);
     L.py += (double)(L.dy * flight);
     L.pz += (double)(L.dz * flight);
@@ -1135,13 +1247,13 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
 
     // CUT boundaries — trim.C:344-352
     int state = MTB_MOVING;
-    if (TR::kGeneric &&
+    if (TR::has(F_CUT) &&
         ((P.bc[0] == MTB_BC_CUT && (L.px > P.w[0] || L.px < 0.0)) ||
         (P.bc[1] == MTB_BC_CUT && (L.py > P.w[1] || L.py < 0.0)) ||
         (P.bc[2] == MTB_BC_CUT && (L.pz > P.w[2] || L.pz < 0.0))))
     {
       state = MTB_LOST;
-      MTB_ATOMIC_ADD(&S.blk_u64[CNT_LOST], 1ull);
+      block_add(&S.blk_u64[CNT_LOST], 1u);
     }
 
     // fate of recoil and projectile — trim.C:357-411
@@ -1155,7 +1267,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
         above = true;
         if (tally_on<TR>(P, MTB_TALLY_PHONON))
           L.casEnuc += (double)el.Elbind; // TrimPhononOut::followRecoil
-        follow = !EVENTS && (!TR::kGeneric || P.follow == MTB_FOLLOW_ALL ||
+        follow = !EVENTS && (!TR::has(F_FOLLOW) || P.follow == MTB_FOLLOW_ALL ||
                              (P.follow == MTB_FOLLOW_GEN_LT && rec_gen < P.follow_max_gen));
         const bool vacancy = E2 > el.Edisp;
         if (vacancy)
@@ -1234,7 +1346,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       if (state == MTB_MOVING && !keep_projectile)
       {
         // both move on and the recoil has less energy: suspend the projectile, fly the recoil
-        suspend_ion<TR>(P, S, sp, L, L.prim);
+        suspend_ion<TR>(P, S, sp, L, L.prim, Erec);
       }
       if (state != MTB_MOVING)
         finish_ion<TR>(P, S, L, rows, state);
@@ -1254,7 +1366,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           R.prim = L.prim;
           log_birth<TR>(P, R, el.Z);
         }
-        suspend_ion<TR>(P, S, sp, R, L.prim);
+        suspend_ion<TR>(P, S, sp, R, L.prim, E2);
       }
       else
       {
@@ -1267,9 +1379,10 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
         L.packed = rpacked;
         L.tag = mtag;
         L.pcls = el.tcls;
+        L.dsafe = dsafe_here;
         log_birth<TR>(P, L, el.Z);
       }
-      if (TR::kGeneric && stack_depth(sp) > sp_max)
+      if (TR::has(F_DIAG) && stack_depth(sp) > sp_max)
         sp_max = stack_depth(sp); // diagnostic high-water mark (generic kernels only)
     }
     else if (state != MTB_MOVING)

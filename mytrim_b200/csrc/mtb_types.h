@@ -217,8 +217,12 @@ struct LaunchParams
   const int32_t * cl_next;      // cl[]
   const double * cl_xyzr;       // 4 per cluster
   double kd[3];
+  double inv_kn[3];             // 1 / kn
   double kn_w[3];               // kn / w: cell index without a division (exact path on near-ties)
-  const uint32_t * cl_near;     // one bit per hash cell: some cell of its scan neighbourhood holds a cluster
+  const uint8_t * cl_dist;      // per hash cell: chessboard distance (in cells, capped at 255) to the nearest cell
+                                // whose scan neighbourhood holds a cluster; 0 = scan here
+  float cl_safe_unit;           // path length an ion can travel per unit of cl_dist above 1 without meeting a
+                                // cluster (smallest cell edge, with a margin); 0 = no skipping (non-periodic box)
   // primaries
   const mtb_ion * primaries;    // device copy, or null for beam mode
   mtb_ion beam;
@@ -226,6 +230,7 @@ struct LaunchParams
   const uint32_t * index_list;  // optional: launch over primaries[index_list[k]], k < n_primaries
   uint32_t * deferred;          // fast kernel: indices of primaries without a projectile class
   uint32_t key0, key1;
+  float share_min_E; // work sharing: smallest energy [eV] of a pair of ions one of which may be donated
   uint32_t rk[20]; // Philox round keys (philox_round_keys): the key schedule is a launch constant
   // outputs
   unsigned long long * u64;     // counter + histogram block

@@ -55,7 +55,7 @@ hs_prepare(hs_engine * e)
   P.layer_mat = e->T.layer_mat.data();
   P.cl_hash = e->T.cl_hash.data();
   P.cl_next = e->T.cl_next.data();
-  P.cl_near = e->T.cl_near.data();
+  P.cl_dist = e->T.cl_dist.data();
   P.cl_xyzr = e->host.cluster_xyzr.data();
   e->u64.assign(u64_block_size(P), 0ull);
   e->f64[0] = e->f64[1] = 0.0;
@@ -188,11 +188,22 @@ hs_run(hs_engine * e, uint64_t n, const mtb_ion * primaries, uint64_t seed, uint
   P.index_list = nullptr;
   P.deferred = nullptr;
   P.u64[CNT_DEFERRED] = 0;
-  if (fast_path_ok(P) && !e->force_generic)
+  // same variant selection as mtb_engine.cu::launch_transport / run_deferred
+  const Variant v = e->force_generic ? VARIANT_GENERIC : pick_variant(P, false);
+  const Variant vc = e->force_generic ? VARIANT_GENERIC : pick_variant(P, true);
+  auto run_variant = [&](Variant which) {
+    if (which == VARIANT_FAST)
+      lane_loop<TraitsFast>(P, S, 0);
+    else if (which == VARIANT_CLUSTERS)
+      lane_loop<TraitsClusters>(P, S, 0);
+    else
+      lane_loop<TraitsGeneric>(P, S, 0);
+  };
+  if (v == VARIANT_FAST)
   {
     std::vector<uint32_t> deferred(n ? n : 1);
     P.deferred = deferred.data();
-    lane_loop<TraitsFast>(P, S, 0);
+    run_variant(v);
     const unsigned long long nd = P.u64[CNT_DEFERRED];
     if (nd)
     {
@@ -201,12 +212,12 @@ hs_run(hs_engine * e, uint64_t n, const mtb_ion * primaries, uint64_t seed, uint
       P.deferred = nullptr;
       P.n_primaries = nd;
       P.u64[CNT_NEXT_PRIMARY] = 0;
-      lane_loop<TraitsGeneric>(P, S, 0);
+      run_variant(vc);
       P.index_list = nullptr;
     }
   }
   else
-    lane_loop<TraitsGeneric>(P, S, 0);
+    run_variant(v);
   hs_flush(e);
   return P.u64[CNT_ERROR] ? MTB_ESTACK : MTB_OK;
 }

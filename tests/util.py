@@ -186,6 +186,7 @@ CONFIGS = {
     "h_on_fe_100keV": dict(ion=(1, 1.008, 1.0e5), materials=[FE], thicknesses=[100000.0]),
     "he_on_fe_100keV": dict(ion=(2, 4.003, 1.0e5), materials=[FE], thicknesses=[100000.0]),
     "c_on_w_1MeV": dict(ion=(6, 12.0, 1.0e6), materials=[W], thicknesses=[10000.0]),
+    "xe_on_uo2_80MeV": dict(ion=(54, 132.0, 8.0e7), materials=[UO2], thicknesses=[1.0e7]),
     "xe_on_zro2_500keV": dict(ion=(54, 131.0, 5.0e5), materials=[ZRO2] * 50, thicknesses=[10.0] * 50,
                               box=(500.0, 100.0, 100.0)),
 }
