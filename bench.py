@@ -144,7 +144,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--primaries", type=int, default=1 << 22, help="cascades per GPU per step")
+    ap.add_argument("--primaries", type=int, default=1 << 23, help="cascades per GPU per step")
     ap.add_argument("--ref-cascades", type=int, default=0, help="cascades per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

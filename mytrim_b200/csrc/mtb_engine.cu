@@ -71,8 +71,8 @@ constexpr int
 min_blocks()
 {
   return TR::kF & F_GEOM_ANY ? (TR::kShare ? MTB_MIN_BLOCKS_GENERIC_SHARE : MTB_MIN_BLOCKS_GENERIC)
-         : TR::kF & F_CLUSTERS ? (TR::kShare ? MTB_MIN_BLOCKS_CLUSTERS_SHARE : MTB_MIN_BLOCKS_CLUSTERS)
-                               : (TR::kShare ? MTB_MIN_BLOCKS_FAST_SHARE : MTB_MIN_BLOCKS_FAST);
+         : TR::kF & (F_CLUSTERS | F_FOLLOW) ? (TR::kShare ? MTB_MIN_BLOCKS_CLUSTERS_SHARE : MTB_MIN_BLOCKS_CLUSTERS)
+                                            : (TR::kShare ? MTB_MIN_BLOCKS_FAST_SHARE : MTB_MIN_BLOCKS_FAST);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -324,7 +324,7 @@ struct mtb_handle
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int sm_count = 0;
-  int bps[3][2] = {{1, 1}, {1, 1}, {1, 1}}; // resident CTAs per SM: [variant][share]
+  int bps[VARIANT_COUNT][2] = {}; // resident CTAs per SM: [variant][share]
   Variant variant = VARIANT_GENERIC, variant_custom = VARIANT_GENERIC; // pick_variant(P, false / true)
 
   HostConfig host; // host copies of the configuration
@@ -460,13 +460,15 @@ build_tables(mtb_handle * h)
   MTB_SETUP_KERNEL(TraitsFastShare, VARIANT_FAST, 1)
   MTB_SETUP_KERNEL(TraitsClusters, VARIANT_CLUSTERS, 0)
   MTB_SETUP_KERNEL(TraitsClustersShare, VARIANT_CLUSTERS, 1)
+  MTB_SETUP_KERNEL(TraitsLayers, VARIANT_LAYERS, 0)
+  MTB_SETUP_KERNEL(TraitsLayersShare, VARIANT_LAYERS, 1)
   MTB_SETUP_KERNEL(TraitsGeneric, VARIANT_GENERIC, 0)
   MTB_SETUP_KERNEL(TraitsGenericShare, VARIANT_GENERIC, 1)
 #undef MTB_SETUP_KERNEL
   MTB_CUDA(cudaFuncSetAttribute(trim_one_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   MTB_CUDA(cudaFuncSetAttribute(stopping_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   if (const char * cap = std::getenv("MYTRIM_B200_BLOCKS_PER_SM")) // tuning knob: resident CTAs per SM
-    for (int v = 0; v < 3; ++v)
+    for (int v = 0; v < VARIANT_COUNT; ++v)
       h->bps[v][0] = std::max(1, std::min(h->bps[v][0], std::atoi(cap)));
   h->dirty = false;
   return MTB_OK;
@@ -499,6 +501,12 @@ launch_kernel(mtb_handle * h, const LaunchParams & P, unsigned blocks, Variant v
         transport_kernel<TraitsClustersShare><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
       else
         transport_kernel<TraitsClusters><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+      break;
+    case VARIANT_LAYERS:
+      if (share)
+        transport_kernel<TraitsLayersShare><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+      else
+        transport_kernel<TraitsLayers><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
       break;
     default:
       if (share)
@@ -553,7 +561,8 @@ launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, cons
   P.stacks = h->d_stacks.p;
   MTB_CUDA(h->d_custom_rows.ensure((size_t)blocks * kBlock * (size_t)(2 + P.n_materials + P.n_tclass)));
   P.custom_rows = h->d_custom_rows.p;
-  const bool defers = v == VARIANT_FAST && primaries_dev != nullptr; // class-less primaries go to a second launch
+  // variants without F_CUSTOM hand class-less primaries to a second launch
+  const bool defers = !(variant_features(v) & F_CUSTOM) && primaries_dev != nullptr;
   P.index_list = nullptr;
   P.deferred = nullptr;
   if (defers)

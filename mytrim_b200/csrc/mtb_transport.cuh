@@ -77,6 +77,8 @@ block_add(unsigned long long * acc, uint32_t v)
 //             tallies, solid/layered sample, no CUT boundaries, projectile classes only
 //   CLUSTERS  the tests/uo2 shape: sampleClusters geometry, per-primary species (fission fragments),
 //             ion log / energy partition, otherwise the north-star options
+//   LAYERS    solid/layered sample with any follow policy, vacancy model and tally (vacenergycount, range,
+//             TrimPrimaries/Recoils, PhononOut, VacMap): the other runmytrim / mytrim_layers shapes
 //   GENERIC   every option at run time
 enum Feature : uint32_t
 {
@@ -105,6 +107,7 @@ constexpr uint32_t kFeatFast = 0;
 constexpr uint32_t kTallyFast = MTB_TALLY_VAC_DEPTH;
 constexpr uint32_t kFeatClusters = F_CUSTOM | F_CLUSTERS | F_TALLY_RT;
 constexpr uint32_t kTallyClusters = MTB_TALLY_IONLOG | MTB_TALLY_PHONON;
+constexpr uint32_t kFeatLayers = F_FOLLOW | F_VACMODEL | F_TALLY_RT;
 constexpr uint32_t kFeatGeneric =
     F_CUSTOM | F_CLUSTERS | F_GEOM_ANY | F_CUT | F_POTENTIAL | F_FOLLOW | F_VACMODEL | F_TALLY_RT | F_DIAG;
 constexpr uint32_t kTallyAll = 0xffffffffu;
@@ -113,6 +116,8 @@ typedef TraitsT<kFeatFast, kTallyFast> TraitsFast;
 typedef TraitsT<kFeatFast | F_SHARE, kTallyFast> TraitsFastShare;
 typedef TraitsT<kFeatClusters, kTallyClusters> TraitsClusters;
 typedef TraitsT<kFeatClusters | F_SHARE, kTallyClusters> TraitsClustersShare;
+typedef TraitsT<kFeatLayers, kTallyAll> TraitsLayers;
+typedef TraitsT<kFeatLayers | F_SHARE, kTallyAll> TraitsLayersShare;
 typedef TraitsT<kFeatGeneric, kTallyAll> TraitsGeneric;
 typedef TraitsT<kFeatGeneric | F_SHARE, kTallyAll> TraitsGenericShare;
 typedef TraitsT<kFeatGeneric | F_EVENTS, kTallyAll> TraitsEvents;
@@ -128,8 +133,16 @@ enum Variant
 {
   VARIANT_FAST = 0,
   VARIANT_CLUSTERS,
-  VARIANT_GENERIC
+  VARIANT_LAYERS,
+  VARIANT_GENERIC,
+  VARIANT_COUNT
 };
+
+inline uint32_t
+variant_features(Variant v)
+{
+  return v == VARIANT_FAST ? kFeatFast : v == VARIANT_CLUSTERS ? kFeatClusters : v == VARIANT_LAYERS ? kFeatLayers : kFeatGeneric;
+}
 
 // Features a configuration needs (F_CUSTOM is decided per primary: variants without it hand
 // class-less primaries to a second launch of a variant that has it).
@@ -171,6 +184,8 @@ pick_variant(const LaunchParams & P, bool custom)
     return VARIANT_FAST;
   if (variant_covers(kFeatClusters, kTallyClusters, P))
     return VARIANT_CLUSTERS;
+  if (!custom && variant_covers(kFeatLayers, kTallyAll, P))
+    return VARIANT_LAYERS;
   return VARIANT_GENERIC;
 }
 

@@ -196,10 +196,12 @@ hs_run(hs_engine * e, uint64_t n, const mtb_ion * primaries, uint64_t seed, uint
       lane_loop<TraitsFast>(P, S, 0);
     else if (which == VARIANT_CLUSTERS)
       lane_loop<TraitsClusters>(P, S, 0);
+    else if (which == VARIANT_LAYERS)
+      lane_loop<TraitsLayers>(P, S, 0);
     else
       lane_loop<TraitsGeneric>(P, S, 0);
   };
-  if (v == VARIANT_FAST)
+  if (!(variant_features(v) & F_CUSTOM))
   {
     std::vector<uint32_t> deferred(n ? n : 1);
     P.deferred = deferred.data();

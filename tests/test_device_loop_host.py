@@ -216,6 +216,37 @@ def test_clusters_variant_equals_generic():
             assert np.array_equal(np.sort(la[f], axis=0), np.sort(lb[f], axis=0)), f
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(follow=capi.FOLLOW_NONE, vacancy_model=capi.VAC_NRT, tally_mask=capi.TALLY_RANGE | capi.TALLY_RECORDS),
+    dict(follow=capi.FOLLOW_GEN_LT, follow_max_gen=2, vacancy_model=capi.VAC_KP, tally_mask=capi.TALLY_RECORDS),
+    dict(tally_mask=capi.TALLY_VAC_ENERGY | capi.TALLY_VAC_DEPTH | capi.TALLY_VACMAP | capi.TALLY_RECORDS),
+])
+def test_layers_variant_equals_generic(cfg):
+    """The layered-sample variant (run-time follow policy, vacancy model and tallies; no clusters, wires,
+    CUT boundaries, other potentials or per-primary species compiled in) against the all-options loop."""
+    with util.HostSimEngine(**cfg) as a, util.HostSimEngine(**cfg) as b:
+        for e in (a, b):
+            c = util.setup_engine(e, "xe_on_zro2_500keV")
+        b._lib.hs_force_generic(b._h, 1)
+        ions = util.primaries_for(c, 4)
+        ions["E"] = 6.0e4
+        ra = a.run(ions, seed=12, records=True)
+        rb = b.run(ions, seed=12, records=True)
+        for f in ra.dtype.names:
+            assert np.array_equal(ra[f], rb[f]), f
+        ca, cb = a.counters(), b.counters()
+        for k in ca:
+            if k != "stack_max":
+                assert abs(ca[k] - cb[k]) <= 1e-12 * abs(cb[k]), k
+        if cfg["tally_mask"] & capi.TALLY_VAC_DEPTH:
+            assert np.array_equal(a.vac_depth()[0], b.vac_depth()[0])
+            assert np.array_equal(a.vac_energy(), b.vac_energy())
+        if cfg["tally_mask"] & capi.TALLY_RANGE:
+            xa, za = a.range_list()
+            xb, zb = b.range_list()
+            assert np.array_equal(np.sort(xa), np.sort(xb)) and len(xa) > 0
+
+
 def test_fast_kernel_defers_unknown_species():
     """Layered sample + TrimVacCount tallies selects the compile-time fast loop; primaries whose
     species has no class are handed to the generic loop and the union equals a generic-only run."""
