@@ -452,6 +452,9 @@ build_tables(mtb_handle * h)
   h->fast = fast_path_ok(P);
   h->variant = pick_variant(P, false);
   h->variant_custom = pick_variant(P, true);
+  if (const char * env = std::getenv("MYTRIM_B200_VARIANT")) // test knob: "generic" forces the all-options kernels
+    if (!std::strcmp(env, "generic"))
+      h->variant = h->variant_custom = VARIANT_GENERIC;
 #define MTB_SETUP_KERNEL(TRAITS, V, SH)                                                                                     \
   MTB_CUDA(cudaFuncSetAttribute(transport_kernel<TRAITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)); \
   MTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->bps[V][SH], transport_kernel<TRAITS>, kBlock, h->smem_bytes));  \

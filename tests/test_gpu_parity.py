@@ -308,6 +308,57 @@ def test_fast_kernel_defers_unknown_species():
         assert abs(ca["steps"] - cb["steps"]) <= 1e-3 * cb["steps"] and ca["primaries"] == cb["primaries"] == len(ions)
 
 
+@pytest.mark.parametrize("which", ["fast", "clusters", "layers"])
+def test_lean_variants_agree_with_generic_kernel(which):
+    """Every lean kernel variant (mtb_transport.cuh: FAST / CLUSTERS / LAYERS) against the all-options kernel
+    on the same primaries and seeds.  Different instantiations contract FMAs differently, so agreement is to
+    the trajectory tolerance; the integer tallies agree for all cascades without a branch flip."""
+    if which == "fast":
+        cfg = dict(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS)
+        def setup(e):
+            c = util.setup_engine(e, "cu_on_cu_10keV")
+            return util.primaries_for(c, 4000)
+    elif which == "layers":
+        cfg = dict(tally_mask=capi.TALLY_VAC_ENERGY | capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS, follow=capi.FOLLOW_GEN_LT,
+                   follow_max_gen=2, vacancy_model=capi.VAC_KP)
+        def setup(e):
+            c = util.setup_engine(e, "xe_on_zro2_500keV")
+            return util.primaries_for(c, 600)
+    else:
+        cfg = dict(tally_mask=capi.TALLY_PHONON | capi.TALLY_RECORDS | capi.TALLY_IONLOG, ionlog_z=54)
+        cl = np.loadtxt(os.path.join(util.GOLDEN, "uo2_out.clcoor"))[:, :4]
+        def setup(e):
+            from tests.test_device_loop_host import _fission_like_primaries
+            e.set_materials([util.UO2, util.XE_GAS])
+            e.set_geometry(capi.GEOM_CLUSTERS, (400.0, 400.0, 400.0), kn=(39, 39, 39), clusters=cl)
+            ions = _fission_like_primaries(400)
+            ions["pos"][:40] = cl[np.arange(40) % len(cl), :3] + 2.0
+            return ions
+    with capi.Engine(**cfg) as a:
+        ions = setup(a)
+        ra = a.run(ions, seed=31, records=True)
+        ca = a.counters()
+        la = len(a.ion_log()) if which == "clusters" else 0
+    os.environ["MYTRIM_B200_VARIANT"] = "generic"
+    try:
+        with capi.Engine(**cfg) as b:
+            setup(b)
+            rb = b.run(ions, seed=31, records=True)
+            cb = b.counters()
+            lb = len(b.ion_log()) if which == "clusters" else 0
+    finally:
+        os.environ.pop("MYTRIM_B200_VARIANT")
+    same = (ra["steps"] == rb["steps"]) & (ra["vacancies"] == rb["vacancies"]) & (ra["ions"] == rb["ions"])
+    assert same.mean() > (0.97 if which == "fast" else 0.85), same.mean()
+    sel = ra["primary_steps"] == rb["primary_steps"]
+    assert sel.mean() > 0.97
+    d = np.linalg.norm(ra["pos"] - rb["pos"], axis=1) / np.maximum(np.linalg.norm(ra["pos"] - ions["pos"], axis=1), 1.0)
+    assert (d[sel] >= TOL).sum() <= 0.005 * len(ions) + 2
+    assert abs(ca["steps"] - cb["steps"]) <= 2e-3 * cb["steps"] and ca["primaries"] == cb["primaries"] == len(ions)
+    assert abs(ca["vacancies_created"] - cb["vacancies_created"]) <= 2e-3 * cb["vacancies_created"]
+    assert abs(la - lb) <= 0.02 * lb + 4
+
+
 def test_work_sharing_pool_is_result_neutral():
     """Few large cascades: idle lanes adopt suspended ions from the shared pool.  Per-ion Philox streams
     make the result independent of which lane follows which ion: integer tallies and per-primary

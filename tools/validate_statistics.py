@@ -36,7 +36,7 @@ ref, summary, _ = util.run_reference_cascades(c["ion"], c["materials"], c["thick
 t_ref = time.time() - t0
 
 runs = {}
-for label, mask in (("generic kernel (PHONON|RECORDS)", capi.TALLY_PHONON | capi.TALLY_RECORDS),
+for label, mask in (("lean variant with energy partition (PHONON|RECORDS)", capi.TALLY_PHONON | capi.TALLY_RECORDS),
                     ("fast kernel (VAC_DEPTH|RECORDS)", capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS)):
     with capi.Engine(tally_mask=mask) as eng:
         util.setup_engine(eng, c)
