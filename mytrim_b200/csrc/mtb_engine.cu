@@ -58,13 +58,13 @@ constexpr int kBlock = MTB_BLOCK;
 #define MTB_MIN_BLOCKS_GENERIC 6
 #endif
 #ifndef MTB_MIN_BLOCKS_FAST_SHARE
-#define MTB_MIN_BLOCKS_FAST_SHARE 5
+#define MTB_MIN_BLOCKS_FAST_SHARE 6
 #endif
 #ifndef MTB_MIN_BLOCKS_CLUSTERS_SHARE
-#define MTB_MIN_BLOCKS_CLUSTERS_SHARE 5
+#define MTB_MIN_BLOCKS_CLUSTERS_SHARE 6
 #endif
 #ifndef MTB_MIN_BLOCKS_GENERIC_SHARE
-#define MTB_MIN_BLOCKS_GENERIC_SHARE 5
+#define MTB_MIN_BLOCKS_GENERIC_SHARE 6
 #endif
 template <class TR>
 constexpr int

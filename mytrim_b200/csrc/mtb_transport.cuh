@@ -765,6 +765,11 @@ close_subtree(const LaunchParams & P, const BlockCtx & S, Lane & L, uint32_t n_p
 // 50x slower.  Shared memory has no such problem.)
 // ---------------------------------------------------------------------------------------------
 #if MTB_DEVICE_CODE
+#ifdef MTB_POOL_NOINLINE
+#define MTB_POOL_FN __device__ __noinline__
+#else
+#define MTB_POOL_FN __device__ __forceinline__
+#endif
 MTB_D unsigned long long
 vload(const unsigned long long * p)
 {
@@ -786,63 +791,63 @@ store_release(unsigned long long * p, unsigned long long v)
   asm volatile("st.release.cta.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-MTB_D bool
-pool_try_push(const BlockCtx & S, const Lane & ion, uint64_t prim)
+// Claim a ring slot for writing (which = POOL_ENQ) or reading (which = POOL_DEQ): the ticket dance of the
+// bounded MPMC queue.  A real call with scalar arguments only: inlined into the suspend / refill paths
+// it cost the sharing kernels 19 registers, i.e. two resident CTAs per SM.
+MTB_POOL_FN PoolSlot *
+pool_claim(PoolSlot * pool, unsigned long long * ctl, int which, unsigned long long * ticket)
 {
   const unsigned long long mask = MTB_POOL_SLOTS - 1;
-  unsigned long long pos = vload(&S.pool_ctl[POOL_ENQ]);
+  const unsigned long long want = which == POOL_ENQ ? 0ull : 1ull; // slot sequence relative to the ticket
+  unsigned long long pos = vload(&ctl[which]);
   for (int tries = 0; tries < 4; ++tries)
   {
-    PoolSlot * slot = S.pool + (pos & mask);
-    const long long dif = (long long)(load_acquire(&slot->seq) - pos);
+    PoolSlot * slot = pool + (pos & mask);
+    const long long dif = (long long)(load_acquire(&slot->seq) - (pos + want));
     if (dif == 0)
     {
-      const unsigned long long seen = atomicCAS(&S.pool_ctl[POOL_ENQ], pos, pos + 1);
+      const unsigned long long seen = atomicCAS(&ctl[which], pos, pos + 1);
       if (seen == pos)
       {
-        atomicAdd(&S.pool_ctl[POOL_WORKING], 1ull); // the entry counts as outstanding work from now on
-        slot->prim = prim;
-        stack_store(&slot->e, ion);
-        store_release(&slot->seq, pos + 1); // publishes the payload
-        return true;
+        if (which == POOL_ENQ)
+          atomicAdd(&ctl[POOL_WORKING], 1ull); // the entry counts as outstanding work from now on
+        *ticket = pos;
+        return slot;
       }
       pos = seen;
     }
     else if (dif < 0)
-      return false; // full
+      return nullptr; // full (push) / empty (pop)
     else
-      pos = vload(&S.pool_ctl[POOL_ENQ]);
+      pos = vload(&ctl[which]);
   }
-  return false;
+  return nullptr;
+}
+
+MTB_D bool
+pool_try_push(const BlockCtx & S, const Lane & ion, uint64_t prim)
+{
+  unsigned long long pos;
+  PoolSlot * slot = pool_claim(S.pool, S.pool_ctl, POOL_ENQ, &pos);
+  if (!slot)
+    return false;
+  slot->prim = prim;
+  stack_store(&slot->e, ion);
+  store_release(&slot->seq, pos + 1); // publishes the payload
+  return true;
 }
 
 MTB_D bool
 pool_try_pop(const BlockCtx & S, Lane & ion, uint64_t * prim)
 {
-  const unsigned long long mask = MTB_POOL_SLOTS - 1;
-  unsigned long long pos = vload(&S.pool_ctl[POOL_DEQ]);
-  for (int tries = 0; tries < 4; ++tries)
-  {
-    PoolSlot * slot = S.pool + (pos & mask);
-    const long long dif = (long long)(load_acquire(&slot->seq) - (pos + 1));
-    if (dif == 0)
-    {
-      const unsigned long long seen = atomicCAS(&S.pool_ctl[POOL_DEQ], pos, pos + 1);
-      if (seen == pos)
-      {
-        *prim = slot->prim;
-        stack_load(&slot->e, ion);
-        store_release(&slot->seq, pos + mask + 1); // hands the slot back to the producers
-        return true;
-      }
-      pos = seen;
-    }
-    else if (dif < 0)
-      return false; // empty
-    else
-      pos = vload(&S.pool_ctl[POOL_DEQ]);
-  }
-  return false;
+  unsigned long long pos;
+  PoolSlot * slot = pool_claim(S.pool, S.pool_ctl, POOL_DEQ, &pos);
+  if (!slot)
+    return false;
+  *prim = slot->prim;
+  stack_load(&slot->e, ion);
+  store_release(&slot->seq, pos + MTB_POOL_SLOTS); // hands the slot back to the producers
+  return true;
 }
 #endif
 

@@ -13,7 +13,7 @@ echo "pytest exit $?" >> $OUT/${TAG}_pytest_gpu.log
 timeout 600 python bench.py --steps 5 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $OUT/${TAG}_launches.csv \
-    python tools/profile_run.py --primaries 1048576 --launches 3 > $OUT/${TAG}_launches.log 2>&1
+    python tools/profile_run.py --primaries 2097152 --launches 3 > $OUT/${TAG}_launches.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:transport_kernel -s 1 -c 1 \
-    -o $OUT/${TAG}_prof -f python tools/profile_run.py --primaries 1048576 --launches 2 > $OUT/${TAG}_prof.log 2>&1
+    -o $OUT/${TAG}_prof -f python tools/profile_run.py --primaries 2097152 --launches 2 > $OUT/${TAG}_prof.log 2>&1
 tail -3 $OUT/${TAG}_smoke.log; tail -5 $OUT/${TAG}_pytest_gpu.log; cat $OUT/${TAG}_bench.json; tail -2 $OUT/${TAG}_bench.err; cat $OUT/${TAG}_bench_ref.json

@@ -8,8 +8,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = sys.argv[1]
-kernel = sys.argv[2] if len(sys.argv) > 2 else "TraitsFastT<(bool)0>"
-sass = sys.argv[3] if len(sys.argv) > 3 else "TraitsFastTILb0E"
+kernel = sys.argv[2] if len(sys.argv) > 2 else "TraitsT<(unsigned int)0, (unsigned int)1>"  # north-star variant
+sass = sys.argv[3] if len(sys.argv) > 3 else "TraitsTILj0ELj1E"
 out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_hotspots.py"), rep, "--kernel", kernel, "--sass-kernel", sass,
                       "--top", "5000"],
                      capture_output=True, text=True).stdout.split("\n")
@@ -27,7 +27,10 @@ def find(lines, s):
 tmarks = [("lookup", "lookup_cluster(const LaunchParams"), ("lane/class helpers", "struct Lane"), ("stack_store", "stack_store(StackEntry"),
           ("stack_load", "stack_load(const StackEntry"), ("log_birth", "log_birth(const LaunchParams"),
           ("finish_ion", "finish_ion(const LaunchParams"), ("depth_tally", "depth_tally(const"),
-          ("vacancy_creation", "vacancy_creation(const"), ("close_cascade", "close_cascade(const"),
+          ("vacancy_creation", "vacancy_creation(const"), ("close_subtree", "close_subtree(const"),
+          ("work-sharing pool", "vload(const unsigned long long"), ("stack cursor / suspend_ion", "stack_entry(const LaunchParams"),
+          ("block_add", "block_add(unsigned long long"), ("variant selection", "needed_features(const"), ("ionlog", "ionlog_append(const"),
+          ("wrap_cell", "wrap_cell(int j"),
           ("loop: setup", "lane_loop(const LaunchParams"), ("loop: refill", "refill: next suspended"),
           ("loop: geometry+norm", "one collision: trim.C:74-424"), ("loop: philox+uniforms", "the four uniforms of this step"),
           ("loop: class/flight", "const float E0 = L.Ecur"), ("loop: element pick+pair", "target element — trim.C:147-156"),
