@@ -109,7 +109,7 @@ def run_reference_arm(args):
     from tests import util
     cores = os.cpu_count() or 1
     if not util.have_reference():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (reference tree absent)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref was not built (reference tree absent)"})
         return 0
     per_step = args.ref_cascades if args.ref_cascades else 400 * cores
     for _ in range(args.warmup):
@@ -134,11 +134,31 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "cascades/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version on
+    communicator creation), so file descriptor 1 is pointed at stderr for the whole run and the result
+    line goes to a private duplicate of the original stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -351,7 +371,7 @@ def main():
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": n_ref / dt, "unit": "cascades/s", "cores": 1, "kind": "port",
                                     "sample": "%d cascades, oracle C restatement, 1 thread" % n_ref}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
