@@ -624,17 +624,18 @@ log_birth(const LaunchParams & P, const Lane & L, int Z)
   ionlog_append(P, L.px, L.py, L.pz, L.E, L.uid, L.prim, Z, L.packed, L.tag, -1);
 }
 
-// an ion has stopped (or left the sample): primary record + death half of the ion log
+// an ion has stopped (or left the sample) at (x, y, z): primary record + death half of the ion log
 template <class TR>
 MTB_HD void
-finish_ion(const LaunchParams & P, const BlockCtx & S, const Lane & L, const float4_t * rows, int state)
+finish_ion(const LaunchParams & P, const BlockCtx & S, const Lane & L, const float4_t * rows, int state, double x, double y,
+           double z)
 {
   if ((L.packed & FLAG_PRIMARY) && P.records)
   {
     mtb_record & r = P.records[L.prim];
-    r.pos[0] = L.px;
-    r.pos[1] = L.py;
-    r.pos[2] = L.pz;
+    r.pos[0] = x;
+    r.pos[1] = y;
+    r.pos[2] = z;
     r.E = L.E;
     r.state = state;
     r.primary_steps = L.ic;
@@ -644,7 +645,7 @@ finish_ion(const LaunchParams & P, const BlockCtx & S, const Lane & L, const flo
     const int Z = current_Z(L, S, rows);
     if (P.ionlog_z && Z != P.ionlog_z)
       return;
-    ionlog_append(P, L.px, L.py, L.pz, L.E, L.uid, L.prim, Z, L.packed, L.tag, state);
+    ionlog_append(P, x, y, z, L.E, L.uid, L.prim, Z, L.packed, L.tag, state);
   }
 }
 
@@ -1091,7 +1092,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     if (!(L.Ecur > 0.0f))
     {
       // the reference would produce NaNs for a projectile without energy; park it instead
-      finish_ion<TR>(P, S, L, rows, MTB_INTERSTITIAL);
+      finish_ion<TR>(P, S, L, rows, MTB_INTERSTITIAL, L.px, L.py, L.pz);
       active = false;
       break;
     }
@@ -1109,7 +1110,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       // vacuum: the reference breaks out with the state still MOVING (trim.C:80-82)
       block_add(&S.blk_u64[CNT_LEFT], 1u);
       --L.ic;
-      finish_ion<TR>(P, S, L, rows, MTB_MOVING);
+      finish_ion<TR>(P, S, L, rows, MTB_MOVING, L.px, L.py, L.pz);
       active = false;
       break;
     }
@@ -1220,14 +1221,17 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     const float p1 = EVENTS ? fsqrt(pc.m2 * E1p) : E1p;
     const float p2 = EVENTS ? fsqrt(pc.m2 * E2) : fsqrt(E1p * E2);
 
-    // recoil is born at the previous collision site — trim.C:306-310
-    const double rx = L.px, ry = L.py, rz = L.pz;
+    // The recoil is born at the previous collision site (trim.C:306-310), the projectile moves on by
+    // dir * (ls - tau).  L.p* stays the collision site until the end of the step and is advanced in place
+    // only on the paths where the projectile flies on: keeping both positions alive across the fate logic
+    // cost seven register moves on every exit of the step.
     const float flight = (ls - P.tau) * P.inv_scale;
+    const double mvx = (double)(L.dx * flight), mvy = (double)(L.dy * flight), mvz = (double)(L.dz * flight);
     const float dsafe_here = L.dsafe; // of the collision site: a recoil starts there
     L.dsafe -= fabsf(flight);
-    L.px += (double)(L.dx * flight);
-    L.py += (double)(L.dy * flight);
-    L.pz += (double)(L.dz * flight);
+#define MTB_AHEAD_X (L.px + mvx)
+#define MTB_AHEAD_Y (L.py + mvy)
+#define MTB_AHEAD_Z (L.pz + mvz)
 
     // unit vector perpendicular to dir with uniform azimuth (replaces trim.C:322-333)
     float qx, qy, qz;
@@ -1268,9 +1272,9 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     // CUT boundaries — trim.C:344-352
     int state = MTB_MOVING;
     if (TR::has(F_CUT) &&
-        ((P.bc[0] == MTB_BC_CUT && (L.px > P.w[0] || L.px < 0.0)) ||
-        (P.bc[1] == MTB_BC_CUT && (L.py > P.w[1] || L.py < 0.0)) ||
-        (P.bc[2] == MTB_BC_CUT && (L.pz > P.w[2] || L.pz < 0.0))))
+        ((P.bc[0] == MTB_BC_CUT && (MTB_AHEAD_X > P.w[0] || MTB_AHEAD_X < 0.0)) ||
+        (P.bc[1] == MTB_BC_CUT && (MTB_AHEAD_Y > P.w[1] || MTB_AHEAD_Y < 0.0)) ||
+        (P.bc[2] == MTB_BC_CUT && (MTB_AHEAD_Z > P.w[2] || MTB_AHEAD_Z < 0.0))))
     {
       state = MTB_LOST;
       block_add(&S.blk_u64[CNT_LOST], 1u);
@@ -1291,7 +1295,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
                              (P.follow == MTB_FOLLOW_GEN_LT && rec_gen < P.follow_max_gen));
         const bool vacancy = E2 > el.Edisp;
         if (vacancy)
-          vacancy_creation<TR>(P, S, L, M, el, rx, ry, Erec, rec_gen);
+          vacancy_creation<TR>(P, S, L, M, el, L.px, L.py, Erec, rec_gen);
         else
         {
           L.casRepl++;
@@ -1299,7 +1303,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
         }
         // TrimVacCount::vacancyCreation / replacementCollision (TrimVacCount.C:31-53): one tally site
         if (tally_on<TR>(P, MTB_TALLY_VAC_DEPTH))
-          depth_tally(P, S, vacancy ? S.hist_vac : S.hist_repl, vacancy ? off_vac(P) : off_repl(P), (int)rx);
+          depth_tally(P, S, vacancy ? S.hist_vac : S.hist_repl, vacancy ? off_vac(P) : off_repl(P), (int)L.px);
       }
       else
       {
@@ -1308,7 +1312,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           const unsigned long long i = MTB_ATOMIC_ADD(&P.u64[CNT_RANGE_N], 1ull);
           if (i < P.range_cap)
           {
-            P.range[i].x = (float)rx;
+            P.range[i].x = (float)L.px;
             P.range[i].Z = el.Z;
           }
         }
@@ -1327,10 +1331,10 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       if (n_events < P.events_cap)
       {
         mtb_event & ev = P.events[n_events];
-        ev.pka_pos[0] = L.px; ev.pka_pos[1] = L.py; ev.pka_pos[2] = L.pz;
+        ev.pka_pos[0] = MTB_AHEAD_X; ev.pka_pos[1] = MTB_AHEAD_Y; ev.pka_pos[2] = MTB_AHEAD_Z;
         ev.pka_dir[0] = L.dx; ev.pka_dir[1] = L.dy; ev.pka_dir[2] = L.dz;
         ev.pka_E = L.E;
-        ev.recoil_pos[0] = rx; ev.recoil_pos[1] = ry; ev.recoil_pos[2] = rz;
+        ev.recoil_pos[0] = L.px; ev.recoil_pos[1] = L.py; ev.recoil_pos[2] = L.pz;
         float qs = 1.0f;
         if (above)
           qs = frsqrt(qx * qx + qy * qy + qz * qz);
@@ -1349,9 +1353,12 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       ++n_events;
       if (state != MTB_MOVING)
       {
-        finish_ion<TR>(P, S, L, rows, state);
+        finish_ion<TR>(P, S, L, rows, state, MTB_AHEAD_X, MTB_AHEAD_Y, MTB_AHEAD_Z);
         active = false;
       }
+      L.px = MTB_AHEAD_X;
+      L.py = MTB_AHEAD_Y;
+      L.pz = MTB_AHEAD_Z;
       break;
     }
 
@@ -1365,16 +1372,21 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       const bool keep_projectile = (state == MTB_MOVING) && (E2 <= Erec);
       if (state == MTB_MOVING && !keep_projectile)
       {
-        // both move on and the recoil has less energy: suspend the projectile, fly the recoil
-        suspend_ion<TR>(P, S, sp, L, L.prim, Erec);
+        // both move on and the recoil has less energy: suspend the projectile (at its new position), fly
+        // the recoil
+        Lane T = L;
+        T.px = MTB_AHEAD_X;
+        T.py = MTB_AHEAD_Y;
+        T.pz = MTB_AHEAD_Z;
+        suspend_ion<TR>(P, S, sp, T, L.prim, Erec);
       }
       if (state != MTB_MOVING)
-        finish_ion<TR>(P, S, L, rows, state);
+        finish_ion<TR>(P, S, L, rows, state, MTB_AHEAD_X, MTB_AHEAD_Y, MTB_AHEAD_Z);
       if (keep_projectile)
       {
         // suspend the recoil instead
         Lane R;
-        R.px = rx; R.py = ry; R.pz = rz;
+        R.px = L.px; R.py = L.py; R.pz = L.pz;
         R.E = (double)Erec;
         R.dx = qx * qs; R.dy = qy * qs; R.dz = qz * qs;
         R.ic = 0;
@@ -1387,10 +1399,13 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           log_birth<TR>(P, R, el.Z);
         }
         suspend_ion<TR>(P, S, sp, R, L.prim, E2);
+        L.px = MTB_AHEAD_X;
+        L.py = MTB_AHEAD_Y;
+        L.pz = MTB_AHEAD_Z;
       }
       else
       {
-        L.px = rx; L.py = ry; L.pz = rz;
+        // the recoil starts where L.p* still is
         L.E = (double)Erec;
         L.Ecur = Erec;
         L.dx = qx * qs; L.dy = qy * qs; L.dz = qz * qs;
@@ -1407,9 +1422,18 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     }
     else if (state != MTB_MOVING)
     {
-      finish_ion<TR>(P, S, L, rows, state);
+      finish_ion<TR>(P, S, L, rows, state, MTB_AHEAD_X, MTB_AHEAD_Y, MTB_AHEAD_Z);
       active = false;
     }
+    else
+    {
+      L.px = MTB_AHEAD_X;
+      L.py = MTB_AHEAD_Y;
+      L.pz = MTB_AHEAD_Z;
+    }
+#undef MTB_AHEAD_X
+#undef MTB_AHEAD_Y
+#undef MTB_AHEAD_Z
       } while (0);
 
     if (EVENTS && !active)
