@@ -46,6 +46,33 @@ def test_trajectories_match_oracle(name, n):
     assert ch["stack_max"] <= 32
 
 
+def test_edge_cases_empty_single_and_degenerate_primaries():
+    """The device loop on an empty batch, one primary, a primary without energy (parked as an interstitial
+    without a collision), starts in front of / behind the layer stack, a sub-threshold primary and a
+    direction that is not normalised."""
+    cfg = dict(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS)
+    orc, hs, c = _pair(cfg, "cu_on_cu_10keV")
+    rec = hs.run(util.primaries_for(c, 0), seed=3, records=True)
+    assert len(rec) == 0 and hs.counters()["steps"] == 0
+    one = util.primaries_for(c, 1)
+    r1, o1 = hs.run(one, seed=3, records=True), orc.run(one, seed=3, records=True)
+    assert r1["steps"][0] == o1["steps"][0] and r1["vacancies"][0] == o1["vacancies"][0]
+    ions = util.primaries_for(c, 5)
+    ions["E"][0] = 0.0
+    ions["pos"][1] = (-40.0, 50.0, 50.0)
+    ions["pos"][2] = (5000.0, 50.0, 50.0)
+    ions["E"][3] = 10.0
+    ions["dir"][4] = (0.0, 0.0, 2.0)
+    r = hs.run(ions, seed=5, records=True)
+    o = orc.run(ions[1:], seed=5, first_index=1, records=True)
+    assert r["steps"][0] == 0 and r["state"][0] == capi.INTERSTITIAL and r["E"][0] == 0.0
+    assert np.array_equal(r["steps"][1:], o["steps"]) and np.array_equal(r["vacancies"][1:], o["vacancies"])
+    assert np.array_equal(r["state"][1:], o["state"])
+    d = np.abs(r["pos"][1:] - o["pos"]).max(axis=1)
+    assert (d < 1e-5 * np.maximum(np.abs(o["pos"]).max(axis=1), 1.0)).all()
+    assert r["vacancies"][3] == 0 and r["ions"][3] == 1
+
+
 def test_stopping_matches_oracle():
     import json, os
     data = json.load(open(os.path.join(util.GOLDEN, "stopping.json")))

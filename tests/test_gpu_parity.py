@@ -438,6 +438,40 @@ def test_published_vacancies_per_ion():
                 assert abs(vpi - want) < 0.04 * want, (key, mode, E, vpi, want)
 
 
+def test_edge_cases_empty_single_and_degenerate_primaries():
+    """Empty batch, one primary, and primaries the reference treats specially: zero energy (the reference
+    would divide by zero; the engine parks the ion as an interstitial without a collision), a start in
+    front of the first layer and beyond the last one (sample_layers.C:26-49: first / last layer), an
+    energy below the displacement threshold."""
+    cfg = dict(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS)
+    with capi.Engine(**cfg) as eng, util.OracleEngine(util.ORC_RNG_PHILOX, **cfg) as orc:
+        c = util.setup_engine(eng, "cu_on_cu_10keV")
+        util.setup_engine(orc, "cu_on_cu_10keV")
+        rec = eng.run(util.primaries_for(c, 0), seed=3, records=True)
+        assert len(rec) == 0
+        cnt = eng.counters()
+        assert cnt["primaries"] == 0 and cnt["steps"] == 0 and cnt["vacancies_created"] == 0
+        assert eng.vac_depth()[0].sum() == 0
+        one = util.primaries_for(c, 1)
+        r1, o1 = eng.run(one, seed=3, records=True), orc.run(one, seed=3, records=True)
+        assert r1["steps"][0] == o1["steps"][0] and r1["vacancies"][0] == o1["vacancies"][0]
+        eng.reset_tallies()
+        ions = util.primaries_for(c, 5)
+        ions["E"][0] = 0.0
+        ions["pos"][1] = (-40.0, 50.0, 50.0)
+        ions["pos"][2] = (5000.0, 50.0, 50.0)
+        ions["E"][3] = 10.0
+        ions["dir"][4] = (0.0, 0.0, 2.0)     # not normalised, along z
+        r = eng.run(ions, seed=5, records=True)
+        o = orc.run(ions[1:], seed=5, first_index=1, records=True)
+        assert r["steps"][0] == 0 and r["state"][0] == capi.INTERSTITIAL and r["E"][0] == 0.0
+        assert np.array_equal(r["steps"][1:], o["steps"]) and np.array_equal(r["vacancies"][1:], o["vacancies"])
+        assert np.array_equal(r["state"][1:], o["state"])
+        d = np.abs(r["pos"][1:] - o["pos"]).max(axis=1)
+        assert (d < 1e-5 * np.maximum(np.abs(o["pos"]).max(axis=1), 1.0)).all()
+        assert r["vacancies"][3] == 0 and r["ions"][3] == 1
+
+
 def test_error_paths_return_status_codes():
     """Nothing exits or throws across the C ABI: bad input comes back as a status + message."""
     import ctypes as C

@@ -18,6 +18,7 @@ ap.add_argument("--primaries", type=int, default=1 << 18)
 ap.add_argument("--launches", type=int, default=2)
 ap.add_argument("--workload", default="cu_on_cu_10keV")
 ap.add_argument("--tally", type=int, default=capi.TALLY_VAC_DEPTH)
+ap.add_argument("--escale", type=float, default=1.0, help="scale the primary energies (short kernels for ncu)")
 args = ap.parse_args()
 
 
@@ -50,11 +51,15 @@ with capi.Engine(tally_mask=args.tally) as eng:
         cl = np.loadtxt(os.path.join(util.GOLDEN, "uo2_out.clcoor"))[:, :4]
         eng.set_materials([util.UO2, util.XE_GAS])
         eng.set_geometry(capi.GEOM_CLUSTERS, (400.0, 400.0, 400.0), kn=(39, 39, 39), clusters=cl)
-        eng.upload_primaries(uo2_fission_primaries(args.primaries))
+        ions = uo2_fission_primaries(args.primaries)
+        ions["E"] *= args.escale
+        eng.upload_primaries(ions)
     else:
         c = util.CONFIGS[args.workload]
         util.setup_engine(eng, c)
-        eng.upload_primaries(util.primaries_for(c, args.primaries))
+        ions = util.primaries_for(c, args.primaries)
+        ions["E"] *= args.escale
+        eng.upload_primaries(ions)
     for i in range(args.launches):
         eng.launch_resident(2344, i * args.primaries)
         eng.synchronize()
