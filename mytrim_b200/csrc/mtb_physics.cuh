@@ -139,7 +139,11 @@ element_stopping(const ProjClass & ion, const LowStop * lowrow, const DevElement
     // (Z1, Z2)-only part tabulated in double on the host (mtb_tables.h)
     const LowStop ls = lowrow[el.zslot];
     if (e <= ls.e_max)
+    {
+      // (a select on purpose: a real branch around the fpow() measured 0.6 % slower than the LG2 the
+      // compiler speculates for it)
       return ls.coef * (ls.power == 0.5f ? sqrt_e : fpow(e, ls.power));
+    }
   }
   return element_stopping_general(ion, el, e);
 }
@@ -165,11 +169,60 @@ struct Scatter
   float c2; // cos^2(theta/2)
 };
 
+// Screened potential at reduced distance r: *sum = V(r) r, *dsum = -(V + V' r) r  (trim.C:196-222)
+MTB_HD void
+screening_sums(int potential, float r, float * sum, float * dsum)
+{
+  if (potential == MTB_POT_UNIVERSAL)
+  {
+    // sum c_i exp(-d_i r) and sum c_i d_i exp(-d_i r): the prefactors ride on the FMAs of the sums
+    const float ex1 = fexp2(-4.6163355918f * r);
+    const float ex2 = fexp2(-1.3594371101f * r);
+    const float ex3 = fexp2(-0.58126183197f * r);
+    const float ex4 = fexp2(-0.29087617414f * r);
+    *sum = fmaf(0.18175f, ex1, fmaf(0.50986f, ex2, fmaf(0.28022f, ex3, 0.028171f * ex4)));
+    *dsum = fmaf(0.58156365f, ex1, fmaf(0.4804359794f, ex2, fmaf(0.112900638f, ex3, 0.00567983702f * ex4)));
+  }
+  else if (potential == MTB_POT_MOLIERE)
+  {
+    const float ex1 = fexp(-0.3f * r);
+    const float ex2 = (ex1 * ex1) * (ex1 * ex1);
+    const float e22 = ex2 * ex2;
+    const float ex3 = ex2 * (e22 * e22);
+    *sum = 0.35f * ex1 + 0.55f * ex2 + 0.1f * ex3;
+    *dsum = 0.105f * ex1 + 0.66f * ex2 + 0.6f * ex3;
+  }
+  else
+  {
+    const float ex1 = fexp(-0.279f * r);
+    const float ex2 = fexp(-0.637f * r);
+    const float ex3 = fexp(-1.1919f * r);
+    *sum = 0.191f * ex1 + 0.474f * ex2 + 0.335f * ex3;
+    *dsum = 0.531865f * ex1 + 0.30181f * ex2 + 0.6437f * ex3;
+  }
+}
+
+// One Newton step of the closest-approach equation (trim.C:192-233) in x = r - b; returns q = fr/fr1.
+//   fr  = b^2/r + v r/eps - r            = sum/eps - x (2b + x)/r
+//   fr1 = -b^2/r^2 + (v + v1 r)/eps - 1  = -(b^2/r^2 + 1) - dsum/eps
+// Both times r^2: q = r (r sum/eps - x (2b + x)) / -(b^2 + r^2 (1 + dsum/eps)) costs ONE reciprocal; 1/r
+// (for v and v1) is formed once, after the iteration.  The SFU pipe bounds this loop: with 1/r inside it,
+// 6 of its 34 instructions were MUFU at 8 pipe cycles each (measured: -1 % kernel time without it).
+MTB_HD float
+newton_step(int potential, float b, float b2, float inv_eps, float x, float * r, float * sum, float * dsum)
+{
+  *r = b + x;
+  screening_sums(potential, *r, sum, dsum);
+  const float num = *r * fmaf(*sum * inv_eps, *r, -(x * fmaf(2.0f, b, x)));
+  const float den = fmaf(*r * *r, fmaf(*dsum, inv_eps, 1.0f), b2);
+  return -fdiv(num, den);
+}
+
 // Biersack-Haggmark MAGIC scattering (trim.C:172-272) for reduced energy eps = sqe^2 and reduced
 // impact parameter b.  The Newton iteration is the reference's (same start value, same map, same
 // stop test |q/r| <= 0.001) but carried in x = r - b so that distant collisions keep full relative
-// accuracy in single precision.  Written for the SFU budget of the kernel: per Newton iteration two
-// reciprocals and the exponentials of the potential; after it one reciprocal for cc, b^cc, one
+// accuracy in single precision.  Written for the SFU budget of the kernel: per Newton iteration one
+// reciprocal and the exponentials of the potential; after it 1/r, one reciprocal for cc, b^cc, one
 // square root and ONE reciprocal for everything else (roc, ff, delta and co share a denominator).
 MTB_HD Scatter
 magic_scatter(int potential, float sqe, float b)
@@ -200,50 +253,19 @@ magic_scatter(int potential, float sqe, float b)
 
   const float inv_eps = frcp(eps);
   const float b2 = b * b;
-  float r, v, v1, q;
-  int guard = 64;
+  float r, v, v1, q, sum, dsum; // sum = v*r, dsum = -(v + v1*r)
+  int guard = 64; // the reference iterates without a bound; a lane must never spin forever
   do
   {
-    r = b + x;
-    const float inv_r = frcp(r);
-    float sum, dsum; // sum = v*r, dsum = -(v + v1*r)
-    if (potential == MTB_POT_UNIVERSAL)
-    {
-      // sum c_i exp(-d_i r) and sum c_i d_i exp(-d_i r): the prefactors ride on the FMAs of the sums
-      const float ex1 = fexp2(-4.6163355918f * r);
-      const float ex2 = fexp2(-1.3594371101f * r);
-      const float ex3 = fexp2(-0.58126183197f * r);
-      const float ex4 = fexp2(-0.29087617414f * r);
-      sum = fmaf(0.18175f, ex1, fmaf(0.50986f, ex2, fmaf(0.28022f, ex3, 0.028171f * ex4)));
-      dsum = fmaf(0.58156365f, ex1, fmaf(0.4804359794f, ex2, fmaf(0.112900638f, ex3, 0.00567983702f * ex4)));
-    }
-    else if (potential == MTB_POT_MOLIERE)
-    {
-      const float ex1 = fexp(-0.3f * r);
-      const float ex2 = (ex1 * ex1) * (ex1 * ex1);
-      const float e22 = ex2 * ex2;
-      const float ex3 = ex2 * (e22 * e22);
-      sum = 0.35f * ex1 + 0.55f * ex2 + 0.1f * ex3;
-      dsum = 0.105f * ex1 + 0.66f * ex2 + 0.6f * ex3;
-    }
-    else
-    {
-      const float ex1 = fexp(-0.279f * r);
-      const float ex2 = fexp(-0.637f * r);
-      const float ex3 = fexp(-1.1919f * r);
-      sum = 0.191f * ex1 + 0.474f * ex2 + 0.335f * ex3;
-      dsum = 0.531865f * ex1 + 0.30181f * ex2 + 0.6437f * ex3;
-    }
+    q = newton_step(potential, b, b2, inv_eps, x, &r, &sum, &dsum);
+    x -= q;
+    --guard;
+  } while ((fabsf(q) > 0.001f * fabsf(b + x)) & (guard != 0));
+  {
+    const float inv_r = frcp(r); // r of the last evaluation, as in the reference
     v = sum * inv_r;
     v1 = -(v + dsum) * inv_r;
-    // fr  = b^2/r + v r/eps - r        = sum/eps - x (2b + x)/r
-    // fr1 = -b^2/r^2 + (v + v1 r)/eps - 1 = -(b^2/r^2 + 1) - dsum/eps
-    const float fr = sum * inv_eps - x * (2.0f * b + x) * inv_r;
-    const float fr1 = -(b2 * inv_r * inv_r + 1.0f) - dsum * inv_eps;
-    q = fdiv(fr, fr1);
-    x -= q;
-    --guard; // the reference iterates without a bound; a lane must never spin forever
-  } while ((fabsf(q) > 0.001f * fabsf(b + x)) & (guard != 0));
+  }
   r = b + x;
 
   // trim.C:235-271 (v, v1 are those of the last evaluated r, as in the reference)

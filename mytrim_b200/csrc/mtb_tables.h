@@ -438,7 +438,7 @@ build_host_tables(const HostConfig & H, HostTables & T, LaunchParams & P, std::s
   P.n_tclass = (int32_t)nt;
   P.n_elements = (int32_t)T.elements.size();
   P.n_materials = (int32_t)T.materials.size();
-  if (P.n_elements + SPECIES_ELEMENT0 > SPECIES_MASK)
+  if (P.n_pclass + SPECIES_CLASS0 > SPECIES_MASK)
   {
     err = "too many elements";
     return MTB_EINVAL;

@@ -210,7 +210,7 @@ struct BlockCtx
   const double * layer_cum;
   const int32_t * layer_mat;
   unsigned int * hist_vac;  // [smem_hist_bins] or null
-  unsigned int * hist_repl; // [smem_hist_bins] or null
+  unsigned int * hist_repl; // [smem_hist_bins] or null; directly behind hist_vac
   unsigned long long * blk_u64; // [CNT_COUNT]
   double * blk_f64;             // [2]
   PoolSlot * pool;               // [MTB_POOL_SLOTS] work-sharing ring of this CTA (share kernels)
@@ -434,10 +434,11 @@ struct Lane
 
 // Select the projectile class after L.packed changed (pop, hand-over to a recoil).
 MTB_HD void
-set_species(Lane & L, const BlockCtx & S)
+set_species(Lane & L, const BlockCtx &)
 {
   const uint32_t species = L.packed & SPECIES_MASK;
-  L.pcls = species == SPECIES_PRIMARY ? L.prim_pcls : S.elements[species - SPECIES_ELEMENT0].tcls;
+  // a popped ion waits for this value behind a global load: no dependent table look-up here
+  L.pcls = species == SPECIES_PRIMARY ? L.prim_pcls : (int32_t)(species - SPECIES_CLASS0);
 }
 
 // Projectile class of a primary: a target class, a registered primary species, or -1.
@@ -630,7 +631,7 @@ MTB_HD void
 finish_ion(const LaunchParams & P, const BlockCtx & S, const Lane & L, const float4_t * rows, int state, double x, double y,
            double z)
 {
-  if ((L.packed & FLAG_PRIMARY) && P.records)
+  if (L.packed & FLAG_PRIMARY) // set only when records were asked for (one test on every exit of an ion)
   {
     mtb_record & r = P.records[L.prim];
     r.pos[0] = x;
@@ -649,9 +650,17 @@ finish_ion(const LaunchParams & P, const BlockCtx & S, const Lane & L, const flo
   }
 }
 
+// `repl` selects the replacement histogram (it follows the vacancy histogram in shared memory and in P.u64)
 MTB_HD void
-depth_tally(const LaunchParams & P, const BlockCtx & S, unsigned int * smem_hist, size_t goff, int x)
+depth_tally(const LaunchParams & P, const BlockCtx & S, bool repl, int x)
 {
+  // smem_hist_bins <= hist_bins: the common case needs one (unsigned) test that also covers x < 0 —
+  // every instruction on this path is issued for 2-4 lanes in almost every iteration of the warp
+  if ((unsigned int)x < (unsigned int)P.smem_hist_bins)
+  {
+    MTB_ATOMIC_ADD(&S.hist_vac[(unsigned int)x + (repl ? (unsigned int)P.smem_hist_bins : 0u)], 1u);
+    return;
+  }
   if (x < 0)
     return;
   if (x >= P.hist_bins)
@@ -660,9 +669,9 @@ depth_tally(const LaunchParams & P, const BlockCtx & S, unsigned int * smem_hist
     x = P.hist_bins - 1;
   }
   if (x < P.smem_hist_bins)
-    MTB_ATOMIC_ADD(&smem_hist[x], 1u);
+    MTB_ATOMIC_ADD(&(repl ? S.hist_repl : S.hist_vac)[x], 1u);
   else
-    MTB_ATOMIC_ADD(&P.u64[goff + (size_t)x], 1ull);
+    MTB_ATOMIC_ADD(&P.u64[(repl ? off_repl(P) : off_vac(P)) + (size_t)x], 1ull);
 }
 
 // vacancyCreation() of the in-tree subclasses
@@ -1005,7 +1014,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           L.ic = 0;
           L.prim = (uint32_t)idx;
           L.uid = EVENTS ? P.single_uid : P.first_index + idx;
-          L.packed = SPECIES_PRIMARY | (((uint32_t)src.gen & GEN_MASK) << GEN_SHIFT) | FLAG_PRIMARY;
+          L.packed = SPECIES_PRIMARY | (((uint32_t)src.gen & GEN_MASK) << GEN_SHIFT) | (P.records ? (uint32_t)FLAG_PRIMARY : 0u);
           L.tag = src.tag;
           L.pZ = src_Z;
           L.pm = src_m;
@@ -1303,7 +1312,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
         }
         // TrimVacCount::vacancyCreation / replacementCollision (TrimVacCount.C:31-53): one tally site
         if (tally_on<TR>(P, MTB_TALLY_VAC_DEPTH))
-          depth_tally(P, S, vacancy ? S.hist_vac : S.hist_repl, vacancy ? off_vac(P) : off_repl(P), (int)L.px);
+          depth_tally(P, S, !vacancy, (int)L.px);
       }
       else
       {
@@ -1368,7 +1377,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       L.casIons++;
       const float qs = frsqrt(qx * qx + qy * qy + qz * qz);
       const uint64_t ruid = child_uid(L.uid, L.ic, w[3]);
-      const uint32_t rpacked = (uint32_t)(SPECIES_ELEMENT0 + M.first_elem + nn) | ((uint32_t)rec_gen << GEN_SHIFT);
+      const uint32_t rpacked = (uint32_t)(SPECIES_CLASS0 + el.tcls) | ((uint32_t)rec_gen << GEN_SHIFT);
       const bool keep_projectile = (state == MTB_MOVING) && (E2 <= Erec);
       if (state == MTB_MOVING && !keep_projectile)
       {

@@ -111,7 +111,7 @@ struct __attribute__((aligned(16))) StackEntry
   float dir[3];
   uint32_t ic;     // collision steps already taken by this ion
   uint64_t uid;    // Philox stream id
-  uint32_t packed; // species | gen << 12 | flags << 28
+  uint32_t packed; // species (0: the primary, else 1 + projectile class) | gen << 12 | flags << 28
   int32_t tag;
 };
 static_assert(sizeof(StackEntry) == 64, "StackEntry layout");
@@ -119,7 +119,7 @@ static_assert(sizeof(StackEntry) == 64, "StackEntry layout");
 enum
 {
   SPECIES_PRIMARY = 0,   // (Z, m) of the lane's current primary
-  SPECIES_ELEMENT0 = 1,  // 1 + global element index
+  SPECIES_CLASS0 = 1,    // 1 + projectile class of the target atom the recoil was (DevElement::tcls)
   SPECIES_MASK = 0xFFF,
   GEN_SHIFT = 12,
   GEN_MASK = 0xFFFF,
