@@ -38,7 +38,8 @@ tmarks = [("lookup", "lookup_cluster(const LaunchParams"), ("lane/class helpers"
           ("loop: move+rotate", "recoil is born at the previous collision site"), ("loop: CUT", "CUT boundaries — trim.C:344-352"),
           ("loop: fate", "fate of recoil and projectile"), ("loop: events", "    if (EVENTS)"), ("loop: who flies next", "who flies next")]
 pmarks = [("proton_stopping", "proton_stopping(const DevElement"), ("element_stopping", "element_stopping(const ProjClass"),
-          ("material_stopping", "material_stopping(const ProjClass"), ("magic: rutherford+guess", "magic_scatter(int potential"),
+          ("material_stopping", "material_stopping(const ProjClass"), ("magic: newton step", "screening_sums(int potential"),
+          ("magic: rutherford+guess", "magic_scatter(int potential"),
           ("magic: newton loop", "  do\n"), ("magic: tail", "// trim.C:235-271"), ("flight_from_pair", "flight_from_pair(const PairM"),
           ("on-the-fly pair", "make_pair_m(const ProjClass")]
 
