@@ -449,6 +449,8 @@ build_tables(mtb_handle * h)
   h->smem_bytes = smem_layout(P).total;
   if (h->smem_bytes > 200 * 1024)
     return fail(MTB_EINVAL, "configuration tables do not fit in shared memory");
+  if (std::getenv("MYTRIM_B200_NO_MONO")) // test / tuning knob: single-element samples through the FAST variant
+    P.mono = 0;
   h->fast = fast_path_ok(P);
   h->variant = pick_variant(P, false);
   h->variant_custom = pick_variant(P, true);
@@ -461,6 +463,8 @@ build_tables(mtb_handle * h)
   h->bps[V][SH] = std::max(h->bps[V][SH], 1);
   MTB_SETUP_KERNEL(TraitsFast, VARIANT_FAST, 0)
   MTB_SETUP_KERNEL(TraitsFastShare, VARIANT_FAST, 1)
+  MTB_SETUP_KERNEL(TraitsMono, VARIANT_MONO, 0)
+  MTB_SETUP_KERNEL(TraitsMonoShare, VARIANT_MONO, 1)
   MTB_SETUP_KERNEL(TraitsClusters, VARIANT_CLUSTERS, 0)
   MTB_SETUP_KERNEL(TraitsClustersShare, VARIANT_CLUSTERS, 1)
   MTB_SETUP_KERNEL(TraitsLayers, VARIANT_LAYERS, 0)
@@ -498,6 +502,12 @@ launch_kernel(mtb_handle * h, const LaunchParams & P, unsigned blocks, Variant v
         transport_kernel<TraitsFastShare><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
       else
         transport_kernel<TraitsFast><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+      break;
+    case VARIANT_MONO:
+      if (share)
+        transport_kernel<TraitsMonoShare><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+      else
+        transport_kernel<TraitsMono><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
       break;
     case VARIANT_CLUSTERS:
       if (share)

@@ -75,6 +75,7 @@ block_add(unsigned long long * acc, uint32_t v)
 // that covers a configuration:
 //   FAST      north-star options: UNIVERSAL potential, follow ALL, vacancies_created++, TrimVacCount depth
 //             tallies, solid/layered sample, no CUT boundaries, projectile classes only
+//   MONO      FAST for a sample of one single-element material (Cu->Cu, H->Fe, He->Fe, C->W of BASELINE.json)
 //   CLUSTERS  the tests/uo2 shape: sampleClusters geometry, per-primary species (fission fragments),
 //             ion log / energy partition, otherwise the north-star options
 //   LAYERS    solid/layered sample with any follow policy, vacancy model and tally (vacenergycount, range,
@@ -92,7 +93,9 @@ enum Feature : uint32_t
   F_FOLLOW = 1u << 7,    // follow policy chosen at run time (else ALL)
   F_VACMODEL = 1u << 8,  // vacancy model chosen at run time (else vacancies_created++)
   F_TALLY_RT = 1u << 9,  // tallies switched at run time within kTally (else exactly kTally)
-  F_DIAG = 1u << 10      // stack high-water mark
+  F_DIAG = 1u << 10,     // stack high-water mark
+  F_MONO = 1u << 11      // the sample is one material made of one element (solid or layers of it): no geometry
+                         // look-up, no vacuum test, no target pick, no loop over elements in the stopping
 };
 
 template <uint32_t F, uint32_t TALLY>
@@ -105,6 +108,7 @@ struct TraitsT
 
 constexpr uint32_t kFeatFast = 0;
 constexpr uint32_t kTallyFast = MTB_TALLY_VAC_DEPTH;
+constexpr uint32_t kFeatMono = F_MONO;
 constexpr uint32_t kFeatClusters = F_CUSTOM | F_CLUSTERS | F_TALLY_RT;
 constexpr uint32_t kTallyClusters = MTB_TALLY_IONLOG | MTB_TALLY_PHONON;
 constexpr uint32_t kFeatLayers = F_FOLLOW | F_VACMODEL | F_TALLY_RT;
@@ -114,6 +118,8 @@ constexpr uint32_t kTallyAll = 0xffffffffu;
 
 typedef TraitsT<kFeatFast, kTallyFast> TraitsFast;
 typedef TraitsT<kFeatFast | F_SHARE, kTallyFast> TraitsFastShare;
+typedef TraitsT<kFeatMono, kTallyFast> TraitsMono;
+typedef TraitsT<kFeatMono | F_SHARE, kTallyFast> TraitsMonoShare;
 typedef TraitsT<kFeatClusters, kTallyClusters> TraitsClusters;
 typedef TraitsT<kFeatClusters | F_SHARE, kTallyClusters> TraitsClustersShare;
 typedef TraitsT<kFeatLayers, kTallyAll> TraitsLayers;
@@ -135,13 +141,14 @@ enum Variant
   VARIANT_CLUSTERS,
   VARIANT_LAYERS,
   VARIANT_GENERIC,
+  VARIANT_MONO,
   VARIANT_COUNT
 };
 
 inline uint32_t
 variant_features(Variant v)
 {
-  return v == VARIANT_FAST ? kFeatFast : v == VARIANT_CLUSTERS ? kFeatClusters : v == VARIANT_LAYERS ? kFeatLayers : kFeatGeneric;
+  return v == VARIANT_FAST ? kFeatFast : v == VARIANT_MONO ? kFeatMono : v == VARIANT_CLUSTERS ? kFeatClusters : v == VARIANT_LAYERS ? kFeatLayers : kFeatGeneric;
 }
 
 // Features a configuration needs (F_CUSTOM is decided per primary: variants without it hand
@@ -181,7 +188,7 @@ inline Variant
 pick_variant(const LaunchParams & P, bool custom)
 {
   if (!custom && variant_covers(kFeatFast, kTallyFast, P))
-    return VARIANT_FAST;
+    return P.mono ? VARIANT_MONO : VARIANT_FAST;
   if (variant_covers(kFeatClusters, kTallyClusters, P))
     return VARIANT_CLUSTERS;
   if (!custom && variant_covers(kFeatLayers, kTallyAll, P))
@@ -1108,13 +1115,15 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     ++L.ic;
     int cluster = -1;
     int mi = 0;
-    if (!(TR::has(F_CLUSTERS) && L.dsafe > 0.0f)) // else: clusters geometry, still provably in the matrix
+    if (TR::has(F_MONO))
+      ; // material 0 everywhere (sample_solid.C:25-29; sample_layers.C:26-49 never returns vacuum)
+    else if (!(TR::has(F_CLUSTERS) && L.dsafe > 0.0f)) // else: clusters geometry, still provably in the matrix
     {
       float safe;
       mi = lookup_material<TR>(P, S, L.px, L.py, L.pz, &cluster, &safe);
       L.dsafe = safe;
     }
-    if (mi < 0)
+    if (!TR::has(F_MONO) && mi < 0)
     {
       // vacuum: the reference breaks out with the state still MOVING (trim.C:80-82)
       block_add(&S.blk_u64[CNT_LEFT], 1u);
@@ -1123,7 +1132,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       active = false;
       break;
     }
-    const DevMaterial & M = S.materials[mi];
+    const DevMaterial & M = S.materials[TR::has(F_MONO) ? 0 : mi];
     const int mtag = (TR::has(F_CLUSTERS) && P.geom_kind == MTB_GEOM_CLUSTERS && mi == 1) ? cluster : M.tag;
     L.casSteps++;
 
@@ -1161,7 +1170,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       pm.sk = r.w;
     }
     else
-      pm = S.pairm[L.pcls * P.n_materials + mi];
+      pm = S.pairm[TR::has(F_MONO) ? L.pcls : L.pcls * P.n_materials + mi];
     float ls;
     const float sqrtE0 = fsqrt(E0);
     const float pmax = flight_from_pair(pm, sqrtE0, &ls);
@@ -1171,13 +1180,14 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
 
     // target element — trim.C:147-156
     int nn = 0;
-    for (; nn < M.n_elem - 1; ++nn)
-    {
-      hh -= S.elements[M.first_elem + nn].t;
-      if (hh <= 0.0f)
-        break;
-    }
-    const DevElement & el = S.elements[M.first_elem + nn];
+    if (!TR::has(F_MONO))
+      for (; nn < M.n_elem - 1; ++nn)
+      {
+        hh -= S.elements[M.first_elem + nn].t;
+        if (hh <= 0.0f)
+          break;
+      }
+    const DevElement & el = S.elements[TR::has(F_MONO) ? 0 : M.first_elem + nn];
 
     // element part of MaterialBase::average — material.C:99-108
     PairE pe;
@@ -1190,13 +1200,14 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       pe.sfi = r.w;
     }
     else
-      pe = S.paire[L.pcls * P.n_tclass + el.tcls];
+      pe = S.paire[TR::has(F_MONO) ? L.pcls : L.pcls * P.n_tclass + el.tcls];
     const float my = pe.my;
 
     const float sqe = pe.sfi * sqrtE0; // sqrt(eps), eps = fi E — trim.C:159-160
     const float b = p * pe.inv_ai;
 
-    const float see = material_stopping(pc, lowrow, M, S.elements, E0, sqrtE0 * pm.sk); // trim.C:166
+    const float see = TR::has(F_MONO) ? (0.0f + element_stopping(pc, lowrow, el, E0, sqrtE0 * pm.sk) * el.t) * M.arho
+                                      : material_stopping(pc, lowrow, M, S.elements, E0, sqrtE0 * pm.sk); // trim.C:166
     const float dee_f = ls * see;
 
     const Scatter sc = magic_scatter(potential, sqe, b);

@@ -237,6 +237,7 @@ struct LaunchParams
   double * f64;                 // [0]=Eel, [1]=Enuc
   int32_t hist_bins, evac_rows;
   int32_t smem_hist_bins;       // depth bins mirrored in shared memory
+  int32_t mono;                 // one material made of one element in a solid/layered sample (host flag: MONO variants)
   mtb_record * records;         // [n_primaries] or null
   mtb_ion_log * ionlog;
   unsigned long long ionlog_cap;

@@ -194,6 +194,8 @@ hs_run(hs_engine * e, uint64_t n, const mtb_ion * primaries, uint64_t seed, uint
   auto run_variant = [&](Variant which) {
     if (which == VARIANT_FAST)
       lane_loop<TraitsFast>(P, S, 0);
+    else if (which == VARIANT_MONO)
+      lane_loop<TraitsMono>(P, S, 0);
     else if (which == VARIANT_CLUSTERS)
       lane_loop<TraitsClusters>(P, S, 0);
     else if (which == VARIANT_LAYERS)

@@ -8,8 +8,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = sys.argv[1]
-kernel = sys.argv[2] if len(sys.argv) > 2 else "TraitsT<(unsigned int)0, (unsigned int)1>"  # north-star variant
-sass = sys.argv[3] if len(sys.argv) > 3 else "TraitsTILj0ELj1E"
+kernel = sys.argv[2] if len(sys.argv) > 2 else "TraitsT<(unsigned int)2048, (unsigned int)1>"  # north-star variant (MONO)
+sass = sys.argv[3] if len(sys.argv) > 3 else "TraitsTILj2048ELj1E"
 out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_hotspots.py"), rep, "--kernel", kernel, "--sass-kernel", sass,
                       "--top", "5000"],
                      capture_output=True, text=True).stdout.split("\n")
