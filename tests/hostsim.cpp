@@ -7,6 +7,7 @@
 // from the GPU in the last bits but follow the same algorithm.  This is NOT part of the product
 // and not a fallback: libmytrim_b200.so fails loudly without a CUDA device.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -44,6 +45,8 @@ hs_prepare(hs_engine * e)
   if (int rc = build_host_tables(e->host, e->T, e->P, e->err))
     return rc;
   LaunchParams & P = e->P;
+  if (std::getenv("MYTRIM_B200_NO_MONO")) // same knob as mtb_engine.cu::build_tables
+    P.mono = 0;
   P.elements = e->T.elements.data();
   P.materials = e->T.materials.data();
   P.ionz = e->T.ionz.data();

@@ -322,3 +322,30 @@ def test_options_potentials_and_scale(opts):
     if "length_scale" in opts:
         # positions are in units of 10 A: the same physics lands in 10x fewer depth bins
         assert ro["pos"][:, 0].mean() < 20.0
+
+
+def test_mono_variant_equals_fast_variant_on_the_host():
+    """A single-element sample takes the MONO variant (no geometry look-up, vacuum test, target pick, element
+    loop); MYTRIM_B200_NO_MONO routes it through FAST.  Same arithmetic: without FMA contraction (host build)
+    the per-primary records and the tallies are identical bit for bit."""
+    import os
+    cfg = dict(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS)
+    out = []
+    for knob in (None, "MYTRIM_B200_NO_MONO"):
+        if knob:
+            os.environ[knob] = "1"
+        try:
+            res = {}
+            for name, n in (("cu_on_cu_10keV", 150), ("h_on_fe_100keV", 100), ("c_on_w_1MeV", 6)):
+                with util.HostSimEngine(**cfg) as hs:
+                    c = util.setup_engine(hs, name)
+                    r = hs.run(util.primaries_for(c, n), seed=77, records=True)
+                    res[name] = (r.copy(), hs.vac_depth()[0].copy(), hs.counters())
+            out.append(res)
+        finally:
+            if knob:
+                os.environ.pop(knob)
+    for name in out[0]:
+        (ra, va, ca), (rb, vb, cb) = out[0][name], out[1][name]
+        assert ra.tobytes() == rb.tobytes(), name
+        assert np.array_equal(va, vb) and ca["steps"] == cb["steps"] and ca["vacancies_created"] == cb["vacancies_created"]

@@ -308,12 +308,14 @@ def test_fast_kernel_defers_unknown_species():
         assert abs(ca["steps"] - cb["steps"]) <= 1e-3 * cb["steps"] and ca["primaries"] == cb["primaries"] == len(ions)
 
 
-@pytest.mark.parametrize("which", ["fast", "clusters", "layers"])
+@pytest.mark.parametrize("which", ["mono", "fast", "clusters", "layers"])
 def test_lean_variants_agree_with_generic_kernel(which):
-    """Every lean kernel variant (mtb_transport.cuh: FAST / CLUSTERS / LAYERS) against the all-options kernel
-    on the same primaries and seeds.  Different instantiations contract FMAs differently, so agreement is to
-    the trajectory tolerance; the integer tallies agree for all cascades without a branch flip."""
-    if which == "fast":
+    """Every lean kernel variant (mtb_transport.cuh: MONO / FAST / CLUSTERS / LAYERS) against the all-options
+    kernel on the same primaries and seeds.  Different instantiations contract FMAs differently, so agreement is
+    to the trajectory tolerance; the integer tallies agree for all cascades without a branch flip.  (A
+    single-element sample takes MONO by default; MYTRIM_B200_NO_MONO routes it through FAST.)"""
+    knob = {"fast": "MYTRIM_B200_NO_MONO"}.get(which)
+    if which in ("mono", "fast"):
         cfg = dict(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS)
         def setup(e):
             c = util.setup_engine(e, "cu_on_cu_10keV")
@@ -334,11 +336,17 @@ def test_lean_variants_agree_with_generic_kernel(which):
             ions = _fission_like_primaries(400)
             ions["pos"][:40] = cl[np.arange(40) % len(cl), :3] + 2.0
             return ions
-    with capi.Engine(**cfg) as a:
-        ions = setup(a)
-        ra = a.run(ions, seed=31, records=True)
-        ca = a.counters()
-        la = len(a.ion_log()) if which == "clusters" else 0
+    if knob:
+        os.environ[knob] = "1"
+    try:
+        with capi.Engine(**cfg) as a:
+            ions = setup(a)
+            ra = a.run(ions, seed=31, records=True)
+            ca = a.counters()
+            la = len(a.ion_log()) if which == "clusters" else 0
+    finally:
+        if knob:
+            os.environ.pop(knob)
     os.environ["MYTRIM_B200_VARIANT"] = "generic"
     try:
         with capi.Engine(**cfg) as b:
@@ -349,7 +357,7 @@ def test_lean_variants_agree_with_generic_kernel(which):
     finally:
         os.environ.pop("MYTRIM_B200_VARIANT")
     same = (ra["steps"] == rb["steps"]) & (ra["vacancies"] == rb["vacancies"]) & (ra["ions"] == rb["ions"])
-    assert same.mean() > (0.97 if which == "fast" else 0.85), same.mean()
+    assert same.mean() > (0.97 if which in ("mono", "fast") else 0.85), same.mean()
     sel = ra["primary_steps"] == rb["primary_steps"]
     assert sel.mean() > 0.97
     d = np.linalg.norm(ra["pos"] - rb["pos"], axis=1) / np.maximum(np.linalg.norm(ra["pos"] - ions["pos"], axis=1), 1.0)
