@@ -598,7 +598,8 @@ build_host_tables(const HostConfig & H, HostTables & T, LaunchParams & P, std::s
   P.hist_bins = bins;
   P.evac_rows = c.evac_rows > 0 ? c.evac_rows : 32;
   P.smem_hist_bins = (c.tally_mask & MTB_TALLY_VAC_DEPTH) ? std::min(bins, kSmemHistMax) : 0;
-  P.mono = (P.n_materials == 1 && P.n_elements == 1 && (P.geom_kind == MTB_GEOM_SOLID || P.geom_kind == MTB_GEOM_LAYERS)) ? 1 : 0;
+  P.one_material = (P.n_materials == 1 && (P.geom_kind == MTB_GEOM_SOLID || P.geom_kind == MTB_GEOM_LAYERS)) ? 1 : 0;
+  P.mono = (P.one_material && P.n_elements == 1) ? 1 : 0;
   P.ionlog_cap = (c.tally_mask & MTB_TALLY_IONLOG) ? (c.ionlog_capacity ? c.ionlog_capacity : (1ull << 20)) : 0;
   P.range_cap = (c.tally_mask & MTB_TALLY_RANGE) ? (c.range_capacity ? c.range_capacity : (1ull << 22)) : 0;
   return MTB_OK;

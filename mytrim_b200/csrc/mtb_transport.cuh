@@ -401,7 +401,8 @@ lookup_material(const LaunchParams & P, const BlockCtx & S, double px, double py
   }
   // sample_solid.C:25-29, sample_layers.C:26-49: the first layer whose cumulative thickness exceeds x;
   // beyond the stack -> last layer
-  if (P.geom_kind == MTB_GEOM_SOLID || P.n_layers == 1)
+  // (a stack of layers of one and the same material, e.g. inputs/samplelayers_zro2_multilayer.in, needs no search)
+  if (P.geom_kind == MTB_GEOM_SOLID || P.n_layers == 1 || P.one_material)
     return 0;
   int lo = 0, hi = P.n_layers - 1;
   while (lo < hi)

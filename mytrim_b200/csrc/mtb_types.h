@@ -248,6 +248,7 @@ struct LaunchParams
   mtb_event * events;
   unsigned long long events_cap;
   uint64_t single_uid;
+  int32_t one_material;         // solid/layered sample whose layers are all the same material (host flag: no layer search)
 };
 
 // offsets inside the u64 block
