@@ -17,6 +17,7 @@
 //   scale L                   length scale
 //   tally vaccount|vacenergycount|range|base|primaries|recoils|phonon
 //   primaries_only 0|1
+//   potential universal|moliere|ckr   TrimBase::_potential (trim.h:63-69; default universal)
 //   box wx wy wz              SampleLayers(wx, wy, wz); default wx = total thickness, 100, 100
 //   layer thickness rho nelem
 //   elem Z m t [Edisp Elbind] (nelem lines after each layer)
@@ -115,7 +116,7 @@ struct Job
   unsigned threads = 1;
   unsigned master = 2344;
   double scale = 1.0;
-  std::string tally = "vaccount", out, seedfile;
+  std::string tally = "vaccount", out, seedfile, potential = "universal";
   bool primaries_only = false;
   bool have_box = false, have_start = false;
   double box[3] = {0, 100, 100};
@@ -188,6 +189,7 @@ buildWorker(const Job & job, Worker & w)
   else
     w.sample = new SampleLayers(thickness, 100.0, 100.0);
   w.trim = makeTrim(job, w.simconf, w.sample, w.probe);
+  w.trim->_potential = job.potential == "moliere" ? TrimBase::MOLIERE : job.potential == "ckr" ? TrimBase::CKR : TrimBase::UNIVERSAL;
   for (auto & l : job.layers)
   {
     auto * mat = new MaterialBase(w.simconf, l.rho);
@@ -367,6 +369,8 @@ main()
       is >> job.tally;
     else if (cmd == "primaries_only")
       is >> job.primaries_only;
+    else if (cmd == "potential")
+      is >> job.potential;
     else if (cmd == "out")
       is >> job.out;
     else if (cmd == "box")

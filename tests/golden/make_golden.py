@@ -10,6 +10,7 @@ Fixtures:
   rng_mt19937.txt             SimconfType::drand()/irand() sequences (simconf.h:52-53).
   stopping.json               MaterialBase::getrstop + average() known answers.
   ref_records_<cfg>.npz       per-primary records of the reference for fixed 32-bit seeds.
+  ref_records_<cfg>_<potential>.npz  the same with TrimBase::_potential = MOLIERE / CKR.
   vacancy_count_published.json the reference's published vacancies/ion table
                                (validation/vacancy_count/vacancy_count_comparison.dat).
 """
@@ -90,6 +91,21 @@ def records():
                             summary=json.dumps(summary))
 
 
+# the other two interatomic potentials of trim.C:194-222, 238-259 (TrimBase::_potential)
+POTENTIAL_CASES = {"moliere": ("cu_on_cu_1keV", 256), "ckr": ("cu_on_cu_1keV", 256)}
+
+
+def potentials():
+    for pot, (name, n) in POTENTIAL_CASES.items():
+        c = util.CONFIGS[name]
+        seeds = util.distinct_seeds(n, master=77)
+        rec, summary, hist = util.run_reference_cascades(c["ion"], c["materials"], c["thicknesses"], seeds,
+                                                         box=c.get("box"), potential=pot)
+        np.savez_compressed(os.path.join(HERE, "ref_records_%s_%s.npz" % (name, pot)), records=rec, seeds=seeds,
+                            vac=hist[:, 1].astype(np.uint64), repl=hist[:, 2].astype(np.uint64),
+                            summary=json.dumps(summary))
+
+
 def published():
     src = "/root/reference/validation/vacancy_count/vacancy_count_comparison.dat"
     rows = [l.strip().split(",") for l in open(src)][2:]
@@ -110,5 +126,6 @@ if __name__ == "__main__":
     rng()
     stopping()
     records()
+    potentials()
     published()
     print("golden fixtures written to", HERE)
