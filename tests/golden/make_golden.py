@@ -11,6 +11,8 @@ Fixtures:
   stopping.json               MaterialBase::getrstop + average() known answers.
   ref_records_<cfg>.npz       per-primary records of the reference for fixed 32-bit seeds.
   ref_records_<cfg>_<potential>.npz  the same with TrimBase::_potential = MOLIERE / CKR.
+  ref_tally_<tally>_<cfg>.npz records (+ output file content) of TrimRange / TrimPrimaries / TrimRecoils /
+                               TrimVacEnergyCount / TrimPhononOut.
   vacancy_count_published.json the reference's published vacancies/ion table
                                (validation/vacancy_count/vacancy_count_comparison.dat).
 """
@@ -106,6 +108,26 @@ def potentials():
                             summary=json.dumps(summary))
 
 
+# the other in-tree tally classes: (reference tally name, configuration, primaries)
+TALLY_CASES = {"range": ("cu_on_cu_1keV", 192), "primaries": ("cu_on_cu_10keV", 64), "recoils": ("cu_on_cu_10keV", 64),
+               "vacenergycount": ("c_on_w_1MeV", 12), "phonon": ("cu_on_cu_1keV", 128)}
+
+
+def tallies():
+    for tally, (name, n) in TALLY_CASES.items():
+        c = util.CONFIGS[name]
+        seeds = util.distinct_seeds(n, master=101)
+        rec, summary, hist = util.run_reference_cascades(c["ion"], c["materials"], c["thicknesses"], seeds,
+                                                         box=c.get("box"), tally=tally)
+        extra = {}
+        if tally == "vacenergycount":
+            extra["evac"] = hist[hist[:, 2] > 0].astype(np.int64)   # non-zero rows (E bin, x bin, count)
+        if tally == "range":
+            extra["ranges_dat"] = np.array(hist)       # the text of <base>_ranges.dat
+        np.savez_compressed(os.path.join(HERE, "ref_tally_%s_%s.npz" % (tally, name)), records=rec, seeds=seeds,
+                            summary=json.dumps(summary), **extra)
+
+
 def published():
     src = "/root/reference/validation/vacancy_count/vacancy_count_comparison.dat"
     rows = [l.strip().split(",") for l in open(src)][2:]
@@ -127,5 +149,6 @@ if __name__ == "__main__":
     stopping()
     records()
     potentials()
+    tallies()
     published()
     print("golden fixtures written to", HERE)

@@ -162,6 +162,11 @@ def run_reference_cascades(ion, materials, thicknesses, seeds, tally="vaccount",
         hist = None
         if os.path.exists(out + "_vac.dat"):
             hist = np.loadtxt(out + "_vac.dat", ndmin=2)
+        elif os.path.exists(out + "_evac.dat"):   # TrimVacEnergyCount::writeOutput: "E x count" lines
+            hist = np.loadtxt(out + "_evac.dat", ndmin=2)
+        elif os.path.exists(out + "_ranges.dat"):  # TrimRange::writeOutput: "#x Z.." header, then "x count.." lines
+            with open(out + "_ranges.dat") as f:
+                hist = f.read()
     return rec, json.loads(stdout[-1]), hist
 
 
