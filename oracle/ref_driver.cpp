@@ -19,6 +19,8 @@
 //   primaries_only 0|1
 //   potential universal|moliere|ckr   TrimBase::_potential (trim.h:63-69; default universal)
 //   box wx wy wz              SampleLayers(wx, wy, wz); default wx = total thickness, 100, 100
+//   sample layers|wire|burried_wire   sample class (default layers); wire samples take `box` as their size and
+//                             the `layer` blocks as material[0], material[1] (thickness unused)
 //   layer thickness rho nelem
 //   elem Z m t [Edisp Elbind] (nelem lines after each layer)
 //   start x y z dx dy dz      primary start (default 0, wy/2, wz/2, dir 1 0 0)
@@ -44,6 +46,8 @@
 #include "element.h"
 #include "material.h"
 #include "sample_layers.h"
+#include "sample_wire.h"
+#include "sample_burried_wire.h"
 #include "ion.h"
 #include "trim.h"
 #include "apps/include/ThreadedTrimBase.h"
@@ -101,7 +105,7 @@ struct LayerDesc
 struct Worker
 {
   SimconfType * simconf = nullptr;
-  SampleLayers * sample = nullptr;
+  SampleBase * sample = nullptr;
   TrimBase * trim = nullptr;
   Probe * probe = nullptr;
   std::vector<unsigned> todo;
@@ -116,7 +120,7 @@ struct Job
   unsigned threads = 1;
   unsigned master = 2344;
   double scale = 1.0;
-  std::string tally = "vaccount", out, seedfile, potential = "universal";
+  std::string tally = "vaccount", out, seedfile, potential = "universal", sample = "layers";
   bool primaries_only = false;
   bool have_box = false, have_start = false;
   double box[3] = {0, 100, 100};
@@ -184,10 +188,15 @@ buildWorker(const Job & job, Worker & w)
   double thickness = 0;
   for (auto & l : job.layers)
     thickness += l.thickness;
-  if (job.have_box)
-    w.sample = new SampleLayers(job.box[0], job.box[1], job.box[2]);
+  SampleLayers * layered = nullptr;
+  if (job.sample == "wire")
+    w.sample = new SampleWire(job.box[0], job.box[1], job.box[2]);
+  else if (job.sample == "burried_wire")
+    w.sample = new SampleBurriedWire(job.box[0], job.box[1], job.box[2]);
+  else if (job.have_box)
+    w.sample = layered = new SampleLayers(job.box[0], job.box[1], job.box[2]);
   else
-    w.sample = new SampleLayers(thickness, 100.0, 100.0);
+    w.sample = layered = new SampleLayers(thickness, 100.0, 100.0);
   w.trim = makeTrim(job, w.simconf, w.sample, w.probe);
   w.trim->_potential = job.potential == "moliere" ? TrimBase::MOLIERE : job.potential == "ckr" ? TrimBase::CKR : TrimBase::UNIVERSAL;
   for (auto & l : job.layers)
@@ -197,7 +206,8 @@ buildWorker(const Job & job, Worker & w)
       mat->_element.push_back(e);
     mat->prepare();
     w.sample->material.push_back(mat);
-    w.sample->layerThickness.push_back(l.thickness);
+    if (layered)
+      layered->layerThickness.push_back(l.thickness);
   }
 }
 
@@ -371,6 +381,8 @@ main()
       is >> job.primaries_only;
     else if (cmd == "potential")
       is >> job.potential;
+    else if (cmd == "sample")
+      is >> job.sample;
     else if (cmd == "out")
       is >> job.out;
     else if (cmd == "box")

@@ -13,6 +13,7 @@ Fixtures:
   ref_records_<cfg>_<potential>.npz  the same with TrimBase::_potential = MOLIERE / CKR.
   ref_tally_<tally>_<cfg>.npz records (+ output file content) of TrimRange / TrimPrimaries / TrimRecoils /
                                TrimVacEnergyCount / TrimPhononOut.
+  ref_geometry_<sample>.npz    records of the reference in a SampleWire / SampleBurriedWire.
   vacancy_count_published.json the reference's published vacancies/ion table
                                (validation/vacancy_count/vacancy_count_comparison.dat).
 """
@@ -128,6 +129,24 @@ def tallies():
                             summary=json.dumps(summary), **extra)
 
 
+# SampleWire (CUT boundaries in x, y; vacuum outside the cylinder) and SampleBurriedWire (INF boundaries, cover
+# layer, matrix around the wire): (sample class, box, materials [wire, cover/matrix], ion, start, primaries)
+GEOMETRY_CASES = {
+    "wire": ("wire", (60.0, 60.0, 1000.0), [util.CU], (29, 63.546, 2.0e4), (30.0, 18.0, 0.0, 0.0, 0.3, 1.0), 192),
+    "burried_wire": ("burried_wire", (100.0, 100.0, 300.0), [util.CU, util.FE], (29, 63.546, 2.0e4),
+                     (50.0, 50.0, -200.0, 0.1, 0.0, 1.0), 128),
+}
+
+
+def geometries():
+    for key, (sample, box, mats, ion, start, n) in GEOMETRY_CASES.items():
+        seeds = util.distinct_seeds(n, master=303)
+        rec, summary, _ = util.run_reference_cascades(ion, mats, [1.0] * len(mats), seeds, box=box, sample=sample,
+                                                      start=start)
+        np.savez_compressed(os.path.join(HERE, "ref_geometry_%s.npz" % key), records=rec, seeds=seeds,
+                            summary=json.dumps(summary))
+
+
 def published():
     src = "/root/reference/validation/vacancy_count/vacancy_count_comparison.dat"
     rows = [l.strip().split(",") for l in open(src)][2:]
@@ -150,5 +169,6 @@ if __name__ == "__main__":
     records()
     potentials()
     tallies()
+    geometries()
     published()
     print("golden fixtures written to", HERE)

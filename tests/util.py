@@ -123,7 +123,7 @@ def run_reference(script, timeout=600):
 
 
 def reference_script(ion, materials, thicknesses, n=0, tally="vaccount", threads=1, seeds_file=None, master=2344,
-                     out=None, primaries_only=False, box=None, start=None, scale=None, potential=None):
+                     out=None, primaries_only=False, box=None, start=None, scale=None, potential=None, sample=None):
     Z, m, E = ion
     lines = ["ion %d %.17g %.17g" % (Z, m, E), "n %d" % n, "threads %d" % threads, "tally %s" % tally,
              "master %d" % master, "primaries_only %d" % int(primaries_only)]
@@ -131,6 +131,8 @@ def reference_script(ion, materials, thicknesses, n=0, tally="vaccount", threads
         lines.append("scale %.17g" % scale)
     if potential is not None:
         lines.append("potential %s" % potential)
+    if sample is not None:
+        lines.append("sample %s" % sample)
     if seeds_file:
         lines.append("seeds %s" % seeds_file)
     if box is not None:
