@@ -14,6 +14,7 @@ Fixtures:
   ref_tally_<tally>_<cfg>.npz records (+ output file content) of TrimRange / TrimPrimaries / TrimRecoils /
                                TrimVacEnergyCount / TrimPhononOut.
   ref_geometry_<sample>.npz    records of the reference in a SampleWire / SampleBurriedWire.
+  ref_options_scale10.npz      records with a length scale of 10 A, per-element Edisp / Elbind and Ef = 5 eV.
   vacancy_count_published.json the reference's published vacancies/ion table
                                (validation/vacancy_count/vacancy_count_comparison.dat).
 """
@@ -147,6 +148,21 @@ def geometries():
                             summary=json.dumps(summary))
 
 
+# run-time options of the path: SimconfType::setLengthScale (positions in units of 10 A), per-element Edisp / Elbind
+# (runmytrim.C:246-250) and the final energy IonBase::_Ef
+OPTION_MATERIAL = {"rho": 8.92, "elements": [{"Z": 29, "m": 63.546, "t": 1.0, "Edisp": 30.0, "Elbind": 2.0}]}
+OPTION_CASE = dict(ion=(29, 63.546, 2.0e4, 5.0), scale=10.0, box=(100.0, 10.0, 10.0), n=96)
+
+
+def options():
+    o = OPTION_CASE
+    seeds = util.distinct_seeds(o["n"], master=404)
+    rec, summary, hist = util.run_reference_cascades(o["ion"], [OPTION_MATERIAL], [o["box"][0]], seeds, box=o["box"],
+                                                     scale=o["scale"])
+    np.savez_compressed(os.path.join(HERE, "ref_options_scale10.npz"), records=rec, seeds=seeds,
+                        vac=hist[:, 1].astype(np.uint64), repl=hist[:, 2].astype(np.uint64), summary=json.dumps(summary))
+
+
 def published():
     src = "/root/reference/validation/vacancy_count/vacancy_count_comparison.dat"
     rows = [l.strip().split(",") for l in open(src)][2:]
@@ -170,5 +186,6 @@ if __name__ == "__main__":
     potentials()
     tallies()
     geometries()
+    options()
     published()
     print("golden fixtures written to", HERE)

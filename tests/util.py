@@ -124,8 +124,8 @@ def run_reference(script, timeout=600):
 
 def reference_script(ion, materials, thicknesses, n=0, tally="vaccount", threads=1, seeds_file=None, master=2344,
                      out=None, primaries_only=False, box=None, start=None, scale=None, potential=None, sample=None):
-    Z, m, E = ion
-    lines = ["ion %d %.17g %.17g" % (Z, m, E), "n %d" % n, "threads %d" % threads, "tally %s" % tally,
+    Z, m, E = ion[:3]
+    lines = ["ion %d %.17g %.17g" % (Z, m, E) + (" %.17g" % ion[3] if len(ion) > 3 else ""), "n %d" % n, "threads %d" % threads, "tally %s" % tally,
              "master %d" % master, "primaries_only %d" % int(primaries_only)]
     if scale is not None:
         lines.append("scale %.17g" % scale)
