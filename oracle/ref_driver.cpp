@@ -15,6 +15,7 @@
 //   seeds <file>              binary uint32[N] per-primary seeds (default: irand() of `master`)
 //   master S                  master seed (runmytrim.C:288)
 //   scale L                   length scale
+//   tmin T / cw C             SimconfType::tmin (default 0.2, as runmytrim) / SimconfType::cw (default 0.001)
 //   tally vaccount|vacenergycount|range|base|primaries|recoils|phonon
 //   primaries_only 0|1
 //   potential universal|moliere|ckr   TrimBase::_potential (trim.h:63-69; default universal)
@@ -119,7 +120,7 @@ struct Job
   unsigned long n = 0;
   unsigned threads = 1;
   unsigned master = 2344;
-  double scale = 1.0;
+  double scale = 1.0, tmin = 0.2, cw = -1.0;
   std::string tally = "vaccount", out, seedfile, potential = "universal", sample = "layers";
   bool primaries_only = false;
   bool have_box = false, have_start = false;
@@ -183,7 +184,9 @@ buildWorker(const Job & job, Worker & w)
 {
   w.simconf = new SimconfType;
   w.simconf->fullTraj = false;
-  w.simconf->tmin = 0.2;
+  w.simconf->tmin = job.tmin;
+  if (job.cw > 0.0)
+    w.simconf->cw = job.cw;
   w.simconf->setLengthScale(job.scale);
   double thickness = 0;
   for (auto & l : job.layers)
@@ -375,6 +378,10 @@ main()
       is >> job.master;
     else if (cmd == "scale")
       is >> job.scale;
+    else if (cmd == "tmin")
+      is >> job.tmin;
+    else if (cmd == "cw")
+      is >> job.cw;
     else if (cmd == "tally")
       is >> job.tally;
     else if (cmd == "primaries_only")

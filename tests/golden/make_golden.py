@@ -15,6 +15,7 @@ Fixtures:
                                TrimVacEnergyCount / TrimPhononOut.
   ref_geometry_<sample>.npz    records of the reference in a SampleWire / SampleBurriedWire.
   ref_options_scale10.npz      records with a length scale of 10 A, per-element Edisp / Elbind and Ef = 5 eV.
+  ref_options_tmin1_cw0p01.npz, ref_options_primaries_only.npz   tmin = 1, cw = 0.01; ThreadedTrimBase::_primaries_only.
   vacancy_count_published.json the reference's published vacancies/ion table
                                (validation/vacancy_count/vacancy_count_comparison.dat).
 """
@@ -163,6 +164,16 @@ def options():
                         vac=hist[:, 1].astype(np.uint64), repl=hist[:, 2].astype(np.uint64), summary=json.dumps(summary))
 
 
+def options2():
+    # SimconfType::tmin / cw (simconf.C:45-47, trim.C:88-94) and ThreadedTrimBase::_primaries_only
+    c = util.CONFIGS["cu_on_cu_10keV"]
+    for key, kw in (("tmin1_cw0p01", dict(tmin=1.0, cw=0.01)), ("primaries_only", dict(primaries_only=True))):
+        seeds = util.distinct_seeds(96, master=505)
+        rec, summary, hist = util.run_reference_cascades(c["ion"], c["materials"], c["thicknesses"], seeds, **kw)
+        np.savez_compressed(os.path.join(HERE, "ref_options_%s.npz" % key), records=rec, seeds=seeds,
+                            vac=hist[:, 1].astype(np.uint64), repl=hist[:, 2].astype(np.uint64), summary=json.dumps(summary))
+
+
 def published():
     src = "/root/reference/validation/vacancy_count/vacancy_count_comparison.dat"
     rows = [l.strip().split(",") for l in open(src)][2:]
@@ -187,5 +198,6 @@ if __name__ == "__main__":
     tallies()
     geometries()
     options()
+    options2()
     published()
     print("golden fixtures written to", HERE)

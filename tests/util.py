@@ -123,7 +123,7 @@ def run_reference(script, timeout=600):
 
 
 def reference_script(ion, materials, thicknesses, n=0, tally="vaccount", threads=1, seeds_file=None, master=2344,
-                     out=None, primaries_only=False, box=None, start=None, scale=None, potential=None, sample=None):
+                     out=None, primaries_only=False, box=None, start=None, scale=None, potential=None, sample=None, tmin=None, cw=None):
     Z, m, E = ion[:3]
     lines = ["ion %d %.17g %.17g" % (Z, m, E) + (" %.17g" % ion[3] if len(ion) > 3 else ""), "n %d" % n, "threads %d" % threads, "tally %s" % tally,
              "master %d" % master, "primaries_only %d" % int(primaries_only)]
@@ -133,6 +133,10 @@ def reference_script(ion, materials, thicknesses, n=0, tally="vaccount", threads
         lines.append("potential %s" % potential)
     if sample is not None:
         lines.append("sample %s" % sample)
+    if tmin is not None:
+        lines.append("tmin %.17g" % tmin)
+    if cw is not None:
+        lines.append("cw %.17g" % cw)
     if seeds_file:
         lines.append("seeds %s" % seeds_file)
     if box is not None:
