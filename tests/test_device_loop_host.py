@@ -349,3 +349,35 @@ def test_mono_variant_equals_fast_variant_on_the_host():
         (ra, va, ca), (rb, vb, cb) = out[0][name], out[1][name]
         assert ra.tobytes() == rb.tobytes(), name
         assert np.array_equal(va, vb) and ca["steps"] == cb["steps"] and ca["vacancies_created"] == cb["vacancies_created"]
+
+
+def test_wire_and_buried_wire_geometry_on_the_host():
+    """SampleWire (CUT boundaries, vacuum outside the cylinder) and SampleBurriedWire (INF boundaries, cover layer,
+    matrix) through the device loop (generic variant: F_GEOM_ANY, F_CUT) against the oracle on the same Philox
+    streams; the oracle's geometry is pinned against the reference in test_oracle_golden.py."""
+    cfg = dict(tally_mask=capi.TALLY_RECORDS)
+    cases = [
+        (capi.GEOM_WIRE, (60.0, 60.0, 1000.0), (capi.BC_CUT, capi.BC_CUT, capi.BC_PBC), [util.CU],
+         dict(pos=(30.0, 18.0, 0.0), direction=(0.0, 0.3, 1.0))),
+        (capi.GEOM_BURIED_WIRE, (100.0, 100.0, 300.0), (capi.BC_INF,) * 3, [util.CU, util.FE],
+         dict(pos=(50.0, 50.0, -200.0), direction=(0.1, 0.0, 1.0))),
+    ]
+    for kind, box, bc, mats, start in cases:
+        with util.OracleEngine(util.ORC_RNG_PHILOX, **cfg) as orc, util.HostSimEngine(**cfg) as hs:
+            for e in (orc, hs):
+                e.set_materials(mats)
+                e.set_geometry(kind, box, bc=bc)
+            ions = capi.make_ions(120, 29, 63.546, 2.0e4, **start)
+            ro = orc.run(ions, seed=13, records=True)
+            rh = hs.run(ions, seed=13, records=True)
+            co, ch = orc.counters(), hs.counters()
+        assert len(set(ro["state"].tolist())) >= 2
+        assert (ro["state"] == rh["state"]).mean() > 0.97
+        same = (ro["vacancies"] == rh["vacancies"]) & (ro["steps"] == rh["steps"]) & (ro["ions"] == rh["ions"])
+        assert same.mean() >= 0.85, same.mean()
+        for k in ("steps", "ions", "left_sample", "lost", "vacancies_created"):
+            assert abs(ch[k] - co[k]) <= 0.02 * co[k] + 2, (kind, k, ch[k], co[k])
+        sel = (ro["primary_steps"] == rh["primary_steps"]) & (ro["state"] == rh["state"])
+        path = np.maximum(np.linalg.norm(ro["pos"] - ions["pos"], axis=1), 1.0)
+        rel = (np.linalg.norm(ro["pos"] - rh["pos"], axis=1) / path)[sel]
+        assert (rel >= TOL).sum() <= max(2, 0.01 * len(rel)) and np.median(rel) < 0.1 * TOL
