@@ -51,6 +51,9 @@ constexpr int kBlock = MTB_BLOCK;
 #ifndef MTB_MIN_BLOCKS_FAST
 #define MTB_MIN_BLOCKS_FAST 7
 #endif
+#ifndef MTB_MIN_BLOCKS_MONO
+#define MTB_MIN_BLOCKS_MONO 7
+#endif
 #ifndef MTB_MIN_BLOCKS_CLUSTERS
 #define MTB_MIN_BLOCKS_CLUSTERS 6
 #endif
@@ -70,7 +73,8 @@ template <class TR>
 constexpr int
 min_blocks()
 {
-  return TR::kF & F_GEOM_ANY ? (TR::kShare ? MTB_MIN_BLOCKS_GENERIC_SHARE : MTB_MIN_BLOCKS_GENERIC)
+  return (TR::kF & F_MONO) && !TR::kShare ? MTB_MIN_BLOCKS_MONO
+         : TR::kF & F_GEOM_ANY ? (TR::kShare ? MTB_MIN_BLOCKS_GENERIC_SHARE : MTB_MIN_BLOCKS_GENERIC)
          : TR::kF & (F_CLUSTERS | F_FOLLOW) ? (TR::kShare ? MTB_MIN_BLOCKS_CLUSTERS_SHARE : MTB_MIN_BLOCKS_CLUSTERS)
                                             : (TR::kShare ? MTB_MIN_BLOCKS_FAST_SHARE : MTB_MIN_BLOCKS_FAST);
 }
