@@ -103,7 +103,7 @@ struct TraitsT
 {
   static constexpr uint32_t kF = F, kTally = TALLY;
   static constexpr bool kEvents = (F & F_EVENTS) != 0, kShare = (F & F_SHARE) != 0, kCustom = (F & F_CUSTOM) != 0;
-  static constexpr bool has(uint32_t f) { return (F & f) != 0; }
+  MTB_HD static constexpr bool has(uint32_t f) { return (F & f) != 0; }
 };
 
 constexpr uint32_t kFeatFast = 0;
