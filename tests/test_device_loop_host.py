@@ -381,3 +381,48 @@ def test_wire_and_buried_wire_geometry_on_the_host():
         path = np.maximum(np.linalg.norm(ro["pos"] - ions["pos"], axis=1), 1.0)
         rel = (np.linalg.norm(ro["pos"] - rh["pos"], axis=1) / path)[sel]
         assert (rel >= TOL).sum() <= max(2, 0.01 * len(rel)) and np.median(rel) < 0.1 * TOL
+
+
+@pytest.mark.parametrize("name,n", [("cu_on_cu_1keV", 4000), ("h_on_fe_100keV", 2500), ("cu_on_cu_10keV", 600)])
+def test_statistics_of_the_host_loop_against_reference_golden(name, n):
+    """CPU twin of the GPU statistical test: the FP32 device loop (host build, Philox streams, azimuth instead of
+    the reference's rejection loop) against per-primary records of the UNMODIFIED reference (tests/golden):
+    two-sample KS on projected range, lateral range, vacancies and electronic loss, means within 4 standard errors."""
+    from scipy import stats
+    gold = np.load(os.path.join(util.GOLDEN, "ref_records_%s.npz" % name))["records"]
+    c = util.CONFIGS[name]
+    with util.HostSimEngine(tally_mask=capi.TALLY_RECORDS) as hs:
+        util.setup_engine(hs, c)
+        rec = hs.run(util.primaries_for(c, n), seed=4242, records=True)
+    for field, getter in (("x", lambda r: r["pos"][:, 0]), ("vacancies", lambda r: r["vacancies"].astype(float)),
+                          ("Eel", lambda r: r["Eel"]),
+                          ("lateral", lambda r: np.hypot(r["pos"][:, 1] - 50.0, r["pos"][:, 2] - 50.0))):
+        a, b = getter(rec), getter(gold)
+        p = stats.ks_2samp(a, b).pvalue
+        assert p > 0.001, (name, field, p)
+        se = np.sqrt(a.var() / len(a) + b.var() / len(b))
+        assert abs(a.mean() - b.mean()) <= 4.0 * se + 1e-12, (name, field, a.mean(), b.mean(), se)
+
+
+@pytest.mark.skipif(not util.have_reference(), reason="oracle/_ref (the compiled reference) is not built")
+@pytest.mark.parametrize("name,n", [("cu_on_cu_1keV", 30000), ("h_on_fe_100keV", 12000)])
+def test_north_star_statistical_criterion_on_the_host_loop(name, n):
+    """The north-star statistical criterion (two-sample KS p > 0.01, means within 1 %) with the FP32 device loop
+    built for the host against the UNMODIFIED reference run here (oracle/_ref, distinct 32-bit seeds, all cores):
+    what a kernel change can be checked against when no GPU is at hand."""
+    from scipy import stats
+    c = util.CONFIGS[name]
+    ref, _, _ = util.run_reference_cascades(c["ion"], c["materials"], c["thicknesses"], util.distinct_seeds(n, master=9),
+                                            threads=os.cpu_count() or 1, box=c.get("box"))
+    with util.HostSimEngine(tally_mask=capi.TALLY_RECORDS) as hs:
+        util.setup_engine(hs, c)
+        rec = hs.run(util.primaries_for(c, n), seed=777, records=True)
+    for field, getter in (("x", lambda r: r["pos"][:, 0]), ("vacancies", lambda r: r["vacancies"].astype(float)),
+                          ("replacements", lambda r: r["replacements"].astype(float)), ("Eel", lambda r: r["Eel"]),
+                          ("steps", lambda r: r["steps"].astype(float)),
+                          ("lateral", lambda r: np.hypot(r["pos"][:, 1] - 50.0, r["pos"][:, 2] - 50.0))):
+        a, b = getter(rec), getter(ref)
+        p = stats.ks_2samp(a, b).pvalue
+        assert p > 0.01, (name, field, p)
+        se = np.sqrt(a.var() / len(a) + b.var() / len(b))
+        assert abs(a.mean() - b.mean()) <= max(0.01 * abs(b.mean()), 4.0 * se), (name, field, a.mean(), b.mean())
