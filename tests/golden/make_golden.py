@@ -15,6 +15,7 @@ Fixtures:
                                TrimVacEnergyCount / TrimPhononOut.
   ref_geometry_<sample>.npz    records of the reference in a SampleWire / SampleBurriedWire.
   ref_options_scale10.npz      records with a length scale of 10 A, per-element Edisp / Elbind and Ef = 5 eV.
+  ref_records_layer_stack.npz  Cu / Fe / W / ZrO2 stack: the layer look-up with different materials.
   ref_options_tmin1_cw0p01.npz, ref_options_primaries_only.npz   tmin = 1, cw = 0.01; ThreadedTrimBase::_primaries_only.
   vacancy_count_published.json the reference's published vacancies/ion table
                                (validation/vacancy_count/vacancy_count_comparison.dat).
@@ -174,6 +175,19 @@ def options2():
                             vac=hist[:, 1].astype(np.uint64), repl=hist[:, 2].astype(np.uint64), summary=json.dumps(summary))
 
 
+# a stack of DIFFERENT materials (sample_layers.C:26-49: linear scan, x < 0 -> first layer, beyond -> last layer)
+STACK_CASE = dict(ion=(29, 63.546, 2.0e4), materials=[util.CU, util.FE, util.W, util.ZRO2],
+                  thicknesses=[30.0, 40.0, 60.0, 500.0], n=128)
+
+
+def stack():
+    o = STACK_CASE
+    seeds = util.distinct_seeds(o["n"], master=606)
+    rec, summary, hist = util.run_reference_cascades(o["ion"], o["materials"], o["thicknesses"], seeds)
+    np.savez_compressed(os.path.join(HERE, "ref_records_layer_stack.npz"), records=rec, seeds=seeds,
+                        vac=hist[:, 1].astype(np.uint64), repl=hist[:, 2].astype(np.uint64), summary=json.dumps(summary))
+
+
 def published():
     src = "/root/reference/validation/vacancy_count/vacancy_count_comparison.dat"
     rows = [l.strip().split(",") for l in open(src)][2:]
@@ -199,5 +213,6 @@ if __name__ == "__main__":
     geometries()
     options()
     options2()
+    stack()
     published()
     print("golden fixtures written to", HERE)

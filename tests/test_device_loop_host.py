@@ -426,3 +426,25 @@ def test_north_star_statistical_criterion_on_the_host_loop(name, n):
         assert p > 0.01, (name, field, p)
         se = np.sqrt(a.var() / len(a) + b.var() / len(b))
         assert abs(a.mean() - b.mean()) <= max(0.01 * abs(b.mean()), 4.0 * se), (name, field, a.mean(), b.mean())
+
+
+def test_stack_of_different_materials_on_the_host():
+    """Layer look-up over DIFFERENT materials (binary search over the cumulative thicknesses; Cu / Fe / W / ZrO2) in
+    the device loop against the oracle, whose look-up is pinned against the reference on the same stack."""
+    from tests.golden.make_golden import STACK_CASE as o
+    cfg = dict(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS)
+    with util.OracleEngine(util.ORC_RNG_PHILOX, **cfg) as orc, util.HostSimEngine(**cfg) as hs:
+        for e in (orc, hs):
+            util.setup_engine(e, o)
+        ions = util.primaries_for(o, 200)
+        ro = orc.run(ions, seed=5, records=True)
+        rh = hs.run(ions, seed=5, records=True)
+        vo, vh = orc.vac_depth()[0], hs.vac_depth()[0]
+    same = (ro["vacancies"] == rh["vacancies"]) & (ro["steps"] == rh["steps"]) & (ro["ions"] == rh["ions"])
+    assert same.mean() >= 0.8, same.mean()
+    sel = ro["primary_steps"] == rh["primary_steps"]
+    path = np.maximum(np.linalg.norm(ro["pos"] - ions["pos"], axis=1), 1.0)
+    rel = (np.linalg.norm(ro["pos"] - rh["pos"], axis=1) / path)[sel]
+    assert sel.mean() >= 0.95 and (rel >= TOL).sum() <= 2 and np.median(rel) < 0.1 * TOL
+    n = max(len(vo), len(vh))
+    assert np.abs(np.pad(vo, (0, n - len(vo))).astype(int) - np.pad(vh, (0, n - len(vh))).astype(int)).sum() <= 0.02 * vo.sum()

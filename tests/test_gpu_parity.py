@@ -58,6 +58,31 @@ def test_trajectories_match_oracle(name, n):
     eng.close()
 
 
+def test_stack_of_different_materials():
+    """Layer look-up over DIFFERENT materials (Cu / Fe / W / ZrO2: the FAST kernel's binary search over the cumulative
+    thicknesses, compound target pick) against the oracle, whose look-up is pinned against the reference on the same
+    stack (tests/test_oracle_golden.py)."""
+    from tests.golden.make_golden import STACK_CASE as o
+    cfg = dict(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS)
+    with capi.Engine(**cfg) as eng, util.OracleEngine(util.ORC_RNG_PHILOX, **cfg) as orc:
+        for e in (eng, orc):
+            util.setup_engine(e, o)
+        ions = util.primaries_for(o, 600)
+        rg = eng.run(ions, seed=5, records=True)
+        ro = orc.run(ions, seed=5, records=True)
+        cg, co = eng.counters(), orc.counters()
+    same = (ro["vacancies"] == rg["vacancies"]) & (ro["steps"] == rg["steps"]) & (ro["ions"] == rg["ions"])
+    assert same.mean() >= 0.8, same.mean()
+    sel = ro["primary_steps"] == rg["primary_steps"]
+    assert sel.mean() >= 0.95
+    path = np.maximum(np.linalg.norm(ro["pos"] - ions["pos"], axis=1), 1.0)
+    rel = (np.linalg.norm(ro["pos"] - rg["pos"], axis=1) / path)[sel]
+    assert (rel >= TOL).sum() <= max(2, 0.005 * len(rel)), ((rel < TOL).mean(), rel.max())
+    assert np.median(rel) < 0.1 * TOL, np.median(rel)
+    for k in ("vacancies_created", "replacements", "steps", "ions"):
+        assert abs(cg[k] - co[k]) <= 0.02 * co[k], k
+
+
 def test_stopping_matches_oracle():
     data = json.load(open(os.path.join(util.GOLDEN, "stopping.json")))
     for name, d in data.items():
