@@ -448,3 +448,19 @@ def test_stack_of_different_materials_on_the_host():
     assert sel.mean() >= 0.95 and (rel >= TOL).sum() <= 2 and np.median(rel) < 0.1 * TOL
     n = max(len(vo), len(vh))
     assert np.abs(np.pad(vo, (0, n - len(vo))).astype(int) - np.pad(vh, (0, n - len(vh))).astype(int)).sum() <= 0.02 * vo.sum()
+
+
+def test_host_loop_against_the_1e6_reference_summary():
+    """The fixture of the GPU suite's 1e6-ion criterion (tests/golden/ref_stats_*_1e6.npz) with a smaller sample of
+    the host build of the loop: KS p > 0.01, means within 1 % (4 standard errors for the noisier observables).
+    The full-size run of the host loop is recorded in profiles/r01_statistics_host_loop_1e6.log."""
+    summary = np.load(os.path.join(util.GOLDEN, "ref_stats_cu_on_cu_10keV_1e6.npz"))
+    c = util.CONFIGS["cu_on_cu_10keV"]
+    n = 8000
+    with util.HostSimEngine(tally_mask=capi.TALLY_RECORDS) as hs:
+        util.setup_engine(hs, c)
+        rec = hs.run(util.primaries_for(c, n), seed=2344, records=True)
+    for name, (mean, ref_mean, D, p) in util.ks_against_summary(rec, summary).items():
+        var = float(summary["m_" + name][1])
+        assert p > 0.01, (name, D, p)
+        assert abs(mean - ref_mean) <= max(0.01 * abs(ref_mean), 4.0 * np.sqrt(var / n)), (name, mean, ref_mean)

@@ -221,3 +221,54 @@ def primaries_for(c, n, seeds=None):
     box = c.get("box")
     wy, wz = (box[1], box[2]) if box else (100.0, 100.0)
     return capi.make_ions(n, Z, m, E, pos=(0.0, wy / 2.0, wz / 2.0), seeds=seeds)
+
+
+# --- north-star statistical criterion against a SUMMARY of a large reference sample -------------------------
+# 1e6 per-primary records of the reference are 72 MB; the committed fixture keeps, per observable, either
+# K quantiles (continuous observables) or the exact histogram (integer observables), plus mean and variance.
+STAT_K = 4096
+STAT_CONTINUOUS = {"projected_range_x": lambda r: r["pos"][:, 0],
+                   "lateral_range": lambda r: np.hypot(r["pos"][:, 1] - 50.0, r["pos"][:, 2] - 50.0),
+                   "electronic_loss_Eel": lambda r: r["Eel"]}
+STAT_INTEGER = {"vacancies_per_ion": lambda r: r["vacancies"], "replacements_per_ion": lambda r: r["replacements"],
+                "collision_steps": lambda r: r["steps"], "ions_followed": lambda r: r["ions"]}
+
+
+def summarize_records(rec):
+    """Summary of per-primary records for ks_against_summary()."""
+    out = {"n": np.array(len(rec))}
+    probs = (np.arange(STAT_K) + 0.5) / STAT_K
+    for name, get in STAT_CONTINUOUS.items():
+        v = np.asarray(get(rec), dtype=np.float64)
+        out["q_" + name] = np.quantile(v, probs)
+        out["m_" + name] = np.array([v.mean(), v.var()])
+    for name, get in STAT_INTEGER.items():
+        v = np.asarray(get(rec), dtype=np.int64)
+        out["h_" + name] = np.bincount(v)
+        out["m_" + name] = np.array([v.mean(), v.var()])
+    return out
+
+
+def ks_against_summary(rec, summary):
+    """{observable: (mean, reference mean, KS D, asymptotic two-sample p)} of records against a summary."""
+    from scipy import stats
+    m = int(summary["n"])
+    n = len(rec)
+    res = {}
+    scale = np.sqrt(n * m / float(n + m))
+    probs = (np.arange(STAT_K) + 0.5) / STAT_K
+    for name, get in STAT_CONTINUOUS.items():
+        v = np.sort(np.asarray(get(rec), dtype=np.float64))
+        F = np.searchsorted(v, summary["q_" + name], side="right") / float(n)
+        D = float(np.abs(F - probs).max())   # resolution 1/(2K) = 1.2e-4, 5 % of the critical D at 1e6 ions
+        res[name] = (v.mean(), float(summary["m_" + name][0]), D, float(stats.distributions.kstwobign.sf(D * scale)))
+    for name, get in STAT_INTEGER.items():
+        h = np.bincount(np.asarray(get(rec), dtype=np.int64))
+        g = np.asarray(summary["h_" + name], dtype=np.float64)
+        L = max(len(h), len(g))
+        ch = np.cumsum(np.pad(h, (0, L - len(h)))) / float(n)
+        cg = np.cumsum(np.pad(g, (0, L - len(g)))) / float(m)
+        D = float(np.abs(ch - cg).max())
+        mean = float((np.arange(len(h)) * h).sum() / n)
+        res[name] = (mean, float(summary["m_" + name][0]), D, float(stats.distributions.kstwobign.sf(D * scale)))
+    return res
