@@ -16,7 +16,8 @@ Fixtures:
   ref_geometry_<sample>.npz    records of the reference in a SampleWire / SampleBurriedWire.
   ref_options_scale10.npz      records with a length scale of 10 A, per-element Edisp / Elbind and Ef = 5 eV.
   ref_records_layer_stack.npz  Cu / Fe / W / ZrO2 stack: the layer look-up with different materials.
-  ref_stats_cu_on_cu_10keV_1e6.npz  quantiles / histograms / means of 1e6 reference cascades (statistical criterion).
+  ref_stats_<cfg>.npz          quantiles / histograms / means of 4e3..1e6 reference cascades per configuration
+                               (statistical criterion; STATISTICS_CASES).
   ref_options_tmin1_cw0p01.npz, ref_options_primaries_only.npz   tmin = 1, cw = 0.01; ThreadedTrimBase::_primaries_only.
   vacancy_count_published.json the reference's published vacancies/ion table
                                (validation/vacancy_count/vacancy_count_comparison.dat).
@@ -189,15 +190,22 @@ def stack():
                         vac=hist[:, 1].astype(np.uint64), repl=hist[:, 2].astype(np.uint64), summary=json.dumps(summary))
 
 
-def statistics_1e6():
-    # the sample of the north-star statistical criterion: 1e6 Cu->Cu 10 keV cascades of the unmodified reference with
-    # distinct 32-bit seeds, summarised (tests/util.py::summarize_records); ~4 min on 8 cores
-    name, n = "cu_on_cu_10keV", 1000000
-    c = util.CONFIGS[name]
-    rec, summary, _ = util.run_reference_cascades(c["ion"], c["materials"], c["thicknesses"], util.distinct_seeds(n, master=1),
-                                                  threads=os.cpu_count() or 1, box=c.get("box"), timeout=3600)
-    np.savez_compressed(os.path.join(HERE, "ref_stats_%s_1e6.npz" % name), summary=json.dumps(summary),
-                        **util.summarize_records(rec))
+# samples of the north-star statistical criterion: cascades of the unmodified reference with distinct 32-bit seeds
+# (SURVEY.md §8c), summarised (tests/util.py::summarize_records).  1e6 Cu->Cu 10 keV cascades take ~4 min on 8 cores.
+STATISTICS_CASES = {"cu_on_cu_10keV": 1000000, "cu_on_cu_1keV": 1000000, "h_on_fe_100keV": 500000,
+                    "he_on_fe_100keV": 100000, "c_on_w_1MeV": 20000, "xe_on_zro2_500keV": 4000}
+
+
+def statistics(only=None):
+    for name, n in STATISTICS_CASES.items():
+        if only and name not in only:
+            continue
+        c = util.CONFIGS[name]
+        rec, summary, _ = util.run_reference_cascades(c["ion"], c["materials"], c["thicknesses"],
+                                                      util.distinct_seeds(n, master=1), threads=os.cpu_count() or 1,
+                                                      box=c.get("box"), timeout=7200)
+        np.savez_compressed(os.path.join(HERE, "ref_stats_%s.npz" % name), summary=json.dumps(summary),
+                            **util.summarize_records(rec))
 
 
 def published():
@@ -226,6 +234,6 @@ if __name__ == "__main__":
     options()
     options2()
     stack()
-    statistics_1e6()
+    statistics()
     published()
     print("golden fixtures written to", HERE)

@@ -451,10 +451,10 @@ def test_stack_of_different_materials_on_the_host():
 
 
 def test_host_loop_against_the_1e6_reference_summary():
-    """The fixture of the GPU suite's 1e6-ion criterion (tests/golden/ref_stats_*_1e6.npz) with a smaller sample of
+    """The fixture of the GPU suite's 1e6-ion criterion (tests/golden/ref_stats_*.npz) with a smaller sample of
     the host build of the loop: KS p > 0.01, means within 1 % (4 standard errors for the noisier observables).
-    The full-size run of the host loop is recorded in profiles/r01_statistics_host_loop_1e6.log."""
-    summary = np.load(os.path.join(util.GOLDEN, "ref_stats_cu_on_cu_10keV_1e6.npz"))
+    The full-size run of the host loop is recorded in profiles/r01_statistics_host_loop_cu_on_cu_10keV.log."""
+    summary = np.load(os.path.join(util.GOLDEN, "ref_stats_cu_on_cu_10keV.npz"))
     c = util.CONFIGS["cu_on_cu_10keV"]
     n = 8000
     with util.HostSimEngine(tally_mask=capi.TALLY_RECORDS) as hs:

@@ -1,9 +1,10 @@
 #!/usr/bin/env python3
-"""North-star statistical criterion WITHOUT a GPU: 1e6 Cu->Cu 10 keV cascades through the host build of the device
-loop (tests/libhostsim.so, same FP32 algorithm and Philox streams as the kernels; all host cores, ~1.5 min on 8)
-against the 1e6-cascade summary of the unmodified reference (tests/golden/ref_stats_cu_on_cu_10keV_1e6.npz).
+"""North-star statistical criterion WITHOUT a GPU: cascades through the host build of the device loop
+(tests/libhostsim.so, same FP32 algorithm and Philox streams as the kernels; all host cores, 1e6 Cu->Cu 10 keV
+cascades take ~1.5 min on 8) against the committed summary of the unmodified reference's cascades for that
+configuration (tests/golden/ref_stats_<workload>.npz, tests/golden/make_golden.py::STATISTICS_CASES).
 
-    python tools/host_statistics.py [--n 1000000] > profiles/r01_statistics_host_loop_1e6.log
+    python tools/host_statistics.py [--workload cu_on_cu_10keV] [--n <as many as the reference sample>]
 """
 import argparse
 import os
@@ -19,15 +20,19 @@ from mytrim_b200 import capi  # noqa: E402
 from tests import util  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=1000000)
+ap.add_argument("--workload", default="cu_on_cu_10keV")
+ap.add_argument("--n", type=int, default=0, help="cascades (default: the size of the reference sample)")
 ap.add_argument("--seed", type=int, default=2344)
 args = ap.parse_args()
+SUMMARY = np.load(os.path.join(util.GOLDEN, "ref_stats_%s.npz" % args.workload))
+if args.n <= 0:
+    args.n = int(SUMMARY["n"])
 W = os.cpu_count() or 1
 PER = (args.n + W - 1) // W
 
 
 def work(i):
-    c = util.CONFIGS["cu_on_cu_10keV"]
+    c = util.CONFIGS[args.workload]
     n = min(PER, args.n - i * PER)
     with util.HostSimEngine(tally_mask=capi.TALLY_RECORDS) as hs:
         util.setup_engine(hs, c)
@@ -38,9 +43,9 @@ if __name__ == "__main__":
     t0 = time.time()
     with Pool(W) as pool:
         rec = np.concatenate(pool.map(work, [i for i in range(W) if i * PER < args.n]))
-    print("host build of the device loop: %d Cu->Cu 10 keV cascades on %d cores in %.0f s (seed %d, global indices 0..n-1: "
-          "the same streams the GPU suite's 1e6-ion test uses)" % (len(rec), W, time.time() - t0, args.seed))
-    summary = np.load(os.path.join(util.GOLDEN, "ref_stats_cu_on_cu_10keV_1e6.npz"))
+    print("host build of the device loop: %d %s cascades on %d cores in %.0f s (seed %d, global indices 0..n-1: "
+          "the same streams the GPU suite's statistical test uses)" % (len(rec), args.workload, W, time.time() - t0, args.seed))
+    summary = SUMMARY
     print("reference: %d cascades of the unmodified library, distinct 32-bit seeds" % int(summary["n"]))
     ok = True
     for k, (a, b, D, p) in util.ks_against_summary(rec, summary).items():
