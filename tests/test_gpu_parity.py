@@ -239,7 +239,8 @@ def test_north_star_statistical_criterion(name):
     summary = np.load(os.path.join(util.GOLDEN, "ref_stats_%s.npz" % name))
     c = util.CONFIGS[name]
     n = int(summary["n"])
-    with capi.Engine(tally_mask=capi.TALLY_RECORDS) as eng:
+    # TrimVacCount tallies + records: the north-star kernels (MONO for the single-element samples, FAST for the ZrO2 stack)
+    with capi.Engine(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS) as eng:
         util.setup_engine(eng, c)
         rec = eng.run(util.primaries_for(c, n), seed=2344, records=True)
     res = util.ks_against_summary(rec, summary)
