@@ -117,10 +117,12 @@ def potentials():
 # the other in-tree tally classes: (reference tally name, configuration, primaries)
 TALLY_CASES = {"range": ("cu_on_cu_1keV", 192), "primaries": ("cu_on_cu_10keV", 64), "recoils": ("cu_on_cu_10keV", 64),
                "vacenergycount": ("c_on_w_1MeV", 12), "phonon": ("cu_on_cu_1keV", 128)}
+# apps/mytrim_layers.C: TrimRecoils on the 50-layer ZrO2 stack of inputs/samplelayers_zro2_multilayer.in
+TALLY_CASES_EXTRA = {"recoils": ("xe_on_zro2_500keV", 8)}
 
 
 def tallies():
-    for tally, (name, n) in TALLY_CASES.items():
+    for tally, (name, n) in list(TALLY_CASES.items()) + list(TALLY_CASES_EXTRA.items()):
         c = util.CONFIGS[name]
         seeds = util.distinct_seeds(n, master=101)
         rec, summary, hist = util.run_reference_cascades(c["ion"], c["materials"], c["thicknesses"], seeds,
