@@ -7,6 +7,7 @@ container (oracle/_ref, see oracle/Makefile).  Run from the repo root:
 Fixtures:
   uo2_out.{Erec,clcoor,dist}  `MYTRIM_SEED=39172 mytrim_uo2 out 10 0.1 1` (tests/uo2/test.sh);
                                byte-identical to the reference's tests/uo2/gold/ files.
+  uo2_out2.{Erec,clcoor,dist} `MYTRIM_SEED=4711 mytrim_uo2 out2 6 0.5 2` (22 bubbles, two fission events).
   rng_mt19937.txt             SimconfType::drand()/irand() sequences (simconf.h:52-53).
   stopping.json               MaterialBase::getrstop + average() known answers.
   ref_records_<cfg>.npz       per-primary records of the reference for fixed 32-bit seeds.
@@ -46,6 +47,12 @@ def uo2():
                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         for ext in ("Erec", "clcoor", "dist"):
             shutil.copy(os.path.join(tmp, "out." + ext), os.path.join(HERE, "uo2_out." + ext))
+        # a second experiment of the same app: smaller, denser bubbles (22 clusters), two fission events
+        env["MYTRIM_SEED"] = "4711"
+        subprocess.run([util.REF_UO2, "out2", "6", "0.5", "2"], cwd=tmp, env=env, check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        for ext in ("Erec", "clcoor", "dist"):
+            shutil.copy(os.path.join(tmp, "out2." + ext), os.path.join(HERE, "uo2_out2." + ext))
 
 
 def rng():
