@@ -543,10 +543,16 @@ launch_grid(const mtb_handle * h, Variant v, uint64_t n, bool * share)
   return (unsigned)(*share ? (uint64_t)h->sm_count * h->bps[v][1] : std::min<uint64_t>(max_blocks, (n + kBlock - 1) / kBlock));
 }
 
+int drain(mtb_handle * h);
+
 int
 launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, const mtb_ion * beam, uint64_t seed,
                  uint64_t first_index, bool want_records)
 {
+  // a previous asynchronous launch may still owe its deferred primaries (their list is re-used below)
+  if (h->deferred_pending)
+    if (int rc = drain(h))
+      return rc;
   LaunchParams & P = h->P;
   P.primaries = primaries_dev;
   if (beam)
@@ -657,6 +663,18 @@ sync_and_check(mtb_handle * h)
   MTB_CUDA(cudaMemcpy(&err, h->d_u64.p + CNT_ERROR, sizeof(err), cudaMemcpyDeviceToHost));
   if (err)
     return fail(MTB_ESTACK, "recoil stack overflow in " + std::to_string(err) + " collision(s)");
+  return MTB_OK;
+}
+
+// Everything an asynchronous mtb_launch_resident left behind — the launch of the deferred (class-less) primaries and
+// the stack-overflow check — has to happen before tallies are read, reduced or reset and before the next launch
+// re-uses the deferral list.
+int
+drain(mtb_handle * h)
+{
+  if (h->timing_pending || h->deferred_pending)
+    return sync_and_check(h);
+  MTB_CUDA(cudaStreamSynchronize(h->stream));
   return MTB_OK;
 }
 } // namespace
@@ -955,6 +973,8 @@ mtb_reset_tallies(mtb_handle * h)
 {
   if (int rc = ensure_ready(h))
     return rc;
+  if (int rc = drain(h))
+    return rc;
   MTB_CUDA(cudaMemsetAsync(h->d_u64.p, 0, h->u64_size * sizeof(unsigned long long), h->stream));
   MTB_CUDA(cudaMemsetAsync(h->d_f64.p, 0, 2 * sizeof(double), h->stream));
   MTB_CUDA(cudaStreamSynchronize(h->stream));
@@ -970,7 +990,8 @@ mtb_get_counters(mtb_handle * h, mtb_counters * out)
     return fail(MTB_EINVAL, "null argument");
   unsigned long long c[CNT_COUNT];
   double f[2];
-  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  if (int rc = drain(h))
+    return rc;
   MTB_CUDA(cudaMemcpy(c, h->d_u64.p, sizeof(c), cudaMemcpyDeviceToHost));
   MTB_CUDA(cudaMemcpy(f, h->d_f64.p, sizeof(f), cudaMemcpyDeviceToHost));
   out->vacancies_created = c[CNT_VAC];
@@ -1007,7 +1028,8 @@ mtb_get_vac_depth(mtb_handle * h, uint64_t * vac, uint64_t * repl, size_t capaci
     return rc;
   const size_t B = (size_t)h->P.hist_bins;
   std::vector<unsigned long long> buf(2 * B);
-  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  if (int rc = drain(h))
+    return rc;
   MTB_CUDA(cudaMemcpy(buf.data(), h->d_u64.p + off_vac(h->P), 2 * B * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   size_t last = 0;
   for (size_t i = 0; i < B; ++i)
@@ -1034,7 +1056,8 @@ mtb_get_vac_energy(mtb_handle * h, uint64_t * evac, size_t rows, size_t bins)
     return fail(MTB_EINVAL, "MTB_TALLY_VAC_ENERGY not enabled");
   const size_t B = (size_t)h->P.hist_bins, R = (size_t)h->P.evac_rows;
   std::vector<unsigned long long> buf(R * B);
-  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  if (int rc = drain(h))
+    return rc;
   MTB_CUDA(cudaMemcpy(buf.data(), h->d_u64.p + off_evac(h->P), R * B * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   std::memset(evac, 0, rows * bins * sizeof(uint64_t));
   for (size_t r = 0; r < std::min(R, rows); ++r)
@@ -1050,7 +1073,8 @@ mtb_get_vacmap(mtb_handle * h, uint64_t * vmap)
     return rc;
   if (!vmap)
     return fail(MTB_EINVAL, "null argument");
-  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  if (int rc = drain(h))
+    return rc;
   MTB_CUDA(cudaMemcpy(vmap, h->d_u64.p + off_vmap(h->P), MTB_VMAP_NX * MTB_VMAP_NY * 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   return MTB_OK;
 }
@@ -1063,7 +1087,8 @@ mtb_get_range_list(mtb_handle * h, float * x, int32_t * Z, size_t capacity, size
   if (!(h->host.cfg.tally_mask & MTB_TALLY_RANGE))
     return fail(MTB_EINVAL, "MTB_TALLY_RANGE not enabled");
   unsigned long long cnt = 0;
-  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  if (int rc = drain(h))
+    return rc;
   MTB_CUDA(cudaMemcpy(&cnt, h->d_u64.p + CNT_RANGE_N, sizeof(cnt), cudaMemcpyDeviceToHost));
   if (n)
     *n = (size_t)cnt;
@@ -1092,7 +1117,8 @@ mtb_get_ion_log(mtb_handle * h, mtb_ion_log * out, size_t capacity, size_t * n)
   if (!(h->host.cfg.tally_mask & MTB_TALLY_IONLOG))
     return fail(MTB_EINVAL, "MTB_TALLY_IONLOG not enabled");
   unsigned long long cnt = 0;
-  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  if (int rc = drain(h))
+    return rc;
   MTB_CUDA(cudaMemcpy(&cnt, h->d_u64.p + CNT_IONLOG_N, sizeof(cnt), cudaMemcpyDeviceToHost));
   const size_t have = (size_t)std::min<unsigned long long>(cnt, h->P.ionlog_cap);
   std::vector<mtb_ion_log> raw(have);
@@ -1133,6 +1159,8 @@ mtb_clear_lists(mtb_handle * h)
 {
   if (int rc = ensure_ready(h))
     return rc;
+  if (int rc = drain(h))
+    return rc;
   MTB_CUDA(cudaMemsetAsync(h->d_u64.p + CNT_IONLOG_N, 0, sizeof(unsigned long long), h->stream));
   MTB_CUDA(cudaMemsetAsync(h->d_u64.p + CNT_RANGE_N, 0, sizeof(unsigned long long), h->stream));
   MTB_CUDA(cudaStreamSynchronize(h->stream));
@@ -1144,7 +1172,8 @@ mtb_tally_device_views(mtb_handle * h, void ** u64_dev, size_t * n_u64, void ** 
 {
   if (int rc = ensure_ready(h))
     return rc;
-  MTB_CUDA(cudaStreamSynchronize(h->stream));
+  if (int rc = drain(h))
+    return rc;
   if (u64_dev)
     *u64_dev = h->d_u64.p;
   if (n_u64)
@@ -1332,7 +1361,8 @@ mtb_allreduce(mtb_handle ** handles, int n_handles)
       return rc;
     if (handles[i]->u64_size != handles[0]->u64_size)
       return fail(MTB_EINVAL, "handles have different tally layouts");
-    MTB_CUDA(cudaStreamSynchronize(handles[i]->stream));
+    if (int rc = drain(handles[i]))
+      return rc;
   }
   if (!g_nccl.load())
     return fail(MTB_ENCCL, "libnccl.so.2 not found");

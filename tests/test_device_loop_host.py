@@ -464,3 +464,25 @@ def test_host_loop_against_the_1e6_reference_summary():
         var = float(summary["m_" + name][1])
         assert p > 0.01, (name, D, p)
         assert abs(mean - ref_mean) <= max(0.01 * abs(ref_mean), 4.0 * np.sqrt(var / n)), (name, mean, ref_mean)
+
+
+@pytest.mark.parametrize("name,n", [(c, max(1, k // 4)) for c, k in __import__("tests.parity_cases", fromlist=["x"]).PER_ION_CASES])
+def test_per_ion_parity_fp32_replay_against_fp64_oracle(name, n):
+    """CPU twin of tests/test_gpu_parity.py::test_per_ion_parity_with_fp32_host_replay: EVERY followed ion of the FP32
+    replay of the device loop against the FP64 oracle on the same Philox streams (ion log joined by ion id).
+    Measured in this container (full case sizes, 1.0e6 ions in total): every ion has its twin with identical integer
+    fields; 35 ions end more than 1e-5 (of the distance from the source) away from their twin."""
+    from tests import parity_cases
+    cfg = dict(tally_mask=capi.TALLY_IONLOG | capi.TALLY_RECORDS, ionlog_capacity=1 << 21)
+    with util.HostSimEngine(**cfg) as hs, util.OracleEngine(util.ORC_RNG_PHILOX, **cfg) as orc:
+        ions = parity_cases.setup_case(hs, name, n)
+        parity_cases.setup_case(orc, name, n)
+        rh = hs.run(ions, seed=2344, records=True)
+        ro = orc.run(ions, seed=2344, records=True)
+        s = util.compare_ion_logs(hs.ion_log(1 << 21), orc.ion_log(1 << 21), ions)
+        r = util.compare_records(rh, ro, ions)
+    assert s["n_test"] == s["n_replay"] == s["joined"] > 0, s
+    assert s["ints_equal"] >= 0.9999 * s["joined"], s
+    assert s["pos_outliers"] <= 2e-4 * s["joined"] + 2 and s["energy_outliers"] == 0, s
+    assert s["median_rel_pos"] < 0.1 * TOL, s
+    assert r["cascades_identical"] >= 0.9 * r["n"] and r["pos_outliers"] == 0, r

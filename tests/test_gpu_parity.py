@@ -31,14 +31,14 @@ def test_trajectories_match_oracle(name, n):
     rg = eng.run(ions, seed=2344, records=True)
     ro = orc.run(ions, seed=2344, records=True)
     same = (ro["vacancies"] == rg["vacancies"]) & (ro["steps"] == rg["steps"]) & (ro["ions"] == rg["ions"])
-    assert same.mean() >= 0.8, same.mean()
+    # fp32-vs-fp64 branch flips (Newton iteration count at |q/r| == 0.001, threshold tests) are rare but real.
+    # Measured on the B200 (round 2): >= 99.9 % of the cascades identical in every configuration
+    assert n - same.sum() <= max_flipped_cascades(n, int(ro["steps"].sum())), same.mean()
     path = np.maximum(np.linalg.norm(ro["pos"] - ions["pos"], axis=1), 1.0)
     sel = ro["primary_steps"] == rg["primary_steps"]
-    assert sel.mean() >= 0.95
+    assert sel.mean() >= 0.995 - 1.0 / n
     rel = (np.linalg.norm(ro["pos"] - rg["pos"], axis=1) / path)[sel]
-    # fp32-vs-fp64 branch flips (Newton iteration count at |q/r| == 0.001, threshold tests) are
-    # rare but real: require 99.5 % of the primaries inside the tolerance and a tiny median
-    assert (rel >= TOL).sum() <= max(2, 0.005 * len(rel)), ((rel < TOL).mean(), rel.max())
+    assert (rel >= TOL).sum() <= max(1, 0.002 * len(rel)), ((rel < TOL).mean(), rel.max())
     assert np.median(rel) < 0.1 * TOL, np.median(rel)
     bad = np.abs(ro["Eel"][same] - rg["Eel"][same]) > TOL * ro["Eel"][same]
     assert bad.sum() <= max(2, 0.005 * same.sum()), bad.sum()
@@ -58,6 +58,84 @@ def test_trajectories_match_oracle(name, n):
     eng.close()
 
 
+# Measured levels (B200, round 2; the numbers printed by tools/per_ion_parity.py, profiles/r02_per_ion_parity.log) are
+# written next to the thresholds below.
+PER_ION_MIN_IDENTICAL = 0.9999     # ions whose integer fields (primary, Z, generation, tag, final state) are bit-identical
+PER_ION_MAX_POS_OUTLIERS = 5e-4    # share of ions whose birth/death point is > TOL (of the distance from the source) off
+# Measured (profiles/r02_per_ion_parity.log, 841 243 ions over the ten cases): against the FP32 replay 841 243 ions joined,
+# 841 243 with identical integer fields (100 %), 112 position outliers (1.3e-4; worst case 26 of 62 579 = 4.2e-4 on the
+# 10 MeV Xe tracks), 3 energy outliers; against the FP64 oracle 100 % identical, 54 position outliers (6.4e-5).
+FLIPS_PER_STEP = 3e-6              # threshold tests that flip between two arithmetics, per collision step (measured ~1e-6)
+
+
+def max_flipped_cascades(n, steps_total):
+    """Cascades that may differ in an integer field: FLIPS_PER_STEP x steps per cascade of them (+1 for small n)."""
+    return max(0.01, FLIPS_PER_STEP * steps_total / n) * n + 1
+
+
+
+@pytest.mark.parametrize("name,n", __import__("tests.parity_cases", fromlist=["x"]).PER_ION_CASES)
+def test_per_ion_parity_with_fp32_host_replay(name, n):
+    """The deterministic criterion as north_star states it: per-ION trajectories of the CUDA kernels against a CPU
+    replay that uses the same Philox streams — tests/libhostsim.so, the device lane loop compiled for the host in
+    FP32 (same source, same ion ids).  Every followed ion is compared through MTB_TALLY_IONLOG (birth and death
+    position and energy, primary, Z, generation, tag, final state), joined by the scheduling-independent ion id; the
+    FP64 oracle is held to the same level.  The two FP32 paths still differ in the last bits (MUFU.EX2/LG2/RCP/RSQ
+    on the device, libm on the host; FMA contraction), so a threshold test can flip; the allowances are the
+    measured levels, not slack."""
+    from tests import parity_cases
+    cfg = dict(tally_mask=capi.TALLY_IONLOG | capi.TALLY_RECORDS, ionlog_capacity=1 << 21)
+    with capi.Engine(**cfg) as eng, util.HostSimEngine(**cfg) as hs, util.OracleEngine(util.ORC_RNG_PHILOX, **cfg) as orc:
+        ions = parity_cases.setup_case(eng, name, n)
+        parity_cases.setup_case(hs, name, n)
+        parity_cases.setup_case(orc, name, n)
+        rg = eng.run(ions, seed=2344, records=True)
+        rh = hs.run(ions, seed=2344, records=True)
+        ro = orc.run(ions, seed=2344, records=True)
+        lg = eng.ion_log(1 << 21)
+        sh = util.compare_ion_logs(lg, hs.ion_log(1 << 21), ions)
+        so = util.compare_ion_logs(lg, orc.ion_log(1 << 21), ions)
+    for partner, s, r in (("fp32 replay", sh, util.compare_records(rg, rh, ions)),
+                          ("fp64 oracle", so, util.compare_records(rg, ro, ions))):
+        print("%s vs %s: %s %s" % (name, partner, s, r))
+        assert s["joined"] >= PER_ION_MIN_IDENTICAL * max(s["n_test"], s["n_replay"]), (partner, s)
+        assert s["ints_equal"] >= PER_ION_MIN_IDENTICAL * max(s["n_test"], s["n_replay"]), (partner, s)
+        assert s["pos_outliers"] <= PER_ION_MAX_POS_OUTLIERS * s["joined"] + 2, (partner, s)
+        assert s["energy_outliers"] <= 3, (partner, s)
+        assert s["median_rel_pos"] < 0.1 * TOL, (partner, s)
+        assert r["n"] - r["cascades_identical"] <= max_flipped_cascades(r["n"], int(rg["steps"].sum())), (partner, r)
+        assert r["pos_outliers"] <= 0.002 * r["n"] + 1, (partner, r)
+
+
+@pytest.mark.parametrize("name,n", [("cu_on_cu_10keV", 4000), ("h_on_fe_100keV", 4000), ("c_on_w_1MeV", 64),
+                                    ("xe_on_zro2_500keV", 24), ("cu_on_cu_150keV", 64), ("xe_on_uo2_10MeV", 2)])
+def test_north_star_kernels_against_fp32_host_replay(name, n):
+    """The ion log is produced by the option-carrying variants; the kernels bench.py times (MONO for the single-element
+    samples, FAST for the compounds: TrimVacCount tallies + records only) are compared per cascade with the same variant
+    of the FP32 host replay: integer record fields, end point of the primary, electronic loss, and the depth histograms."""
+    cfg = dict(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS)
+    with capi.Engine(**cfg) as eng, util.HostSimEngine(**cfg) as hs:
+        c = util.setup_engine(eng, name)
+        util.setup_engine(hs, name)
+        ions = util.primaries_for(c, n)
+        rg = eng.run(ions, seed=2344, records=True)
+        rh = hs.run(ions, seed=2344, records=True)
+        r = util.compare_records(rg, rh, ions)
+        cg, ch = eng.counters(), hs.counters()
+        vg, rpg = eng.vac_depth()
+        vh, rph = hs.vac_depth()
+    print("%s MONO/FAST vs fp32 replay: %s" % (name, r))
+    assert n - r["cascades_identical"] <= max_flipped_cascades(n, cg["steps"]), r
+    assert r["pos_outliers"] <= 0.002 * n + 1 and r["eel_outliers"] <= 0.002 * n + 1 and r["median_rel_pos"] < 0.1 * TOL, r
+    for k in ("vacancies_created", "replacements", "steps", "ions"):
+        assert abs(cg[k] - ch[k]) <= 2e-3 * ch[k], (k, cg[k], ch[k])
+    m = max(len(vg), len(vh))
+    d = np.abs(np.pad(vg, (0, m - len(vg))).astype(int) - np.pad(vh, (0, m - len(vh))).astype(int)).sum()
+    # the depth bin is the truncated x coordinate: an end point within the position error (~1e-3 A at 1e4 A depth) of
+    # an integer lands in the neighbouring bin (measured 82 of 49 527 on the 10 MeV Xe tracks)
+    assert d <= (2.0 * (1.0 - r["cascades_identical"] / n) + 5e-3) * vh.sum() + 5, d
+
+
 def test_stack_of_different_materials():
     """Layer look-up over DIFFERENT materials (Cu / Fe / W / ZrO2: the FAST kernel's binary search over the cumulative
     thicknesses, compound target pick) against the oracle, whose look-up is pinned against the reference on the same
@@ -72,12 +150,12 @@ def test_stack_of_different_materials():
         ro = orc.run(ions, seed=5, records=True)
         cg, co = eng.counters(), orc.counters()
     same = (ro["vacancies"] == rg["vacancies"]) & (ro["steps"] == rg["steps"]) & (ro["ions"] == rg["ions"])
-    assert same.mean() >= 0.8, same.mean()
+    assert len(ions) - same.sum() <= max_flipped_cascades(len(ions), int(ro["steps"].sum())), same.mean()
     sel = ro["primary_steps"] == rg["primary_steps"]
-    assert sel.mean() >= 0.95
+    assert sel.mean() >= 0.99
     path = np.maximum(np.linalg.norm(ro["pos"] - ions["pos"], axis=1), 1.0)
     rel = (np.linalg.norm(ro["pos"] - rg["pos"], axis=1) / path)[sel]
-    assert (rel >= TOL).sum() <= max(2, 0.005 * len(rel)), ((rel < TOL).mean(), rel.max())
+    assert (rel >= TOL).sum() <= max(1, 0.002 * len(rel)), ((rel < TOL).mean(), rel.max())
     assert np.median(rel) < 0.1 * TOL, np.median(rel)
     for k in ("vacancies_created", "replacements", "steps", "ions"):
         assert abs(cg[k] - co[k]) <= 0.02 * co[k], k

@@ -200,6 +200,12 @@ CONFIGS = {
     "he_on_fe_100keV": dict(ion=(2, 4.003, 1.0e5), materials=[FE], thicknesses=[100000.0]),
     "c_on_w_1MeV": dict(ion=(6, 12.0, 1.0e6), materials=[W], thicknesses=[10000.0]),
     "xe_on_uo2_80MeV": dict(ion=(54, 132.0, 8.0e7), materials=[UO2], thicknesses=[1.0e7]),
+    # the file-energy / long-cascade configurations of SURVEY.md §8d (validation/cu_on_cu/cu_on_cu.json:3-16,
+    # validation/h_on_fe, tests/json/xe_on_uo2.json)
+    "cu_on_cu_150keV": dict(ion=(29, 63.546, 1.5e5), materials=[CU], thicknesses=[1000.0]),
+    "h_on_fe_1MeV": dict(ion=(1, 1.008, 1.0e6), materials=[FE], thicknesses=[1.0e6]),
+    "xe_on_uo2_10MeV": dict(ion=(54, 131.904, 1.0e7), thicknesses=[100000.0], materials=[
+        {"rho": 10.97, "elements": [{"Z": 92, "m": 238.03, "t": 1.0}, {"Z": 8, "m": 15.999, "t": 2.0}]}]),
     "xe_on_zro2_500keV": dict(ion=(54, 131.0, 5.0e5), materials=[ZRO2] * 50, thicknesses=[10.0] * 50,
                               box=(500.0, 100.0, 100.0)),
 }
@@ -272,3 +278,49 @@ def ks_against_summary(rec, summary):
         mean = float((np.arange(len(h)) * h).sum() / n)
         res[name] = (mean, float(summary["m_" + name][0]), D, float(stats.distributions.kstwobign.sf(D * scale)))
     return res
+
+
+# --- deterministic criterion, per ION (north_star: "per-ion trajectories match, within 1e-5 relative FP tolerance, a
+# CPU replay that uses the same Philox stream") -------------------------------------------------------------------
+def compare_ion_logs(a, b, primaries, first_index=0, tol=1e-5):
+    """Joins two ion logs (MTB_TALLY_IONLOG: one entry per followed ion with its birth and death state) by the
+    scheduling-independent ion id and compares EVERY ion: integer fields (primary, Z, generation, tag, final state)
+    bit for bit; birth and death position relative to the distance from the primary's source point (the scale of
+    the coordinates the FP32 arithmetic carried); birth and final energy relative to the primary's energy and,
+    separately, to the ion's own energy.  `a` is the path under test, `b` the replay.  Returns the counts."""
+    assert len(np.unique(a["uid"])) == len(a) and len(np.unique(b["uid"])) == len(b), "ion ids collide"
+    common, xa, xb = np.intersect1d(a["uid"], b["uid"], return_indices=True)
+    A, B = a[xa], b[xb]
+    ints = np.ones(len(A), dtype=bool)
+    for f in ("primary", "Z", "gen", "tag", "state"):
+        ints &= A[f] == B[f]
+    src = primaries[(B["primary"] - first_index).astype(np.int64)]
+    scale = np.maximum(np.linalg.norm(B["pos1"] - src["pos"], axis=1), 1.0)
+    d0 = np.linalg.norm(A["pos0"] - B["pos0"], axis=1) / scale
+    d1 = np.linalg.norm(A["pos1"] - B["pos1"], axis=1) / scale
+    e0 = np.abs(A["E0"] - B["E0"])
+    e1 = np.abs(A["E1"] - B["E1"])
+    pos_ok = (d0 < tol) & (d1 < tol)
+    e_prim_ok = (e0 < tol * src["E"]) & (e1 < tol * src["E"])
+    e_own_ok = e0 <= tol * B["E0"]
+    return dict(n_test=len(a), n_replay=len(b), joined=len(common), ints_equal=int(ints.sum()),
+                pos_outliers=int((ints & ~pos_ok).sum()), energy_outliers=int((ints & ~e_prim_ok).sum()),
+                own_energy_outliers=int((ints & ~e_own_ok).sum()),
+                all_ok=int((ints & pos_ok & e_prim_ok).sum()),
+                median_rel_pos=float(np.median(d1[ints])) if ints.any() else 0.0,
+                max_rel_pos=float(np.maximum(d0, d1)[ints].max()) if ints.any() else 0.0)
+
+
+def compare_records(ra, rb, primaries, tol=1e-5):
+    """Per-primary records of two runs: cascades whose integer fields all agree, and among the primaries with the
+    same number of collisions the ones whose end point differs by more than tol of the distance travelled."""
+    ints = np.ones(len(ra), dtype=bool)
+    for f in ("vacancies", "replacements", "steps", "ions", "state", "primary_steps"):
+        ints &= ra[f] == rb[f]
+    sel = ra["primary_steps"] == rb["primary_steps"]
+    scale = np.maximum(np.linalg.norm(rb["pos"] - primaries["pos"], axis=1), 1.0)
+    rel = np.linalg.norm(ra["pos"] - rb["pos"], axis=1) / scale
+    eel = np.abs(ra["Eel"] - rb["Eel"]) > tol * np.maximum(rb["Eel"], 1e-300)
+    return dict(n=len(ra), cascades_identical=int(ints.sum()), same_primary_steps=int(sel.sum()),
+                pos_outliers=int((sel & (rel >= tol)).sum()), eel_outliers=int((ints & eel).sum()),
+                median_rel_pos=float(np.median(rel[sel])) if sel.any() else 0.0)
