@@ -387,6 +387,9 @@ protected:
   virtual void deviceHooks(DeviceHooks & h) const;
   /// Called by trimBatch() after the device tallies have been updated.
   virtual void collectDeviceTallies() {}
+  /// Called when the batch engine was (re)created: its tallies restart at zero, so subclasses forget what they
+  /// had already merged from the previous engine.
+  virtual void resetDeviceBaselines() {}
 
   SimconfType * _simconf;
   SampleBase * _sample;
@@ -403,9 +406,22 @@ protected:
   bool ensureEngine(bool batch);
   std::string _error;
 
+public:
+  /// The engines snapshot SimconfType (tmin, tau, cw, length scale), _potential, the sample's materials and
+  /// geometry and the hook description.  Every trim()/trimBatch() call compares a fingerprint of those with the
+  /// snapshot and rebuilds the engine when something changed (the reference reads them on every call);
+  /// invalidateEngine() forces the rebuild.
+  void invalidateEngine();
+
 private:
+  // two engines: the batch engine keeps the device tallies of trimBatch() while trim() calls (single-ion event
+  // mode, no tallies) come and go on their own handle
   mtb_handle * _engine;
-  bool _engine_batch;
+  mtb_handle * _engine_single;
+  unsigned long long _engine_fp, _engine_single_fp;
+  unsigned long long configFingerprint(bool batch, const mtb_config & cfg, const std::vector<mtb_material> & mats,
+                                       const std::vector<mtb_element> & els, const mtb_geometry & g,
+                                       const std::vector<double> & storage) const;
   std::vector<mtb_event> _events;
   unsigned long long _seen_vac, _seen_steps;
   double _seen_eel, _seen_enuc;
@@ -551,6 +567,7 @@ protected:
   virtual void writeOutput();
   virtual void deviceHooks(MyTRIM_NS::DeviceHooks & h) const;
   virtual void collectDeviceTallies();
+  virtual void resetDeviceBaselines() { _dev_vac.clear(); _dev_repl.clear(); }
 
 private:
   std::vector<unsigned int> _vac_bin, _repl_bin;
@@ -568,6 +585,7 @@ protected:
   virtual void writeOutput();
   virtual void deviceHooks(MyTRIM_NS::DeviceHooks & h) const;
   virtual void collectDeviceTallies();
+  virtual void resetDeviceBaselines() { _dev_evac.clear(); }
 
 private:
   std::vector<std::vector<unsigned int>> _evac_bin, _dev_evac;
@@ -586,6 +604,7 @@ protected:
   virtual void writeOutput();
   virtual void deviceHooks(MyTRIM_NS::DeviceHooks & h) const;
   virtual void collectDeviceTallies();
+  virtual void resetDeviceBaselines() { _dev_seen = 0; }
 
 private:
   std::vector<std::vector<Real>> _range;

@@ -725,7 +725,8 @@ sampleClusters::describe(mtb_geometry & g, std::vector<double> & storage) const
 TrimBase::TrimBase(SimconfType * sc, SampleBase * sample)
   : _potential(UNIVERSAL), _simconf(sc), _sample(sample), _pka(nullptr), _recoil(nullptr), _material(nullptr),
     _element(nullptr), recoil_queue_ptr(nullptr), terminate(false), _ls(0), _dee(0), _den(0), _base_name("mytrim"),
-    _engine(nullptr), _engine_batch(false), _seen_vac(0), _seen_steps(0), _seen_eel(0), _seen_enuc(0)
+    _engine(nullptr), _engine_single(nullptr), _engine_fp(0), _engine_single_fp(0), _seen_vac(0), _seen_steps(0),
+    _seen_eel(0), _seen_enuc(0)
 {
 }
 
@@ -733,6 +734,45 @@ TrimBase::~TrimBase()
 {
   if (_engine)
     mtb_destroy(_engine);
+  if (_engine_single)
+    mtb_destroy(_engine_single);
+}
+
+void
+TrimBase::invalidateEngine()
+{
+  _engine_fp = _engine_single_fp = 0;
+}
+
+namespace
+{
+inline void
+fnv(unsigned long long & h, const void * p, size_t n)
+{
+  const unsigned char * b = static_cast<const unsigned char *>(p);
+  for (size_t i = 0; i < n; ++i)
+    h = (h ^ b[i]) * 1099511628211ull;
+}
+} // namespace
+
+unsigned long long
+TrimBase::configFingerprint(bool batch, const mtb_config & cfg, const std::vector<mtb_material> & mats,
+                            const std::vector<mtb_element> & els, const mtb_geometry & g,
+                            const std::vector<double> & storage) const
+{
+  unsigned long long h = 1469598103934665603ull ^ (batch ? 1u : 0u);
+  fnv(h, &cfg, sizeof(cfg));
+  if (!mats.empty())
+    fnv(h, mats.data(), mats.size() * sizeof(mtb_material));
+  if (!els.empty())
+    fnv(h, els.data(), els.size() * sizeof(mtb_element));
+  mtb_geometry gg = g; // the pointers address `storage`, whose content is hashed instead
+  gg.layer_thickness = nullptr;
+  gg.cluster_xyzr = nullptr;
+  fnv(h, &gg, sizeof(gg));
+  if (!storage.empty())
+    fnv(h, storage.data(), storage.size() * sizeof(double));
+  return h ? h : 1ull;
 }
 
 bool
@@ -767,13 +807,11 @@ TrimBase::engine()
 bool
 TrimBase::ensureEngine(bool batch)
 {
-  if (_engine && _engine_batch == batch)
-    return true;
-  if (_engine)
-    mtb_destroy(_engine);
-  _engine = nullptr;
+  mtb_handle *& eng = batch ? _engine : _engine_single;
+  unsigned long long & eng_fp = batch ? _engine_fp : _engine_single_fp;
 
   mtb_config cfg;
+  std::memset(&cfg, 0, sizeof(cfg)); // padding bytes are part of the fingerprint
   mtb_default_config(&cfg);
   cfg.tmin = _simconf->tmin;
   cfg.tau = _simconf->tau;
@@ -800,13 +838,6 @@ TrimBase::ensureEngine(bool batch)
     cfg.hist_bins = h.hist_bins;
     cfg.ionlog_capacity = h.ionlog_capacity;
   }
-  if (mtb_create(&cfg, &_engine) != MTB_OK)
-  {
-    _error = mtb_last_error();
-    _engine = nullptr;
-    return false;
-  }
-  pushTables(_engine, _simconf);
 
   std::vector<mtb_material> mats;
   std::vector<mtb_element> els;
@@ -823,24 +854,46 @@ TrimBase::ensureEngine(bool batch)
   }
   std::vector<double> storage;
   mtb_geometry g;
+  std::memset(&g, 0, sizeof(g));
   if (!_sample->describe(g, storage))
   {
     _error = "this SampleBase subclass has a host-only lookupMaterial(): the device needs describe()";
-    mtb_destroy(_engine);
-    _engine = nullptr;
     return false;
   }
-  if (mtb_set_materials(_engine, (int)mats.size(), mats.data(), (int)els.size(), els.data()) != MTB_OK ||
-      mtb_set_geometry(_engine, &g) != MTB_OK)
+
+  // the reference reads SimconfType, _potential, the materials and the sample on every trim() call: rebuild the
+  // engine when any of them changed since the snapshot
+  const unsigned long long fp = configFingerprint(batch, cfg, mats, els, g, storage);
+  if (eng && eng_fp == fp)
+    return true;
+  if (eng)
+    mtb_destroy(eng);
+  eng = nullptr;
+  eng_fp = 0;
+  if (batch)
+  {
+    // a new batch engine starts its tallies at zero
+    _seen_vac = _seen_steps = 0;
+    _seen_eel = _seen_enuc = 0.0;
+    resetDeviceBaselines();
+  }
+
+  if (mtb_create(&cfg, &eng) != MTB_OK)
   {
     _error = mtb_last_error();
-    mtb_destroy(_engine);
-    _engine = nullptr;
+    eng = nullptr;
     return false;
   }
-  _engine_batch = batch;
-  _seen_vac = _seen_steps = 0;
-  _seen_eel = _seen_enuc = 0.0;
+  pushTables(eng, _simconf);
+  if (mtb_set_materials(eng, (int)mats.size(), mats.data(), (int)els.size(), els.data()) != MTB_OK ||
+      mtb_set_geometry(eng, &g) != MTB_OK)
+  {
+    _error = mtb_last_error();
+    mtb_destroy(eng);
+    eng = nullptr;
+    return false;
+  }
+  eng_fp = fp;
   return true;
 }
 
@@ -889,7 +942,7 @@ TrimBase::trim(IonBase * pka, std::queue<IonBase *> & recoils)
   for (;;)
   {
     mtb_ion work = ion;
-    const int rc = mtb_trim_one(_engine, &work, _simconf->philoxKey(), uid, &final_state, _events.data(),
+    const int rc = mtb_trim_one(_engine_single, &work, _simconf->philoxKey(), uid, &final_state, _events.data(),
                                 _events.size(), &n);
     if (rc == MTB_ECAPACITY)
     {

@@ -89,6 +89,67 @@ main()
               n, sc.vacancies_created, sc.EelTotal, hist_vac, hist_repl, xsum / n, trim.vacancies().size(),
               rec[0].vacancies, rec[0].pos[0]);
 
+  // --- 1b. trim() and trimBatch() alternating on the SAME object: the batch engine and its merged tallies survive a
+  // single-ion call (two handles), and a configuration change between calls rebuilds the engine ---
+  {
+    std::queue<IonBase *> q;
+    IonBase * one = new IonBase(29, 63.546, 1.0e4);
+    one->_gen = 0;
+    one->_dir = Point(1, 0, 0);
+    one->_pos = Point(0, 50, 50);
+    sample.averages(one);
+    const int vac_before_single = sc.vacancies_created;
+    trim.trim(one, q);
+    const int single_vac = sc.vacancies_created - vac_before_single; // host hook of TrimVacCount ran
+    while (!q.empty())
+    {
+      delete q.front();
+      q.pop();
+    }
+    delete one;
+    std::vector<IonBase *> prim2;
+    for (int i = 0; i < n; ++i)
+    {
+      IonBase * p = new IonBase(29, 63.546, 1.0e4);
+      p->_gen = 0;
+      p->_dir = Point(1, 0, 0);
+      p->_pos = Point(0, 50, 50);
+      prim2.push_back(p);
+    }
+    if (!trim.trimBatch(prim2))
+    {
+      std::fprintf(stderr, "second trimBatch failed: %s\n", trim.lastError().c_str());
+      return 1;
+    }
+    unsigned long hv2 = 0;
+    for (unsigned v : trim.vacancies())
+      hv2 += v;
+    // a changed option must reach the device: tmin 0.2 -> 5 lengthens the free flights, fewer collisions
+    const int vac_mid = sc.vacancies_created;
+    sc.tmin = 5.0;
+    std::vector<IonBase *> prim3;
+    for (int i = 0; i < n; ++i)
+    {
+      IonBase * p = new IonBase(29, 63.546, 1.0e4);
+      p->_gen = 0;
+      p->_dir = Point(1, 0, 0);
+      p->_pos = Point(0, 50, 50);
+      prim3.push_back(p);
+    }
+    if (!trim.trimBatch(prim3))
+    {
+      std::fprintf(stderr, "third trimBatch failed: %s\n", trim.lastError().c_str());
+      return 1;
+    }
+    unsigned long hv3 = 0;
+    for (unsigned v : trim.vacancies())
+      hv3 += v;
+    sc.tmin = 0.2;
+    std::printf(" \"alternate\": {\"single_vac\": %d, \"hist_vac_after_second\": %lu, \"vacancies_after_second\": %d, "
+                "\"hist_vac_after_third\": %lu, \"vacancies_third\": %d},\n",
+                single_vac, hv2, vac_mid, hv3, sc.vacancies_created - vac_mid);
+  }
+
   // --- 2. the reference's per-ion loop with a user subclass: trim() + host hooks ---
   SimconfType sc2;
   sc2.seed(77);

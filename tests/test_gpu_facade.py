@@ -40,6 +40,14 @@ def test_facade_batch_and_user_subclass():
     assert abs(b["hist_repl"] - repl.sum()) <= 0.002 * repl.sum()
     assert abs(b["mean_x"] - rec["pos"][:, 0].mean()) < 1e-3 * rec["pos"][:, 0].mean()
     assert b["rec0_vac"] == rec["vacancies"][0] and abs(b["rec0_x"] - rec["pos"][0, 0]) < 1e-4
+    # 1b. trim() between two trimBatch() calls on the same object: merged tallies keep growing (no baseline underflow),
+    # and a changed SimconfType option rebuilds the engine
+    a = res["alternate"]
+    assert 0 <= a["single_vac"] < 400
+    assert abs(a["hist_vac_after_second"] - 2 * b["hist_vac"]) <= 0.03 * 2 * b["hist_vac"] + a["single_vac"]
+    assert abs(a["vacancies_after_second"] - 2 * b["vacancies"]) <= 0.03 * 2 * b["vacancies"] + a["single_vac"]
+    assert a["hist_vac_after_third"] > a["hist_vac_after_second"]
+    assert abs(a["vacancies_third"] - b["vacancies"]) > 0.02 * b["vacancies"]   # tmin = 5 changes the physics
     # 2. per-ion trim() with host hooks: statistically the same physics (different stream ids)
     s = res["single"]
     n = s["n"]
