@@ -4,14 +4,21 @@
 // writes basename.clcoor (bubble coordinates), basename.Erec (energy, generation, MD tag of every Xe
 // recoil) and basename.dist (displacement of every Xe recoil from the centre of its bubble of origin).
 //
-// Difference from the reference driver: all 2*Nev fragments are generated first (host mt19937, same
-// inverse-CDF sampling) and followed in ONE batch on the GPU; the per-ion pre/post analysis of
-// mytrim_uo2.C:281-338 runs afterwards on the engine's ion log.
+// Difference from the reference driver: the fragments are generated in chunks of events (host mt19937, same
+// inverse-CDF sampling) and every chunk is followed in ONE batch on a GPU; the per-ion pre/post analysis of
+// mytrim_uo2.C:281-338 runs afterwards on the engine's ion log.  MYTRIM_GPUS=<n> deals the chunks over n GPUs
+// (one host thread each); the output files are written in event order and do not depend on n.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
+#include <deque>
 #include <iostream>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "mytrim/simconf.h"
@@ -116,20 +123,148 @@ main(int argc, char * argv[])
   FILE * erec = std::fopen(ename, "wt");
   FILE * rdist = std::fopen(dname, "wt");
 
-  // The ion log holds a birth and a death entry per Xe ion; events are processed in chunks so that
-  // it stays bounded however many events are requested.
+  // Events are processed in chunks (the ion log holds a birth and a death entry per Xe ion: it stays bounded
+  // however many events are requested).  The chunks are dealt round-robin over the GPUs: the main thread draws
+  // the fragments of chunk after chunk from the run's RNG (the source stream is sequential), one worker thread
+  // per GPU follows them, and the output lines are written in event order — so the files do not depend on the
+  // number of GPUs (Philox stream id of a fragment = its global index; the log is sorted by fragment and ion id).
   const int chunk_events = std::getenv("MYTRIM_UO2_CHUNK") ? std::max(1, std::atoi(std::getenv("MYTRIM_UO2_CHUNK"))) : 32768;
-  TrimXeLog trim(simconf, sample, 1ull << 22);
+  int ngpu = std::getenv("MYTRIM_GPUS") ? std::max(1, std::atoi(std::getenv("MYTRIM_GPUS"))) : 1;
+  ngpu = std::min(ngpu, std::max(1, mtb_device_count()));
+  const int n_chunks = (Nev + chunk_events - 1) / chunk_events;
+
+  struct Chunk
+  {
+    std::vector<IonBase *> primaries;
+    uint64_t first_stream = 0;
+    std::string erec, dist;
+    bool done = false;
+  };
+  struct Device
+  {
+    std::unique_ptr<SimconfType> simconf;
+    std::unique_ptr<TrimXeLog> trim;
+    std::deque<int> todo;
+    double kernel_ms = 0.0;
+    std::string error;
+  };
+  std::vector<Chunk> chunks(n_chunks);
+  std::vector<Device> devices(ngpu);
+  for (int d = 0; d < ngpu; ++d)
+  {
+    devices[d].simconf.reset(new SimconfType);
+    devices[d].simconf->seed(seed < 0 ? -seed : seed); // same Philox key on every device
+    devices[d].simconf->device = d;
+    devices[d].trim.reset(new TrimXeLog(devices[d].simconf.get(), sample, 1ull << 22));
+  }
+  std::mutex mtx;
+  std::condition_variable cv;
+  bool no_more = false, failed = false;
+
+  auto worker = [&](int d) {
+    Device & dev = devices[d];
+    std::vector<mtb_ion_log> log;
+    char line[256];
+    for (;;)
+    {
+      int c;
+      {
+        std::unique_lock<std::mutex> lk(mtx);
+        cv.wait(lk, [&] { return !dev.todo.empty() || no_more || failed; });
+        if (failed || dev.todo.empty())
+          return;
+        c = dev.todo.front();
+        dev.todo.pop_front();
+      }
+      Chunk & ch = chunks[c];
+      dev.simconf->setStreamId(ch.first_stream);
+      bool ok = dev.trim->trimBatch(ch.primaries);
+      if (!ok)
+        dev.error = dev.trim->lastError();
+      size_t n = 0;
+      if (ok)
+      {
+        float ms = 0.f;
+        if (mtb_last_kernel_ms(dev.trim->engine(), &ms) == MTB_OK)
+          dev.kernel_ms += ms;
+        mtb_get_ion_log(dev.trim->engine(), nullptr, 0, &n);
+        log.resize(n);
+        if (n && mtb_get_ion_log(dev.trim->engine(), log.data(), n, &n) != MTB_OK)
+        {
+          ok = false;
+          dev.error = mtb_last_error();
+        }
+        mtb_clear_lists(dev.trim->engine());
+      }
+      for (auto * p : ch.primaries)
+        delete p;
+      ch.primaries.clear();
+      if (ok)
+      {
+        // the device appends log entries in scheduling order: sort by fragment, then ion id
+        std::sort(log.begin(), log.end(), [](const mtb_ion_log & a, const mtb_ion_log & b) {
+          return a.primary != b.primary ? a.primary < b.primary : a.uid < b.uid;
+        });
+        for (const auto & l : log)
+        {
+          // mark ions born in the MD energy gap (mytrim_uo2.C:285-287)
+          const int md = (l.E0 > 200 && l.E0 < 12000) ? 1 : 0;
+          if (l.gen > 0)
+          {
+            std::snprintf(line, sizeof(line), "%f\t%d\t%d\n", l.E0, l.gen, md);
+            ch.erec += line;
+          }
+          if (l.tag >= 0)
+          {
+            // displacement from the centre of the bubble of origin, minimum image (mytrim_uo2.C:296-337)
+            Real d2 = 0.0;
+            for (int i = 0; i < 3; ++i)
+            {
+              Real dif = sample->c[i][l.tag] - l.pos0[i];
+              if (sample->bc[i] == SampleBase::PBC)
+                dif -= std::round(dif / sample->w[i]) * sample->w[i];
+              const Real centre = l.pos0[i] + dif;
+              d2 += (centre - l.pos1[i]) * (centre - l.pos1[i]);
+            }
+            std::snprintf(line, sizeof(line), "%f %d %f %f %f\n", std::sqrt(d2), md, l.pos1[0], l.pos1[1], l.pos1[2]);
+            ch.dist += line;
+          }
+        }
+      }
+      {
+        std::lock_guard<std::mutex> lk(mtx);
+        ch.done = true;
+        if (!ok)
+          failed = true;
+      }
+      cv.notify_all();
+    }
+  };
+  std::vector<std::thread> threads;
+  for (int d = 0; d < ngpu; ++d)
+    threads.emplace_back(worker, d);
+
   MassInverter mass;
   EnergyInverter energy;
   Real Efiss = 0.0;
-  std::vector<mtb_ion_log> log;
-  double kernel_ms = 0.0; // device time of the transport launches (reported when MYTRIM_TIMING is set)
   unsigned long long n_primaries = 0;
-  for (int first = 0; first < Nev; first += chunk_events)
+  int next_to_write = 0;
+  auto flush_done = [&](std::unique_lock<std::mutex> &) {
+    while (next_to_write < n_chunks && chunks[next_to_write].done)
+    {
+      Chunk & ch = chunks[next_to_write++];
+      std::fputs(ch.erec.c_str(), erec);
+      std::fputs(ch.dist.c_str(), rdist);
+      std::string().swap(ch.erec);
+      std::string().swap(ch.dist);
+    }
+  };
+  for (int c = 0; c < n_chunks && !failed; ++c)
   {
+    const int first = c * chunk_events;
+    Chunk & ch = chunks[c];
+    ch.first_stream = 2ull * (uint64_t)first;
     // fission fragment pairs (mytrim_uo2.C:226-266)
-    std::vector<IonBase *> primaries;
     for (int n = first; n < std::min(Nev, first + chunk_events); ++n)
     {
       const Real A1 = mass.x(simconf->drand());
@@ -161,70 +296,65 @@ main(int argc, char * argv[])
       ff2->_m = A2;
       ff2->_E = E2 * 1.0e6;
       ff2->setEf();
-      primaries.push_back(ff1);
-      primaries.push_back(ff2);
+      ch.primaries.push_back(ff1);
+      ch.primaries.push_back(ff2);
       Efiss += ff1->_E + ff2->_E;
     }
-
-    if (!trim.trimBatch(primaries))
+    n_primaries += ch.primaries.size();
     {
-      std::cerr << "ERROR: " << trim.lastError() << std::endl;
-      return 1;
+      // at most two chunks in flight per GPU: the fragments of 1e8 primaries never exist at the same time
+      std::unique_lock<std::mutex> lk(mtx);
+      cv.wait(lk, [&] {
+        flush_done(lk);
+        return failed || c - next_to_write < 2 * ngpu;
+      });
+      devices[c % ngpu].todo.push_back(c);
     }
-    {
-      float ms = 0.f;
-      if (mtb_last_kernel_ms(trim.engine(), &ms) == MTB_OK)
-        kernel_ms += ms;
-      n_primaries += primaries.size();
-    }
-    for (auto * p : primaries)
-      delete p;
-
-    size_t n = 0;
-    mtb_get_ion_log(trim.engine(), nullptr, 0, &n);
-    log.resize(n);
-    if (n && mtb_get_ion_log(trim.engine(), log.data(), n, &n) != MTB_OK)
-    {
-      std::cerr << "ERROR: " << mtb_last_error() << std::endl;
-      return 1;
-    }
-    mtb_clear_lists(trim.engine());
-
-    for (const auto & l : log)
-    {
-      // mark ions born in the MD energy gap (mytrim_uo2.C:285-287)
-      const int md = (l.E0 > 200 && l.E0 < 12000) ? 1 : 0;
-      if (l.gen > 0)
-        std::fprintf(erec, "%f\t%d\t%d\n", l.E0, l.gen, md);
-      if (l.tag >= 0)
-      {
-        // displacement from the centre of the bubble of origin, minimum image (mytrim_uo2.C:296-337)
-        Real d2 = 0.0;
-        for (int i = 0; i < 3; ++i)
-        {
-          Real dif = sample->c[i][l.tag] - l.pos0[i];
-          if (sample->bc[i] == SampleBase::PBC)
-            dif -= std::round(dif / sample->w[i]) * sample->w[i];
-          const Real centre = l.pos0[i] + dif;
-          d2 += (centre - l.pos1[i]) * (centre - l.pos1[i]);
-        }
-        std::fprintf(rdist, "%f %d %f %f %f\n", std::sqrt(d2), md, l.pos1[0], l.pos1[1], l.pos1[2]);
-      }
-    }
+    cv.notify_all();
   }
+  {
+    std::unique_lock<std::mutex> lk(mtx);
+    no_more = true;
+    cv.notify_all();
+    cv.wait(lk, [&] {
+      flush_done(lk);
+      return failed || next_to_write == n_chunks;
+    });
+  }
+  cv.notify_all();
+  for (auto & t : threads)
+    t.join();
   std::fclose(erec);
   std::fclose(rdist);
-
-  if (std::getenv("MYTRIM_TIMING"))
+  if (failed)
   {
-    mtb_counters cnt;
-    if (mtb_get_counters(trim.engine(), &cnt) == MTB_OK && kernel_ms > 0.0)
-      std::fprintf(stderr,
-                   "{\"workload\": \"uo2_fission\", \"primaries\": %llu, \"collision_steps\": %llu, \"ions\": %llu, "
-                   "\"kernel_ms\": %.3f, \"primaries_per_s\": %.4g, \"collision_steps_per_s\": %.4g}\n",
-                   n_primaries, (unsigned long long)cnt.steps, (unsigned long long)cnt.ions, kernel_ms,
-                   n_primaries / (kernel_ms * 1e-3), cnt.steps / (kernel_ms * 1e-3));
+    for (auto & dev : devices)
+      if (!dev.error.empty())
+        std::cerr << "ERROR: " << dev.error << std::endl;
+    return 1;
   }
+
+  // join the per-GPU totals (the analogue of threadJoin)
+  double kernel_ms = 0.0; // slowest GPU: the devices run concurrently
+  unsigned long long steps = 0, ions = 0;
+  for (auto & dev : devices)
+  {
+    simconf->EelTotal += dev.simconf->EelTotal;
+    simconf->EnucTotal += dev.simconf->EnucTotal;
+    simconf->vacancies_created += dev.simconf->vacancies_created;
+    kernel_ms = std::max(kernel_ms, dev.kernel_ms);
+    mtb_counters cnt;
+    if (dev.trim->engine() && mtb_get_counters(dev.trim->engine(), &cnt) == MTB_OK)
+    {
+      steps += cnt.steps;
+      ions += cnt.ions;
+    }
+  }
+  if (std::getenv("MYTRIM_TIMING") && kernel_ms > 0.0)
+    std::fprintf(stderr,
+                 "{\"workload\": \"uo2_fission\", \"gpus\": %d, \"primaries\": %llu, \"collision_steps\": %llu, "
+                 "\"ions\": %llu, \"kernel_ms\": %.3f, \"primaries_per_s\": %.4g, \"collision_steps_per_s\": %.4g}\n",
+                 ngpu, n_primaries, steps, ions, kernel_ms, n_primaries / (kernel_ms * 1e-3), steps / (kernel_ms * 1e-3));
 
   // energy accounting of the whole run (the reference prints it per event, mytrim_uo2.C:345-349)
   std::cout << simconf->EelTotal << std::endl;

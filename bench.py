@@ -1,20 +1,22 @@
 #!/usr/bin/env python3
-"""bench.py — full ion cascades per second on the north-star workload.
+"""bench.py — full ion cascades per second.
 
-Workload (BASELINE.json / SURVEY.md §8d config 1): Cu (Z=29, m=63.546) ions at 10 keV into a
-1000 A Cu layer (rho 8.92), full recoil cascades (follow ALL), TrimVacCount tallies.  A "step" is
-one batch of `--primaries` cascades per GPU through the transport kernel.
+Headline workload (BASELINE.json / SURVEY.md §8d config 1): Cu (Z=29, m=63.546) ions at 10 keV into a
+1000 A Cu layer (rho 8.92), full recoil cascades (follow ALL), TrimVacCount tallies.  A "step" is one batch
+of `--primaries` cascades per GPU through the transport kernel.  `--workload` times one of the other
+BASELINE.json configurations instead (h_on_fe_100keV, he_on_fe_100keV, c_on_w_1MeV, xe_on_zro2_500keV,
+uo2_fission); the default run also measures every one of them once per GPU and reports them under
+"configs" (the headline metric and config do not change).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-value   = cascades/s with the primaries already resident in HBM (device time of the K launches,
-          CUDA events on the launching stream, max over ranks, plus the per-step tally all-reduce
-          when N > 1)
-e2e     = the same metric through mtb_run() with HOST buffers: every step copies its primaries
-          host->device (pinned memory) and reads the tallies back.
-The reference arm (--impl reference) times the UNMODIFIED reference library (oracle/_ref) on all
-host cores on a bounded sample of the same workload.
+value   = cascades/s with the primaries already resident in HBM (device time of the K launches, CUDA events on
+          the launching stream, max over ranks, plus the ONE tally join of the job when N > 1)
+e2e     = the same metric through mtb_run() with HOST buffers: every step copies its primaries host->device
+          (pinned memory) and reads the tallies back; the tally join over the ranks is inside the clock.
+The reference arm (--impl reference) times the UNMODIFIED reference library (oracle/_ref) on all host cores on a
+bounded sample of the same workload.
 """
 import argparse
 import ctypes
@@ -30,9 +32,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 FLOP_PER_STEP = 930.0  # FP32-equivalent flops per collision step, SURVEY.md §8d
-WORKLOAD = "cu_on_cu_10keV"
-WORKLOAD_DESC = "Cu->Cu 10 keV, 1000 A Cu layer, full cascades, TrimVacCount tallies (validation/cu_on_cu)"
+HEADLINE = "cu_on_cu_10keV"
 MASTER_SEED = 2344
+FP32_LANES = 148 * 128  # FP32 lanes of a B200: 148 SMs x 4 sub-partitions x 32
 
 
 class ClockSampler:
@@ -89,15 +91,48 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def reference_cascades_per_s(n, threads, timeout=900):
+# ---------------------------------------------------------------------------------------------------------
+# reference arm: the unmodified reference library on the host cores
+# ---------------------------------------------------------------------------------------------------------
+REF_TALLY = {1: "vaccount", 2: "vacenergycount"}
+
+
+def reference_cascades_per_s(workload, n, threads, timeout=900):
     """Times oracle/_ref/ref_driver (the unmodified reference library, runmytrim-equivalent set-up)."""
+    from mytrim_b200 import workloads
     from tests import util
-    c = util.CONFIGS[WORKLOAD]
-    lines = util.reference_script(c["ion"], c["materials"], c["thicknesses"], n=n, tally="vaccount",
-                                  threads=threads, master=MASTER_SEED)
+    c = workloads.CONFIGS[workload]
+    tally = REF_TALLY.get(workloads.BENCH_WORKLOADS[workload]["tally"], "vaccount")
+    lines = util.reference_script(c["ion"], c["materials"], c["thicknesses"], n=n, tally=tally,
+                                  threads=threads, master=MASTER_SEED, box=c.get("box"))
     lines.append("run")
     out = util.run_reference("\n".join(lines) + "\n", timeout=timeout)
     return json.loads(out[-1])
+
+
+def reference_uo2_primaries_per_s(events_per_proc, procs, timeout=900):
+    """The reference's own apps/mytrim_uo2.C (oracle/_ref/mytrim_uo2, single-threaded by design): one process per
+    core, each with its own seed and `events_per_proc` fission events of the gold geometry (r = 10, Cbf = 0.1)."""
+    import tempfile
+    from tests import util
+    t0 = time.perf_counter()
+    with tempfile.TemporaryDirectory() as tmp:
+        ps = []
+        for k in range(procs):
+            env = util.ref_env()
+            env["MYTRIM_SEED"] = str(39172 + k)
+            ps.append(subprocess.Popen([util.REF_UO2, os.path.join(tmp, "o%d" % k), "10", "0.1", str(events_per_proc)],
+                                       env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+        for p in ps:
+            p.wait(timeout=timeout)
+    dt = time.perf_counter() - t0
+    n = 2 * events_per_proc * procs
+    return {"n": n, "seconds": dt, "cascades_per_s": n / dt, "steps": 0}
+
+
+# reference cascades per core and step (a step of the reference arm is ~2-20 s of wall time on all cores)
+REF_PER_CORE = {"cu_on_cu_10keV": 400, "h_on_fe_100keV": 2000, "he_on_fe_100keV": 100, "c_on_w_1MeV": 8,
+                "xe_on_zro2_500keV": 2, "uo2_fission": 2}
 
 
 def run_reference_arm(args):
@@ -106,30 +141,39 @@ def run_reference_arm(args):
         return 0
     import __graft_entry__ as g
     g.build_test_infrastructure()
+    from mytrim_b200 import workloads
     from tests import util
     cores = os.cpu_count() or 1
-    if not util.have_reference():
+    name = args.workload
+    if not util.have_reference() or (name == "uo2_fission" and not os.path.exists(util.REF_UO2)):
         emit({"impl": "reference", "unavailable": "oracle/_ref was not built (reference tree absent)"})
         return 0
-    per_step = args.ref_cascades if args.ref_cascades else 400 * cores
+    per_step = args.ref_cascades if args.ref_cascades else REF_PER_CORE[name] * cores
+
+    def once(n):
+        if name == "uo2_fission":
+            return reference_uo2_primaries_per_s(max(1, n // (2 * cores)), cores)
+        return reference_cascades_per_s(name, n, cores)
+
     for _ in range(args.warmup):
-        reference_cascades_per_s(max(per_step // 8, cores), cores)
+        once(max(per_step // 8, cores))
     t_total, n_total, steps_total = 0.0, 0, 0
     for _ in range(args.steps):
-        r = reference_cascades_per_s(per_step, cores)
+        r = once(per_step)
         t_total += r["seconds"]
         n_total += r["n"]
         steps_total += r["steps"]
     value = n_total / t_total
-    sample = "%d steps x %d Cu->Cu 10 keV cascades on %d threads (unmodified reference, TrimVacCount)" % (
-        args.steps, per_step, cores)
+    sample = "%d steps x %d cascades of %s on %d threads (unmodified reference)" % (args.steps, n_total // args.steps,
+                                                                                 name, cores)
     line = {
         "impl": "reference", "metric": "cascades_per_s", "value": value, "unit": "cascades/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "description": WORKLOAD_DESC, "primaries_per_step": per_step},
-        "collision_steps_per_s": steps_total / t_total,
+        "config": {"workload": name, "description": workloads.BENCH_WORKLOADS[name]["desc"],
+                   "primaries_per_step": n_total // args.steps},
+        "collision_steps_per_s": steps_total / t_total if steps_total else None,
         "cpu_baseline": {"value": value, "unit": "cascades/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "cascades/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -157,6 +201,27 @@ def emit(line):
     os.write(_RESULT_FD if _RESULT_FD is not None else 1, (json.dumps(line) + "\n").encode())
 
 
+def load_profile_json(name):
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return None
+
+
+def c_abi_allreduce_check(timeout=120):
+    """mtb_allreduce (the C-ABI tally join of a single-process multi-GPU job, dlopen'd NCCL) on GPUs 0 and 1 in a
+    child process with a hard time limit: two handles, primaries sharded by global index, reduced tallies equal
+    one GPU running everything."""
+    try:
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "allreduce_check.py")], capture_output=True,
+                           text=True, timeout=timeout)
+    except subprocess.TimeoutExpired:
+        return "timeout"
+    last = p.stdout.strip().split("\n")[-1] if p.stdout.strip() else ""
+    return last if p.returncode == 0 and last.startswith("ok") else "failed: " + (last or p.stderr.strip()[-200:])
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -164,11 +229,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--primaries", type=int, default=1 << 23, help="cascades per GPU per step")
+    ap.add_argument("--workload", default=HEADLINE, help="BASELINE.json configuration to time")
+    ap.add_argument("--primaries", type=int, default=0, help="cascades per GPU per step (default: per workload)")
     ap.add_argument("--ref-cascades", type=int, default=0, help="cascades per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the one-launch-per-configuration sweep")
     args = ap.parse_args()
 
+    from mytrim_b200 import workloads
+    if args.workload not in workloads.BENCH_WORKLOADS:
+        raise SystemExit("unknown workload %s (have: %s)" % (args.workload, ", ".join(workloads.BENCH_WORKLOADS)))
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -192,35 +262,47 @@ def main():
         dist.barrier()
 
     from mytrim_b200 import capi
-    from tests import util
+    from mytrim_b200 import dist as mdist
+    lib = capi.load_library()
 
-    B = args.primaries
-    c = util.CONFIGS[WORKLOAD]
-    eng = capi.Engine(tally_mask=capi.TALLY_VAC_DEPTH, device=local_rank)
-    util.setup_engine(eng, c)
-
-    # primaries in pinned host memory (the e2e arm copies them every step)
-    pinned = torch.empty(B * capi.ION_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
-    ions = np.frombuffer(pinned.numpy(), dtype=capi.ION_DTYPE)
-    ions[:] = util.primaries_for(c, B)
+    name = args.workload
+    wl = workloads.BENCH_WORKLOADS[name]
+    B = args.primaries if args.primaries else wl["primaries"]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def make_engine(wname, n):
+        w = workloads.BENCH_WORKLOADS[wname]
+        kw = dict(tally_mask=w["tally"], device=local_rank)
+        if w["tally"] & capi.TALLY_IONLOG:
+            kw.update(ionlog_z=w.get("ionlog_z", 0), ionlog_capacity=max(1 << 20, 64 * n))
+        e = capi.Engine(**kw)
+        # primaries in pinned host memory (the e2e arm copies them every step); every rank its own share of the
+        # fission events, the beams are identical primaries
+        host = torch.empty(n * capi.ION_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        arr = np.frombuffer(host.numpy(), dtype=capi.ION_DTYPE)
+        arr[:] = workloads.setup_workload(e, wname, n, first_primary=rank * n)
+        return e, host
+
+    eng, pinned = make_engine(name, B)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # tallies as torch tensors over the engine's device memory (for the NCCL reduction)
-    from mytrim_b200 import dist as mdist
+    # the tally join: ONE all-gather of the engine's tally blocks + a local reduction (mytrim_b200/dist.py),
+    # the analogue of runmytrim's threadJoin
+    eng.upload_primaries_ptr(B, pinned.data_ptr())
+    eng.synchronize()
     t_u64, t_f64 = mdist.tally_tensors(eng)
+    reducer = mdist.TallyReducer(t_u64, t_f64)
 
-    def reduce_tallies():
-        """Only the additive tallies cross NVLink (mytrim_b200/dist.py): the analogue of threadJoin."""
+    def reduce_tallies(write_back=True):
         if world == 1:
             return 0.0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        mdist.reduce_tallies(t_u64, t_f64)
+        reducer.reduce(write_back=write_back)
         e1.record()
         e1.synchronize()
         return e0.elapsed_time(e1)
@@ -228,37 +310,50 @@ def main():
     def first_index(step):
         return (step * world + rank) * B
 
+    has_log = bool(wl["tally"] & capi.TALLY_IONLOG)
+
     # ---------------- resident arm: `value` ----------------
-    eng.upload_primaries_ptr(B, pinned.data_ptr())
-    eng.synchronize()
     step_id = 0
     for _ in range(args.warmup):
         eng.launch_resident(MASTER_SEED, first_index(step_id))
         eng.synchronize()
+        if has_log:
+            lib.mtb_clear_lists(eng._h)
         step_id += 1
-    if world > 1:
-        # warm-up of the collective itself (NCCL builds its communicator lazily on first use)
-        for _ in range(args.warmup):
-            mdist.reduce_tallies(torch.zeros_like(t_u64), torch.zeros_like(t_f64))
+    for _ in range(args.warmup):
+        reduce_tallies(write_back=False)  # warm-up of the collective on the very buffers the timed join uses
     eng.reset_tallies()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     t_wall0 = time.perf_counter()
-    dev_ms, red_ms = 0.0, 0.0
+    dev_ms = 0.0
     for _ in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations (outside the CUDA-event brackets)
         torch.cuda.synchronize()
         eng.launch_resident(MASTER_SEED, first_index(step_id))
         eng.synchronize()
         dev_ms += eng.last_kernel_ms()
+        if has_log:
+            lib.mtb_clear_lists(eng._h)
         step_id += 1
     barrier()
     wall_resident = time.perf_counter() - t_wall0
     clocks = sampler.stop()
     counters = eng.counters()  # this rank's tallies over the timed steps
-    red_ms = reduce_tallies()  # whole-job tallies (one reduction per job, as in runmytrim's threadJoin)
+    red_ms = reduce_tallies()  # whole-job tallies (one join per job, as in runmytrim's threadJoin)
     total = eng.counters() if world > 1 else counters
+    reduction_check = None
+    if world > 1:
+        # self-check of the join: the totals every rank now holds equal the sum of the W contributions
+        pu, pf = reducer.per_rank()
+        ok = bool((pu[:, :mdist.N_ADDITIVE_COUNTERS].sum(dim=0) == t_u64[:mdist.N_ADDITIVE_COUNTERS]).all()) and \
+            bool((pu[:, mdist.N_COUNTER_SLOTS:].sum(dim=0) == t_u64[mdist.N_COUNTER_SLOTS:]).all()) and \
+            bool(torch.allclose(pf.sum(dim=0), t_f64, rtol=1e-12)) and \
+            int(t_u64[4]) == B * world * args.steps
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        reduction_check = "ok" if int(flag[0]) == 1 else "MISMATCH"
     t_rank = torch.tensor([dev_ms + red_ms, dev_ms, float(counters["steps"])], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t_rank.clone()
@@ -276,16 +371,29 @@ def main():
     # ---------------- end-to-end arm: host buffers through mtb_run ----------------
     vac_host = np.zeros(1 << 14, dtype=np.uint64)
     repl_host = np.zeros(1 << 14, dtype=np.uint64)
+    evac_host = np.zeros((32, 1 << 14), dtype=np.uint64) if wl["tally"] & capi.TALLY_VAC_ENERGY else None
+    log_host = np.zeros(max(1 << 20, 64 * B), dtype=capi.IONLOG_DTYPE) if has_log else None
     nb = ctypes.c_size_t()
     cnt = capi.Counters()
-    lib = capi.load_library()
+    d2h = [0]
 
     def e2e_step(step):
         rc = lib.mtb_run(eng._h, B, pinned.data_ptr(), MASTER_SEED, first_index(step), None)
         if rc != 0:
             raise RuntimeError(lib.mtb_last_error().decode())
         lib.mtb_get_counters(eng._h, ctypes.byref(cnt))
-        lib.mtb_get_vac_depth(eng._h, vac_host.ctypes.data, repl_host.ctypes.data, len(vac_host), ctypes.byref(nb))
+        nbytes = ctypes.sizeof(capi.Counters)
+        if wl["tally"] & capi.TALLY_VAC_DEPTH:
+            lib.mtb_get_vac_depth(eng._h, vac_host.ctypes.data, repl_host.ctypes.data, len(vac_host), ctypes.byref(nb))
+            nbytes += vac_host.nbytes + repl_host.nbytes
+        if evac_host is not None:
+            lib.mtb_get_vac_energy(eng._h, evac_host.ctypes.data, evac_host.shape[0], evac_host.shape[1])
+            nbytes += evac_host.nbytes
+        if has_log:
+            lib.mtb_get_ion_log(eng._h, log_host.ctypes.data, len(log_host), ctypes.byref(nb))
+            lib.mtb_clear_lists(eng._h)
+            nbytes += nb.value * capi.IONLOG_DTYPE.itemsize
+        d2h[0] = nbytes
 
     e2e_step(step_id)
     step_id += 1
@@ -295,16 +403,55 @@ def main():
     for _ in range(args.steps):
         e2e_step(step_id)
         step_id += 1
+    if world > 1:
+        reducer.reduce(write_back=True)  # the job's tally join belongs to the end-to-end time
+        lib.mtb_get_counters(eng._h, ctypes.byref(cnt))
     barrier()
     e2e_s = time.perf_counter() - t0
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = cascades / float(t_e[0])
-    d2h = ctypes.sizeof(capi.Counters) + vac_host.nbytes + repl_host.nbytes
+    e2e_primaries_total = int(cnt.primaries)
+    eng.close()
 
+    # ---------------- every BASELINE.json configuration once per GPU ----------------
+    configs = {}
+    if not args.no_configs:
+        for cname, cw in workloads.BENCH_WORKLOADS.items():
+            n = cw["primaries"]
+            if cname == name:
+                ms, st = kernel_ms / args.steps, counters["steps"] / args.steps
+                n = B
+            else:
+                e2, host2 = make_engine(cname, n)
+                e2.upload_primaries_ptr(n, host2.data_ptr())
+                e2.launch_resident(MASTER_SEED, rank * n)          # warm-up
+                e2.synchronize()
+                e2.reset_tallies()
+                flush.zero_()
+                torch.cuda.synchronize()
+                e2.launch_resident(MASTER_SEED, (world + rank) * n)
+                e2.synchronize()
+                ms, st = e2.last_kernel_ms(), e2.counters()["steps"]
+                e2.close()
+            v = torch.tensor([ms, float(st)], dtype=torch.float64, device="cuda")
+            if world > 1:
+                vmax, vsum = v.clone(), v.clone()
+                dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
+                dist.all_reduce(vsum, op=dist.ReduceOp.SUM)
+            else:
+                vmax, vsum = v, v
+            t = float(vmax[0]) * 1e-3
+            configs[cname] = {"cascades_per_s": n * world / t, "collision_steps_per_s": float(vsum[1]) / t,
+                              "steps_per_cascade": float(vsum[1]) / (n * world), "primaries_per_gpu": n,
+                              "kernel_ms": float(vmax[0]), "what": cw["desc"]}
+
+    if world > 1:
+        barrier()
     if rank != 0:
         if world > 1:
+            # rank 0 may still exercise the C-ABI join on GPUs 0 and 1: wait on the host, not in an NCCL kernel
             dist.destroy_process_group()
         return 0
 
@@ -314,31 +461,43 @@ def main():
     lib.mtb_measure_fp32_peak.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)]
     peak_src = "measured (fp32_peak_kernel, FFMA x 148 SMs, this run)"
     if lib.mtb_measure_fp32_peak(local_rank, ctypes.byref(tf), ctypes.byref(ms)) != 0 or tf.value <= 0:
-        tf.value = 148 * 128 * 2 * 1.965e9 / 1e12
+        tf.value = FP32_LANES * 2 * 1.965e9 / 1e12
         peak_src = "nominal 148 SM x 128 lanes x 2 x 1965 MHz (probe failed)"
     steps_per_s_gpu0 = counters["steps"] / (kernel_ms * 1e-3)
     achieved = steps_per_s_gpu0 * FLOP_PER_STEP / 1e12
-    # DRAM traffic of the kernel: bytes per cascade from the committed ncu --set full capture
-    # (profiles/traffic.json, written by tools/ncu_traffic.py), scaled to this launch size
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f)["dram_bytes_per_cascade"] * B
-    except (OSError, KeyError, ValueError):
-        pass
+    # Counters that cannot be measured outside a profiler come from the committed ncu --set full capture of the same
+    # kernel on the same workload (profiles/traffic.json, profiles/ncu_metrics.json, written by tools/ncu_traffic.py
+    # and tools/ncu_metrics.py) and are scaled to this run's launch size and rate; the line says so.
+    traffic, traffic_src = None, None
+    tj = load_profile_json("traffic.json")
+    if tj and name == HEADLINE:
+        traffic = tj["dram_bytes_per_cascade"] * B
+        traffic_src = "profiles/traffic.json (ncu --set full, %s), bytes per cascade x this launch size" % tj.get("source", "?")
     roofline = {
         "bound": "fp32-issue", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved / tf.value,
-        "traffic": traffic, "kernel": "transport_kernel", "flop_per_collision_step": FLOP_PER_STEP,
+        "traffic": traffic, "traffic_source": traffic_src, "kernel": "transport_kernel",
+        "flop_per_collision_step": FLOP_PER_STEP,
         "collision_steps_per_launch": counters["steps"] / args.steps,
         "kernel_ms_per_launch": kernel_ms / args.steps, "peak_source": peak_src,
         "note": "no dense contraction on this path (SURVEY.md §8d): work = 930 FP32-equivalent flop per collision "
-                "step; HBM traffic is O(100 B) per cascade",
+                "step (the reference's operation count); HBM traffic is O(100 B) per cascade",
     }
+    mj = load_profile_json("ncu_metrics.json")
+    if mj and name == HEADLINE and clocks.get("sm_mhz"):
+        # machine-side view: thread instructions the kernel really executes per second against the FP32 lanes
+        thread_inst_per_s = mj["thread_inst_per_cascade"] * (B * args.steps) / (kernel_ms * 1e-3)
+        roofline.update({
+            "issue_frac": thread_inst_per_s / (FP32_LANES * clocks["sm_mhz"] * 1e6),
+            "thread_inst_per_collision_step": mj["thread_inst_per_cascade"] / (counters["steps"] / (B * args.steps)),
+            "warp_efficiency": mj["warp_execution_efficiency"],
+            "issue_slots_busy_pct": mj.get("issue_slots_busy_pct"),
+            "issue_frac_source": "instruction counts from profiles/ncu_metrics.json (ncu --set full, %s) x this run's "
+                                 "cascade rate / (148 x 128 lanes x SM clock under load)" % mj.get("source", "?")})
     line = {
         "metric": "cascades_per_s", "value": value, "unit": "cascades/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": job_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (+f64 position/energy accumulators)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "description": WORKLOAD_DESC, "primaries_per_gpu_per_step": B,
+        "config": {"workload": name, "description": wl["desc"], "primaries_per_gpu_per_step": B,
                    "l2": "256 MB buffer written between timed iterations", "tally_reduction_ms": red_ms},
         "collision_steps_per_s": coll_steps / (job_ms * 1e-3),
         "steps_per_cascade": coll_steps / cascades,
@@ -348,32 +507,44 @@ def main():
         "wall_s_resident_arm": wall_resident,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "cascades/s", "h2d_bytes_per_step": int(B * capi.ION_DTYPE.itemsize),
-                "d2h_bytes_per_step": int(d2h)},
+                "d2h_bytes_per_step": int(d2h[0]), "includes_tally_join": world > 1,
+                "primaries_in_joined_tallies": e2e_primaries_total},
         "gpu_launches": 2 * args.steps,
         "roofline": roofline,
     }
+    if configs:
+        line["configs"] = configs
+    if world > 1:
+        dist.destroy_process_group()  # the other ranks have left: GPUs 0 and 1 are free for the single-process check
+        line["reduction_check"] = reduction_check
+        line["c_abi_allreduce_check"] = c_abi_allreduce_check()
     if not args.no_cpu_baseline:
+        from tests import util
         g.build_test_infrastructure()
         cores = os.cpu_count() or 1
-        if util.have_reference():
-            n_ref = 2000 * cores   # ~2 s of wall time, ~30 core-seconds
-            r = reference_cascades_per_s(n_ref, cores)
+        if name == "uo2_fission" and os.path.exists(util.REF_UO2):
+            r = reference_uo2_primaries_per_s(1, cores)
             line["cpu_baseline"] = {
                 "value": r["cascades_per_s"], "unit": "cascades/s", "cores": cores, "kind": "reference",
-                "sample": "%d Cu->Cu 10 keV cascades, unmodified reference library on %d threads, %.1f s" % (
-                    n_ref, cores, r["seconds"])}
-        else:
+                "sample": "%d fission fragments, unmodified apps/mytrim_uo2.C, one process per core, %.1f s" % (
+                    r["n"], r["seconds"])}
+        elif name != "uo2_fission" and util.have_reference():
+            n_ref = 5 * REF_PER_CORE[name] * cores   # a few seconds of wall time
+            r = reference_cascades_per_s(name, n_ref, cores)
+            line["cpu_baseline"] = {
+                "value": r["cascades_per_s"], "unit": "cascades/s", "cores": cores, "kind": "reference",
+                "sample": "%d cascades of %s, unmodified reference library on %d threads, %.1f s" % (
+                    n_ref, name, cores, r["seconds"])}
+        elif name != "uo2_fission":
             n_ref = 300
             orc = util.OracleEngine(util.ORC_RNG_PHILOX, tally_mask=capi.TALLY_VAC_DEPTH)
-            util.setup_engine(orc, c)
+            c = util.setup_engine(orc, name)
             t0 = time.perf_counter()
             orc.run(util.primaries_for(c, n_ref), seed=MASTER_SEED)
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": n_ref / dt, "unit": "cascades/s", "cores": 1, "kind": "port",
                                     "sample": "%d cascades, oracle C restatement, 1 thread" % n_ref}
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
     return 0
 
 

@@ -143,6 +143,9 @@ public:
   uint64_t philoxKey() const { return _philox_key; }
   /// next unused stream id; every trim()/trimBatch() primary consumes one.
   uint64_t nextStreamId(uint64_t n = 1) { const uint64_t v = _stream; _stream += n; return v; }
+  /// A driver that shards one run over several SimconfType objects (one per GPU) gives every shard the global
+  /// index of its first primary: results then do not depend on the split.
+  void setStreamId(uint64_t first) { _stream = first; }
   /// CUDA device the engines created from this SimconfType run on.
   int device = 0;
 

@@ -279,8 +279,20 @@ int mtb_hist_bins(mtb_handle * h, size_t * bins, size_t * evac_rows);
 /* Raw device views of the additive tallies so a caller can reduce them across GPUs with
  * its own collective (torch.distributed / NCCL): u64 block and f64 block. */
 int mtb_tally_device_views(mtb_handle * h, void ** u64_dev, size_t * n_u64, void ** f64_dev, size_t * n_f64);
-/* Single-process multi-GPU reduction of the additive tallies into handles[0] (NCCL all-reduce). */
+/* Single-process multi-GPU join of the additive tallies (replaces ThreadedTrimBase::threadJoin, runmytrim.C:316-323):
+ * NCCL all-reduce over the handles' tally blocks, IN PLACE on every handle — afterwards each handle holds the job
+ * totals (sum of the counters, histograms and energies; max of the stack high-water mark).  Call it once, when all
+ * handles have finished: a second call, or more primaries followed by another call, would add the totals up again. */
 int mtb_allreduce(mtb_handle ** handles, int n_handles);
+
+/* Fission-fragment source of the UO2 experiment (replaces the event loop head of apps/mytrim_uo2.C:226-270): events
+ * [first_event, first_event + n_events) of the sequence a std::mt19937 seeded with `seed` produces — fragment mass from
+ * the cumulative fission yield (MassInverter, invert.C:30-56), total kinetic energy (EnergyInverter, invert.C:59-78),
+ * Z1 = round(92 A1 / 235), isotropic back-to-back directions, uniform origin in the box w.  Writes 2 n_events
+ * primaries (gen 0, tag -1, Ef = 3 eV as IonBase::setEf gives them) and returns their summed energy in *e_total.
+ * Host only; sharding a run = giving every GPU its own event range. */
+int mtb_fission_pairs(uint32_t seed, uint64_t first_event, uint64_t n_events, const double w[3], mtb_ion * out,
+                      double * e_total);
 
 /* Measures the FP32 FMA issue rate of `device` (the roofline denominator of this path). */
 int mtb_measure_fp32_peak(int device, double * tflops, float * ms);

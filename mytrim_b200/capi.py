@@ -229,6 +229,21 @@ def make_ions(n, Z, m, E, pos=(0.0, 50.0, 50.0), direction=(1.0, 0.0, 0.0), Ef=3
     return ions
 
 
+def fission_pairs(seed, first_event, n_events, w):
+    """mtb_fission_pairs: the fission-fragment source of the UO2 experiment (2 primaries per event)."""
+    lib = load_library()
+    lib.mtb_fission_pairs.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(C.c_double), C.c_void_p,
+                                      C.POINTER(C.c_double)]
+    lib.mtb_fission_pairs.restype = C.c_int
+    ions = np.zeros(2 * n_events, dtype=ION_DTYPE)
+    box = (C.c_double * 3)(*w)
+    e = C.c_double()
+    rc = lib.mtb_fission_pairs(seed, first_event, n_events, box, ions.ctypes.data, C.byref(e))
+    if rc != OK:
+        raise MytrimError(rc, "mtb_fission_pairs")
+    return ions
+
+
 class EngineBase:
     """Call sequence of the reference apps over a C library with the mtb_ entry-point shapes."""
 

@@ -1247,6 +1247,61 @@ EnergyInverter::f(Real x) const
 
 } // namespace MyTRIM_NS
 
+// ---- C ABI: the fission-fragment source of the UO2 experiment (include/mytrim_b200.h) -------
+extern "C" int
+mtb_fission_pairs(uint32_t seed, uint64_t first_event, uint64_t n_events, const double w[3], mtb_ion * out, double * e_total)
+{
+  if (!w || (n_events && !out))
+    return MTB_EINVAL;
+  std::mt19937 rng(seed);
+  std::uniform_real_distribution<double> uniform(0, 1);
+  MyTRIM_NS::MassInverter mass;
+  MyTRIM_NS::EnergyInverter energy;
+  double sum = 0.0;
+  for (uint64_t ev = 0; ev < first_event + n_events; ++ev)
+  {
+    // same draw order as apps/mytrim_uo2.C:226-262: mass, energy, direction (rejection), origin
+    const double A1 = mass.x(uniform(rng)), A2 = 235.0 - A1;
+    energy.setMass(A1);
+    const double Etot = energy.x(uniform(rng));
+    double d[3], norm;
+    do
+    {
+      for (int i = 0; i < 3; ++i)
+        d[i] = 2.0 * uniform(rng) - 1.0;
+      norm = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+    } while (norm <= 0.0001 || norm > 1.0);
+    double pos[3];
+    for (int i = 0; i < 3; ++i)
+      pos[i] = uniform(rng) * w[i];
+    if (ev < first_event)
+      continue; // the source stream is sequential: a shard skips the events before its range
+    const double E1 = Etot * A2 / (A1 + A2), E2 = Etot - E1;
+    const int Z1 = (int)std::round((A1 * 92.0) / 235.0);
+    const double inv = 1.0 / std::sqrt(norm);
+    mtb_ion * o = out + 2 * (ev - first_event);
+    std::memset(o, 0, 2 * sizeof(mtb_ion));
+    for (int k = 0; k < 2; ++k)
+    {
+      for (int i = 0; i < 3; ++i)
+      {
+        o[k].pos[i] = pos[i];
+        o[k].dir[i] = (k ? -1.0 : 1.0) * d[i] * inv;
+      }
+      o[k].E = (k ? E2 : E1) * 1.0e6;
+      o[k].m = k ? A2 : A1;
+      o[k].Z = k ? 92 - Z1 : Z1;
+      o[k].Ef = 3.0;
+      o[k].gen = 0;
+      o[k].tag = -1;
+      sum += o[k].E;
+    }
+  }
+  if (e_total)
+    *e_total = sum;
+  return MTB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // apps/include + apps/src: the threaded tallies runmytrim uses
 // ---------------------------------------------------------------------------------------------

@@ -56,6 +56,8 @@ class TallyReducer:
         blocks = self.all.view(self.world, self.nu + self.nf)
         u = blocks[:, :self.nu].sum(dim=0)
         u[IDX_STACK_MAX] = blocks[:, IDX_STACK_MAX].max()
+        # slots 10..15 are rank-local bookkeeping (work counter, list lengths, error flag): not joined
+        u[IDX_STACK_MAX + 1:N_COUNTER_SLOTS] = self.u64[IDX_STACK_MAX + 1:N_COUNTER_SLOTS]
         f = blocks[:, self.nu:].contiguous().view(torch.float64).sum(dim=0)
         if write_back:
             self.u64.copy_(u)

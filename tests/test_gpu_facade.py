@@ -175,3 +175,34 @@ def test_batched_mytrim_uo2_driver(tmp_path):
     assert 0.4 * n_cpu < n_gpu < 2.5 * n_cpu, (n_gpu, n_cpu)
     # displacement of Xe recoils from their bubble centre: bubble radius is 10 A, most recoils stay near
     assert dist_gpu.shape[1] == 5 and np.median(dist_gpu[:, 0]) < 60.0
+
+
+def _run_uo2(apps, base, nev, env_extra, cbf="1.0"):
+    env = dict(os.environ, MYTRIM_SEED="777", MYTRIM_TIMING="1", **env_extra)
+    out = subprocess.run([os.path.join(apps, "mytrim_uo2"), str(base), "10", cbf, str(nev)], capture_output=True, text=True,
+                         timeout=900, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    timing = [json.loads(l) for l in out.stderr.splitlines() if l.startswith('{"workload"')]
+    return [float(x) for x in out.stdout.strip().split("\n")[-3:]], timing[-1]
+
+
+def test_mytrim_uo2_outputs_do_not_depend_on_chunks_or_gpus(tmp_path):
+    """apps/mytrim_uo2.cpp deals chunks of fission events over MYTRIM_GPUS devices and writes the output lines in event
+    order: .Erec / .dist / .clcoor are byte-identical for any chunk size and any number of GPUs (Philox stream id of a
+    fragment = its global index; reference loop apps/mytrim_uo2.C:226-342)."""
+    apps = _apps()
+    nev = 24
+    e_one, t_one = _run_uo2(apps, tmp_path / "one", nev, {})
+    e_chk, t_chk = _run_uo2(apps, tmp_path / "chk", nev, {"MYTRIM_UO2_CHUNK": "5"})
+    for ext in ("Erec", "dist", "clcoor"):
+        assert open(str(tmp_path / "one") + "." + ext).read() == open(str(tmp_path / "chk") + "." + ext).read(), ext
+    assert t_one["collision_steps"] == t_chk["collision_steps"] and t_one["primaries"] == 2 * nev
+    assert abs(e_one[0] - e_chk[0]) <= 1e-9 * e_one[0]
+    assert len(open(tmp_path / "one.Erec").read().strip().split("\n")) > 100
+    if capi.load_library().mtb_device_count() >= 2:
+        e_two, t_two = _run_uo2(apps, tmp_path / "two", nev, {"MYTRIM_UO2_CHUNK": "5", "MYTRIM_GPUS": "2"})
+        assert t_two["gpus"] == 2
+        for ext in ("Erec", "dist", "clcoor"):
+            assert open(str(tmp_path / "one") + "." + ext).read() == open(str(tmp_path / "two") + "." + ext).read(), ext
+        assert t_two["collision_steps"] == t_one["collision_steps"]
+        assert abs(e_two[0] - e_one[0]) <= 1e-9 * e_one[0]

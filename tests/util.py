@@ -185,48 +185,9 @@ def distinct_seeds(n, master=2344):
     return (x & np.uint64(0xFFFFFFFF)).astype(np.uint32)
 
 
-# --- the BASELINE.json configurations -------------------------------------------
-CU = {"rho": 8.92, "elements": [{"Z": 29, "m": 63.546, "t": 1.0}]}
-FE = {"rho": 7.8658, "elements": [{"Z": 26, "m": 55.847, "t": 1.0}]}
-W = {"rho": 19.35, "elements": [{"Z": 74, "m": 183.85, "t": 1.0}]}
-ZRO2 = {"rho": 6.52, "elements": [{"Z": 40, "m": 90.0, "t": 1.0}, {"Z": 8, "m": 16.0, "t": 2.0}]}
-UO2 = {"rho": 10.0, "elements": [{"Z": 92, "m": 235.0, "t": 1.0}, {"Z": 8, "m": 16.0, "t": 2.0}]}
-XE_GAS = {"rho": 3.5, "elements": [{"Z": 54, "m": 132.0, "t": 1.0}]}
-
-CONFIGS = {
-    "cu_on_cu_10keV": dict(ion=(29, 63.546, 1.0e4), materials=[CU], thicknesses=[1000.0]),
-    "cu_on_cu_1keV": dict(ion=(29, 63.546, 1.0e3), materials=[CU], thicknesses=[100000.0]),
-    "h_on_fe_100keV": dict(ion=(1, 1.008, 1.0e5), materials=[FE], thicknesses=[100000.0]),
-    "he_on_fe_100keV": dict(ion=(2, 4.003, 1.0e5), materials=[FE], thicknesses=[100000.0]),
-    "c_on_w_1MeV": dict(ion=(6, 12.0, 1.0e6), materials=[W], thicknesses=[10000.0]),
-    "xe_on_uo2_80MeV": dict(ion=(54, 132.0, 8.0e7), materials=[UO2], thicknesses=[1.0e7]),
-    # the file-energy / long-cascade configurations of SURVEY.md §8d (validation/cu_on_cu/cu_on_cu.json:3-16,
-    # validation/h_on_fe, tests/json/xe_on_uo2.json)
-    "cu_on_cu_150keV": dict(ion=(29, 63.546, 1.5e5), materials=[CU], thicknesses=[1000.0]),
-    "h_on_fe_1MeV": dict(ion=(1, 1.008, 1.0e6), materials=[FE], thicknesses=[1.0e6]),
-    "xe_on_uo2_10MeV": dict(ion=(54, 131.904, 1.0e7), thicknesses=[100000.0], materials=[
-        {"rho": 10.97, "elements": [{"Z": 92, "m": 238.03, "t": 1.0}, {"Z": 8, "m": 15.999, "t": 2.0}]}]),
-    "xe_on_zro2_500keV": dict(ion=(54, 131.0, 5.0e5), materials=[ZRO2] * 50, thicknesses=[10.0] * 50,
-                              box=(500.0, 100.0, 100.0)),
-}
-
-
-def setup_engine(eng, cfgname_or_dict):
-    c = CONFIGS[cfgname_or_dict] if isinstance(cfgname_or_dict, str) else cfgname_or_dict
-    eng.set_materials(c["materials"])
-    box = c.get("box")
-    if box:
-        eng.set_layers(c["thicknesses"], wy=box[1], wz=box[2], wx=box[0])
-    else:
-        eng.set_layers(c["thicknesses"])
-    return c
-
-
-def primaries_for(c, n, seeds=None):
-    Z, m, E = c["ion"]
-    box = c.get("box")
-    wy, wz = (box[1], box[2]) if box else (100.0, 100.0)
-    return capi.make_ions(n, Z, m, E, pos=(0.0, wy / 2.0, wz / 2.0), seeds=seeds)
+# --- the BASELINE.json configurations: mytrim_b200/workloads.py ---------------------------
+from mytrim_b200.workloads import (CONFIGS, CU, FE, UO2, W, XE_GAS, ZRO2, primaries_for,  # noqa: E402,F401
+                                   setup_engine)
 
 
 # --- north-star statistical criterion against a SUMMARY of a large reference sample -------------------------
