@@ -328,6 +328,7 @@ struct mtb_handle
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int sm_count = 0;
+  int smem_optin = 0; // cudaDevAttrMaxSharedMemoryPerBlockOptin
   int bps[VARIANT_COUNT][2] = {}; // resident CTAs per SM: [variant][share]
   Variant variant = VARIANT_GENERIC, variant_custom = VARIANT_GENERIC; // pick_variant(P, false / true)
 
@@ -451,7 +452,7 @@ build_tables(mtb_handle * h)
   }
 
   h->smem_bytes = smem_layout(P).total;
-  if (h->smem_bytes > 200 * 1024)
+  if (h->smem_bytes > 200 * 1024 || (int)h->smem_bytes > h->smem_optin)
     return fail(MTB_EINVAL, "configuration tables do not fit in shared memory");
   if (std::getenv("MYTRIM_B200_NO_MONO")) // test / tuning knob: single-element samples through the FAST variant
     P.mono = 0;
@@ -461,8 +462,12 @@ build_tables(mtb_handle * h)
   if (const char * env = std::getenv("MYTRIM_B200_VARIANT")) // test knob: "generic" forces the all-options kernels
     if (!std::strcmp(env, "generic"))
       h->variant = h->variant_custom = VARIANT_GENERIC;
+  // The attribute belongs to the kernel, not to the handle: several engines with different table sizes live in one
+  // process (a Trim object's batch and single-ion engines, one engine per configuration in bench.py), so it is set to
+  // the device limit once and for all; the occupancy query and the launches use the handle's own size.
+  const int smem_limit = h->smem_optin;
 #define MTB_SETUP_KERNEL(TRAITS, V, SH)                                                                                     \
-  MTB_CUDA(cudaFuncSetAttribute(transport_kernel<TRAITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)); \
+  MTB_CUDA(cudaFuncSetAttribute(transport_kernel<TRAITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit)); \
   MTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->bps[V][SH], transport_kernel<TRAITS>, kBlock, h->smem_bytes));  \
   h->bps[V][SH] = std::max(h->bps[V][SH], 1);
   MTB_SETUP_KERNEL(TraitsFast, VARIANT_FAST, 0)
@@ -476,8 +481,8 @@ build_tables(mtb_handle * h)
   MTB_SETUP_KERNEL(TraitsGeneric, VARIANT_GENERIC, 0)
   MTB_SETUP_KERNEL(TraitsGenericShare, VARIANT_GENERIC, 1)
 #undef MTB_SETUP_KERNEL
-  MTB_CUDA(cudaFuncSetAttribute(trim_one_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  MTB_CUDA(cudaFuncSetAttribute(stopping_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  MTB_CUDA(cudaFuncSetAttribute(trim_one_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
+  MTB_CUDA(cudaFuncSetAttribute(stopping_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
   if (const char * cap = std::getenv("MYTRIM_B200_BLOCKS_PER_SM")) // tuning knob: resident CTAs per SM
     for (int v = 0; v < VARIANT_COUNT; ++v)
       h->bps[v][0] = std::max(1, std::min(h->bps[v][0], std::atoi(cap)));
@@ -740,6 +745,7 @@ mtb_create(const mtb_config * cfg, mtb_handle ** out)
   if (const char * env = std::getenv("MYTRIM_B200_SHARE_BELOW")) // tuning knob: primaries per lane
     h->share_below = std::strtoull(env, nullptr, 10);
   h->sm_count = prop.multiProcessorCount;
+  h->smem_optin = (int)prop.sharedMemPerBlockOptin;
   cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess)
     e = cudaEventCreate(&h->ev0);

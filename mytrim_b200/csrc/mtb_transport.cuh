@@ -938,10 +938,101 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
   // whole warp is out of work, and no `continue` jumps back to the loop head from divergent code, so
   // the 32 lanes reconverge at the vote in every iteration (a lane-level early exit or continue lets
   // the compiler split the warp for good — measured: 15 instead of 29 active threads).
+#ifndef MTB_DEFER
+#define MTB_DEFER 0
+#endif
+#ifndef MTB_DEFER_EVERY
+#define MTB_DEFER_EVERY 2
+#endif
+  // Batched hand-over (experiment, -DMTB_DEFER=<T>): the end-of-step paths (recoil hand-over, stack push/pop, ion end,
+  // refill) cost ~25 % of the warp instructions at 2-9 active lanes because almost every iteration has SOME lane that
+  // needs them.  With MTB_DEFER a lane that needs one parks its collision result in registers and sits out until at
+  // least T lanes of the warp need the hand-over phase or MTB_DEFER_EVERY iterations have passed; the phase then runs
+  // once for all of them.
+  constexpr bool DEFER = MTB_DEFER > 0 && !EVENTS && !TR::kShare && MTB_DEVICE_CODE;
+  uint32_t pend = 0; // bit 0: a collision result waits for its hand-over; bit 1: recoil to follow; bits 2..: state
+  float sqx = 0.f, sqy = 0.f, sqz = 0.f, sErec = 0.f, smx = 0.f, smy = 0.f, smz = 0.f, sdsafe = 0.f;
+  uint32_t sw3 = 0, srp = 0;
+  int32_t smtag = 0;
+  uint32_t iter = 0;
+
   for (;;)
   {
+    bool resolve = true;
+#if MTB_DEVICE_CODE
+    if (DEFER)
+    {
+      const unsigned int need = __ballot_sync(0xffffffffu, pend != 0 || (!active && !done));
+      ++iter;
+      resolve = __popc(need) >= MTB_DEFER || (iter % MTB_DEFER_EVERY) == 0 || need == 0xffffffffu;
+    }
+#endif
+    if (DEFER && resolve && pend)
+    {
+      // ---------------- deferred "who flies next" (same logic as at the end of the collision below) ----------------
+      const int state = (int)(pend >> 2);
+      const bool follow = (pend & 2u) != 0;
+      pend = 0;
+      const double mvx = (double)smx, mvy = (double)smy, mvz = (double)smz;
+      const float E2 = L.Ecur;
+      if (follow)
+      {
+        L.casIons++;
+        const float qs = frsqrt(sqx * sqx + sqy * sqy + sqz * sqz);
+        const uint64_t ruid = child_uid(L.uid, L.ic, sw3);
+        const bool keep_projectile = (state == MTB_MOVING) && (E2 <= sErec);
+        if (state == MTB_MOVING && !keep_projectile)
+        {
+          Lane T = L;
+          T.px = L.px + mvx;
+          T.py = L.py + mvy;
+          T.pz = L.pz + mvz;
+          suspend_ion<TR>(P, S, sp, T, L.prim, sErec);
+        }
+        if (state != MTB_MOVING)
+          finish_ion<TR>(P, S, L, rows, state, L.px + mvx, L.py + mvy, L.pz + mvz);
+        if (keep_projectile)
+        {
+          Lane R;
+          R.px = L.px; R.py = L.py; R.pz = L.pz;
+          R.E = (double)sErec;
+          R.dx = sqx * qs; R.dy = sqy * qs; R.dz = sqz * qs;
+          R.ic = 0;
+          R.uid = ruid;
+          R.packed = srp;
+          R.tag = smtag;
+          if (tally_on<TR>(P, MTB_TALLY_IONLOG))
+          {
+            R.prim = L.prim;
+            log_birth<TR>(P, R, S.pclass[(srp & SPECIES_MASK) - SPECIES_CLASS0].Z);
+          }
+          suspend_ion<TR>(P, S, sp, R, L.prim, E2);
+          L.px += mvx;
+          L.py += mvy;
+          L.pz += mvz;
+        }
+        else
+        {
+          L.E = (double)sErec;
+          L.Ecur = sErec;
+          L.dx = sqx * qs; L.dy = sqy * qs; L.dz = sqz * qs;
+          L.ic = 0;
+          L.uid = ruid;
+          L.packed = srp;
+          L.tag = smtag;
+          L.pcls = (int32_t)((srp & SPECIES_MASK) - SPECIES_CLASS0);
+          L.dsafe = sdsafe;
+          log_birth<TR>(P, L, S.pclass[L.pcls].Z);
+        }
+      }
+      else
+      {
+        finish_ion<TR>(P, S, L, rows, state, L.px + mvx, L.py + mvy, L.pz + mvz);
+        active = false;
+      }
+    }
     // ---------------- refill: next suspended ion, else next primary ----------------
-    if (!done && !active)
+    if (resolve && !done && !active)
     {
       if (sp & MTB_STACK_DEPTH_BITS)
       {
@@ -1102,7 +1193,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       __nanosleep(400); // the whole warp is polling: back off
 #endif
 
-    if (active)
+    if (active && !(DEFER && pend))
       do
       {
     // ---------------- one collision: trim.C:74-424 ----------------
@@ -1247,7 +1338,8 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     // only on the paths where the projectile flies on: keeping both positions alive across the fate logic
     // cost seven register moves on every exit of the step.
     const float flight = (ls - P.tau) * P.inv_scale;
-    const double mvx = (double)(L.dx * flight), mvy = (double)(L.dy * flight), mvz = (double)(L.dz * flight);
+    const float mfx = L.dx * flight, mfy = L.dy * flight, mfz = L.dz * flight;
+    const double mvx = (double)mfx, mvy = (double)mfy, mvz = (double)mfz;
     const float dsafe_here = L.dsafe; // of the collision site: a recoil starts there
     L.dsafe -= fabsf(flight);
 #define MTB_AHEAD_X (L.px + mvx)
@@ -1384,7 +1476,28 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     }
 
     // ---------------- who flies next ----------------
-    if (follow)
+    if (DEFER)
+    {
+      if (follow || state != MTB_MOVING)
+      {
+        // park the result; the hand-over phase at the loop head picks it up (L.p* stays the collision site)
+        pend = 1u | (follow ? 2u : 0u) | ((uint32_t)state << 2);
+        sqx = qx; sqy = qy; sqz = qz;
+        sErec = Erec;
+        smx = mfx; smy = mfy; smz = mfz;
+        sw3 = w[3];
+        srp = (uint32_t)(SPECIES_CLASS0 + el.tcls) | ((uint32_t)rec_gen << GEN_SHIFT);
+        smtag = mtag;
+        sdsafe = dsafe_here;
+      }
+      else
+      {
+        L.px = MTB_AHEAD_X;
+        L.py = MTB_AHEAD_Y;
+        L.pz = MTB_AHEAD_Z;
+      }
+    }
+    else if (follow)
     {
       L.casIons++;
       const float qs = frsqrt(qx * qx + qy * qy + qz * qz);

@@ -17,9 +17,12 @@ Fixtures:
   ref_geometry_<sample>.npz    records of the reference in a SampleWire / SampleBurriedWire.
   ref_options_scale10.npz      records with a length scale of 10 A, per-element Edisp / Elbind and Ef = 5 eV.
   ref_records_layer_stack.npz  Cu / Fe / W / ZrO2 stack: the layer look-up with different materials.
-  ref_stats_<cfg>.npz          quantiles / histograms / means of 4e3..1e6 reference cascades per configuration
+  ref_stats_<cfg>.npz          quantiles / histograms / means of 1e5..1e6 reference cascades per configuration
                                (statistical criterion; STATISTICS_CASES).
   ref_options_tmin1_cw0p01.npz, ref_options_primaries_only.npz   tmin = 1, cw = 0.01; ThreadedTrimBase::_primaries_only.
+  ref_output_evac_<cfg>.npz, ref_output_ranges_<cfg>.npz   content of the files the reference's writeOutput() wrote for
+                               validation/c_on_w/input.json (2000 primaries) and validation/cu_on_cu/cu_on_cu.json (1e5).
+  ref_uo2_seed777.npz          summary of .Erec / .dist of `MYTRIM_SEED=777 mytrim_uo2 out 10 1.0 100` (44 bubbles).
   vacancy_count_published.json the reference's published vacancies/ion table
                                (validation/vacancy_count/vacancy_count_comparison.dat).
 """
@@ -202,7 +205,7 @@ def stack():
 # samples of the north-star statistical criterion: cascades of the unmodified reference with distinct 32-bit seeds
 # (SURVEY.md §8c), summarised (tests/util.py::summarize_records).  1e6 Cu->Cu 10 keV cascades take ~4 min on 8 cores.
 STATISTICS_CASES = {"cu_on_cu_10keV": 1000000, "cu_on_cu_1keV": 1000000, "h_on_fe_100keV": 500000,
-                    "he_on_fe_100keV": 100000, "c_on_w_1MeV": 20000, "xe_on_zro2_500keV": 4000}
+                    "he_on_fe_100keV": 100000, "c_on_w_1MeV": 100000, "xe_on_zro2_500keV": 100000}
 
 
 def statistics(only=None):
@@ -215,6 +218,26 @@ def statistics(only=None):
                                                       box=c.get("box"), timeout=7200)
         np.savez_compressed(os.path.join(HERE, "ref_stats_%s.npz" % name), summary=json.dumps(summary),
                             **util.summarize_records(rec))
+
+
+# what the reference's own writeOutput() puts into <base>_evac.dat (TrimVacEnergyCount.C:70-81) and <base>_ranges.dat
+# (TrimRange.C:66-121) for samples large enough to compare the GPU drivers' files with them statistically
+# (SURVEY.md §8f row 1): validation/c_on_w/input.json (vacenergycount) and validation/cu_on_cu/cu_on_cu.json (range)
+OUTPUT_CASES = {"evac": ("c_on_w_1MeV", "vacenergycount", 2000), "ranges": ("cu_on_cu_150keV", "range", 100000)}
+
+
+def outputs():
+    for key, (name, tally, n) in OUTPUT_CASES.items():
+        c = util.CONFIGS[name]
+        rec, summary, hist = util.run_reference_cascades(c["ion"], c["materials"], c["thicknesses"],
+                                                         util.distinct_seeds(n, master=707), tally=tally,
+                                                         threads=os.cpu_count() or 1, timeout=3600)
+        if key == "evac":
+            np.savez_compressed(os.path.join(HERE, "ref_output_evac_%s.npz" % name), n=n,
+                                evac=hist[hist[:, 2] > 0].astype(np.int64), shape=hist[:, :2].max(axis=0).astype(np.int64) + 1,
+                                vacancies=int(rec["vacancies"].sum()))
+        else:
+            np.savez_compressed(os.path.join(HERE, "ref_output_ranges_%s.npz" % name), n=n, ranges_dat=np.array(hist))
 
 
 def published():
@@ -244,5 +267,6 @@ if __name__ == "__main__":
     options2()
     stack()
     statistics()
+    outputs()
     published()
     print("golden fixtures written to", HERE)

@@ -147,9 +147,12 @@ def test_unmodified_reference_uo2_app_through_facade(tmp_path):
 
 
 def test_batched_mytrim_uo2_driver(tmp_path):
-    """apps/mytrim_uo2.cpp (all fission fragments in one GPU batch) against the oracle's restatement of
-    the reference experiment: identical bubble placement for the same seed, same energy partition and a
-    compatible yield of Xe recoils knocked out of the bubbles."""
+    """apps/mytrim_uo2.cpp (fission fragments in GPU batches) against the UNMODIFIED reference's own run of the same
+    experiment (`MYTRIM_SEED=777 mytrim_uo2 out 10 1.0 100`, 44 bubbles, 17 607 Xe recoils; summary committed as
+    tests/golden/ref_uo2_seed777.npz by tests/golden/make_golden.py): identical bubble placement for the same seed, and the
+    content of .Erec / .dist — recoil energy, generation, MD flag, displacement from the bubble centre — as distributions
+    (two-sample KS distance on the quantile summaries; recoils of one event are correlated, so the bound is on D, not
+    on an i.i.d. p-value), recoil yield per event and energy partition."""
     import ctypes as C
     apps = _apps()
     env = dict(os.environ, MYTRIM_SEED="777")
@@ -159,22 +162,40 @@ def test_batched_mytrim_uo2_driver(tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     eel, enuc, balance = (float(x) for x in out.stdout.strip().split("\n")[-3:])
     frac_gpu = eel / (eel + enuc + balance)
-    n_gpu = len(open(tmp_path / "gpu.Erec").read().strip().split("\n")) / nev
+    erec = np.loadtxt(tmp_path / "gpu.Erec", ndmin=2)
     dist_gpu = np.loadtxt(tmp_path / "gpu.dist", ndmin=2)
+    ref = np.load(os.path.join(util.GOLDEN, "ref_uo2_seed777.npz"))
 
+    # bubble placement: the oracle's restatement (pinned byte for byte on the reference's gold files) with this seed
     lib = C.CDLL(util.ORACLE_LIB)
     lib.orc_uo2_experiment.argtypes = [C.c_char_p, C.c_double, C.c_double, C.c_int, C.c_uint32,
                                        C.POINTER(C.c_double), C.POINTER(C.c_double)]
     e1, e2 = C.c_double(), C.c_double()
-    nev_ref = 6
-    assert lib.orc_uo2_experiment(str(tmp_path / "cpu").encode(), 10.0, 1.0, nev_ref, 777, C.byref(e1), C.byref(e2)) == 0
+    assert lib.orc_uo2_experiment(str(tmp_path / "cpu").encode(), 10.0, 1.0, 1, 777, C.byref(e1), C.byref(e2)) == 0
     assert open(tmp_path / "gpu.clcoor").read() == open(tmp_path / "cpu.clcoor").read()
-    frac_cpu = e1.value / e2.value
-    assert abs(frac_gpu - frac_cpu) < 0.01, (frac_gpu, frac_cpu)
-    n_cpu = len(open(tmp_path / "cpu.Erec").read().strip().split("\n")) / nev_ref
-    assert 0.4 * n_cpu < n_gpu < 2.5 * n_cpu, (n_gpu, n_cpu)
-    # displacement of Xe recoils from their bubble centre: bubble radius is 10 A, most recoils stay near
-    assert dist_gpu.shape[1] == 5 and np.median(dist_gpu[:, 0]) < 60.0
+
+    def ks_distance(sample, quantiles):
+        k = len(quantiles)
+        F = np.searchsorted(np.sort(sample), quantiles, side="right") / float(len(sample))
+        return float(np.abs(F - (np.arange(k) + 0.5) / k).max())
+
+    d_energy = ks_distance(erec[:, 0], ref["q_energy"])
+    d_dist = ks_distance(dist_gpu[:, 0], ref["q_dist"])
+    per_event = len(erec) / nev
+    gen_gpu = np.bincount(erec[:, 1].astype(int), minlength=len(ref["h_gen"])) / float(len(erec))
+    gen_ref = ref["h_gen"] / float(ref["h_gen"].sum())
+    m = max(len(gen_gpu), len(gen_ref))
+    d_gen = float(np.abs(np.cumsum(np.pad(gen_gpu, (0, m - len(gen_gpu)))) - np.cumsum(np.pad(gen_ref, (0, m - len(gen_ref))))).max())
+    print("uo2 vs reference: D(energy) %.4f D(displacement) %.4f D(generation) %.4f recoils/event %.1f (ref %.1f) "
+          "md %.4f (ref %.4f) Eel fraction %.4f (ref %.4f)" % (d_energy, d_dist, d_gen, per_event, float(ref["recoils_per_event"]),
+                                                               erec[:, 2].mean(), float(ref["md_fraction"]), frac_gpu,
+                                                               float(ref["eel_fraction"])))
+    # two halves (50 events each) of the reference's own run differ by D = 0.008 / 0.007 / 0.019
+    assert d_energy < 0.02 and d_dist < 0.02 and d_gen < 0.03, (d_energy, d_dist, d_gen)
+    assert abs(per_event - float(ref["recoils_per_event"])) < 0.1 * float(ref["recoils_per_event"])
+    assert abs(erec[:, 2].mean() - float(ref["md_fraction"])) < 0.01
+    assert abs(frac_gpu - float(ref["eel_fraction"])) < 0.003, (frac_gpu, float(ref["eel_fraction"]))
+    assert dist_gpu.shape[1] == 5
 
 
 def _run_uo2(apps, base, nev, env_extra, cbf="1.0"):

@@ -644,3 +644,21 @@ def test_error_paths_return_status_codes():
     assert lib.mtb_create(C.byref(cfg), C.byref(h)) == capi.EINVAL
     cfg = capi.default_config(device=99)
     assert lib.mtb_create(C.byref(cfg), C.byref(h)) == capi.EINVAL
+
+
+def test_engines_with_different_table_sizes_coexist():
+    """The dynamic shared-memory limit is an attribute of the kernel, not of a handle: an engine with small tables
+    created while one with histogram mirrors is alive must not shrink the limit under it (the façade keeps a batch
+    and a single-ion engine per Trim object; bench.py one engine per configuration)."""
+    c = util.CONFIGS["cu_on_cu_10keV"]
+    ions = util.primaries_for(c, 2000)
+    with capi.Engine(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS) as big:
+        util.setup_engine(big, c)
+        r0 = big.run(ions, seed=3, records=True)
+        with capi.Engine(tally_mask=0) as small:
+            util.setup_engine(small, c)
+            small.run(ions[:100], seed=3)
+            ion, state, ev = small.trim_one(ions[0], 3, 7)
+            assert len(ev) > 0
+            r1 = big.run(ions, seed=3, records=True)
+    assert np.array_equal(r0["steps"], r1["steps"]) and np.array_equal(r0["pos"], r1["pos"])

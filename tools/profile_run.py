@@ -18,12 +18,13 @@ ap.add_argument("--primaries", type=int, default=1 << 18)
 ap.add_argument("--launches", type=int, default=2)
 ap.add_argument("--workload", default="cu_on_cu_10keV")
 ap.add_argument("--tally", type=int, default=capi.TALLY_VAC_DEPTH)
+ap.add_argument("--ionlog-z", type=int, default=54, help="Z filter of the ion log (tally bit 64)")
 ap.add_argument("--escale", type=float, default=1.0, help="scale the primary energies (short kernels for ncu)")
 args = ap.parse_args()
 
 
 
-with capi.Engine(tally_mask=args.tally) as eng:
+with capi.Engine(tally_mask=args.tally, ionlog_z=args.ionlog_z) as eng:
     if args.workload == "uo2_fission":
         from mytrim_b200 import workloads
         ions = workloads.setup_workload(eng, "uo2_fission", args.primaries)   # mtb_fission_pairs: the app's source
