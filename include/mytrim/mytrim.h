@@ -28,6 +28,7 @@
 #include <queue>
 #include <random>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../mytrim_b200.h"
@@ -349,6 +350,10 @@ struct DeviceHooks
   int ionlog_z = 0;
   int hist_bins = 0;
   unsigned long long ionlog_capacity = 0; ///< entries (birth + death halves); 0 = engine default
+  unsigned long long range_capacity = 0;  ///< entries of the range list; 0 = engine default
+  /// trimBatch() hands the primaries to the device in chunks of this many (0 = all at once) and calls
+  /// collectDeviceTallies() after each: list-type tallies (range list) stay bounded however large the run is.
+  unsigned long long batch_chunk = 0;
 };
 
 class TrimBase
@@ -426,6 +431,18 @@ private:
                                        const std::vector<mtb_element> & els, const mtb_geometry & g,
                                        const std::vector<double> & storage) const;
   std::vector<mtb_event> _events;
+  // trim() is handed one ion at a time, but the caller's queue shows which ions come next: every ion waiting there is
+  // followed in the same launch (mtb_trim_many, one GPU lane per ion) and its collision events are kept until the
+  // caller asks for that ion.  An app's queue loop costs one launch per generation of a cascade instead of one per ion.
+  struct Followed
+  {
+    mtb_ion start;                // the ion as it was when it was followed (a changed ion is followed again)
+    std::vector<mtb_event> events;
+  };
+  std::unordered_map<const IonBase *, Followed> _followed;
+  bool followQueued(IonBase * pka, const mtb_ion & ion, std::queue<IonBase *> & recoils);
+  std::vector<mtb_event> _batch_events;
+  std::vector<uint32_t> _batch_counts;
   unsigned long long _seen_vac, _seen_steps;
   double _seen_eel, _seen_enuc;
 };

@@ -303,6 +303,16 @@ int mtb_measure_fp32_peak(int device, double * tflops, float * ms);
 int mtb_trim_one(mtb_handle * h, mtb_ion * ion, uint64_t seed, uint64_t uid, int32_t * final_state,
                  mtb_event * events, size_t capacity, size_t * n_events);
 
+/* The same for a batch of ions in ONE launch (one GPU lane per ion; replaces the per-ion round trip when a reference
+ * app's queue loop, runmytrim.C:76-92, hands TrimBase::trim() one ion at a time: the façade follows all queued ions of
+ * a generation at once).  Ion i uses Philox stream uids[i] (first_uid + i when uids is null) and writes its collisions to
+ * events[i * events_per_ion ...]; counts[i] is the number of collisions it had.  Where counts[i] > events_per_ion the
+ * record of that ion is incomplete (its first events_per_ion events are valid): follow it again with the same stream
+ * id — mtb_trim_one or another batch with that ion's uid — and a larger buffer; the replay is identical.
+ * ions[i] and final_states[i] receive the final state of every completely recorded ion. */
+int mtb_trim_many(mtb_handle * h, size_t n, mtb_ion * ions, uint64_t seed, uint64_t first_uid, const uint64_t * uids,
+                  int32_t * final_states, mtb_event * events, size_t events_per_ion, uint32_t * counts);
+
 /* Replaces MaterialBase::getrstop (material.C:113-122) for a batch of (Z1, m1, E) in material
  * `material`; runs the same device function the transport kernel uses. */
 int mtb_stopping(mtb_handle * h, int material, size_t n, const int32_t * Z1, const double * m1,

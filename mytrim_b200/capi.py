@@ -147,6 +147,7 @@ def declare(lib, prefix):
     f("hist_bins", vp, szp, szp)
     f("tally_device_views", vp, C.POINTER(vp), szp, C.POINTER(vp), szp)
     f("trim_one", vp, vp, C.c_uint64, C.c_uint64, C.POINTER(C.c_int32), vp, C.c_size_t, szp)
+    f("trim_many", vp, C.c_size_t, vp, C.c_uint64, C.c_uint64, vp, vp, vp, C.c_size_t, vp)
     f("stopping", vp, C.c_int, C.c_size_t, vp, vp, vp, vp)
     f("destroy", vp)
     f("get_tables", vp, vp, vp, vp)
@@ -337,6 +338,22 @@ class EngineBase:
         self._check(self._fn("trim_one")(self._h, ion.ctypes.data, seed, uid, C.byref(st), ev.ctypes.data,
                                          capacity, C.byref(n)))
         return ion[0], st.value, ev[:n.value].copy()
+
+
+def _trim_many(self, ions, seed, first_uid, events_per_ion, uids=None):
+    """mtb_trim_many: every ion of the batch in one launch; returns (final ions, final states, counts, events[n][K])."""
+    ions = np.array(ions, dtype=ION_DTYPE).copy()
+    n = len(ions)
+    ev = np.zeros((n, events_per_ion), dtype=EVENT_DTYPE)
+    counts = np.zeros(n, dtype=np.uint32)
+    states = np.zeros(n, dtype=np.int32)
+    u = None if uids is None else np.ascontiguousarray(uids, dtype=np.uint64)
+    self._check(self._fn("trim_many")(self._h, n, ions.ctypes.data, seed, first_uid, None if u is None else u.ctypes.data,
+                                      states.ctypes.data, ev.ctypes.data, events_per_ion, counts.ctypes.data))
+    return ions, states, counts, ev
+
+
+EngineBase.trim_many = _trim_many
 
 
 class Engine(EngineBase):

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <sstream>
 #include <typeinfo>
 
@@ -837,6 +838,7 @@ TrimBase::ensureEngine(bool batch)
     cfg.ionlog_z = h.ionlog_z;
     cfg.hist_bins = h.hist_bins;
     cfg.ionlog_capacity = h.ionlog_capacity;
+    cfg.range_capacity = h.range_capacity;
   }
 
   std::vector<mtb_material> mats;
@@ -918,7 +920,113 @@ ionToAbi(const IonBase * in, mtb_ion & o)
 }
 } // namespace
 
-// One ion: the device follows it (mtb_trim_one), the hooks run here in the reference's order
+namespace
+{
+// the container behind a std::queue (its protected member `c`), read-only
+template <class T>
+const std::deque<T> &
+queueContainer(const std::queue<T> & q)
+{
+  struct Access : std::queue<T>
+  {
+    static const std::deque<T> & get(const std::queue<T> & q) { return q.*(&Access::c); }
+  };
+  return Access::get(q);
+}
+} // namespace
+
+// Follows `pka` and every ion that waits in the caller's queue and has not been followed yet in one launch
+// (mtb_trim_many), ions with long trajectories in further launches with buffers of the size the first one reported.
+bool
+TrimBase::followQueued(IonBase * pka, const mtb_ion & ion, std::queue<IonBase *> & recoils)
+{
+  const size_t kMaxBatch = 8192, kFirstEvents = 32, kMaxEventsPerLaunch = 1u << 20;
+  std::vector<const IonBase *> who(1, pka);
+  std::vector<mtb_ion> ions(1, ion);
+  for (IonBase * q : queueContainer(recoils))
+  {
+    if (who.size() >= kMaxBatch)
+      break;
+    if (q == pka || !q)
+      continue;
+    mtb_ion a;
+    ionToAbi(q, a);
+    auto it = _followed.find(q);
+    if (it != _followed.end())
+    {
+      if (std::memcmp(&it->second.start, &a, sizeof(a)) == 0)
+        continue;
+      _followed.erase(it);
+    }
+    who.push_back(q);
+    ions.push_back(a);
+  }
+  const size_t n = who.size();
+  const uint64_t first_uid = _simconf->nextStreamId(n);
+  const std::vector<mtb_ion> start = ions;
+  _batch_events.resize(n * kFirstEvents);
+  _batch_counts.resize(n);
+  if (mtb_trim_many(_engine_single, n, ions.data(), _simconf->philoxKey(), first_uid, nullptr, nullptr, _batch_events.data(),
+                    kFirstEvents, _batch_counts.data()) != MTB_OK)
+  {
+    _error = mtb_last_error();
+    return false;
+  }
+  std::vector<size_t> longer; // ions with more collisions than the first buffer holds
+  for (size_t i = 0; i < n; ++i)
+  {
+    if (_batch_counts[i] > kFirstEvents)
+    {
+      longer.push_back(i);
+      continue;
+    }
+    Followed & f = _followed[who[i]];
+    f.start = start[i];
+    f.events.assign(_batch_events.begin() + i * kFirstEvents, _batch_events.begin() + i * kFirstEvents + _batch_counts[i]);
+  }
+  // the long ones again, grouped so that a launch holds at most kMaxEventsPerLaunch events; same stream ids, so the
+  // trajectories are the ones the first launch counted
+  std::sort(longer.begin(), longer.end(), [this](size_t a, size_t b) { return _batch_counts[a] < _batch_counts[b]; });
+  const std::vector<uint32_t> counts = _batch_counts;
+  for (size_t lo = 0; lo < longer.size();)
+  {
+    size_t hi = lo + 1;
+    while (hi < longer.size() && (hi - lo + 1) * (size_t)counts[longer[hi]] <= kMaxEventsPerLaunch)
+      ++hi;
+    const size_t m = hi - lo, cap = counts[longer[hi - 1]];
+    std::vector<mtb_ion> sub(m);
+    std::vector<uint64_t> uids(m);
+    for (size_t k = 0; k < m; ++k)
+    {
+      sub[k] = start[longer[lo + k]];
+      uids[k] = first_uid + longer[lo + k];
+    }
+    _batch_events.resize(m * cap);
+    _batch_counts.resize(m);
+    if (mtb_trim_many(_engine_single, m, sub.data(), _simconf->philoxKey(), 0, uids.data(), nullptr, _batch_events.data(), cap,
+                      _batch_counts.data()) != MTB_OK)
+    {
+      _error = mtb_last_error();
+      return false;
+    }
+    for (size_t k = 0; k < m; ++k)
+    {
+      if (_batch_counts[k] != counts[longer[lo + k]])
+      {
+        _error = "event replay of an ion differs from its first pass";
+        return false;
+      }
+      Followed & f = _followed[who[longer[lo + k]]];
+      f.start = start[longer[lo + k]];
+      f.events.assign(_batch_events.begin() + k * cap, _batch_events.begin() + k * cap + _batch_counts[k]);
+    }
+    lo = hi;
+  }
+  return true;
+}
+
+// One ion: the device follows it (with everything else that waits in the caller's queue, followQueued), the hooks run
+// here in the reference's order
 // (trim.C:357-418): followRecoil -> vacancyCreation | replacementCollision, or
 // dissipateRecoilEnergy; then checkPKAState.  Recoils the hooks accept go to the caller's queue.
 void
@@ -934,28 +1042,24 @@ TrimBase::trim(IonBase * pka, std::queue<IonBase *> & recoils)
   }
   mtb_ion ion;
   ionToAbi(pka, ion);
-  if (_events.size() < 4096)
-    _events.resize(4096);
-  size_t n = 0;
-  int32_t final_state = MTB_MOVING;
-  const uint64_t uid = _simconf->nextStreamId();
-  for (;;)
+  auto hit = _followed.find(pka);
+  if (hit != _followed.end() && std::memcmp(&hit->second.start, &ion, sizeof(ion)) != 0)
   {
-    mtb_ion work = ion;
-    const int rc = mtb_trim_one(_engine_single, &work, _simconf->philoxKey(), uid, &final_state, _events.data(),
-                                _events.size(), &n);
-    if (rc == MTB_ECAPACITY)
+    _followed.erase(hit); // the caller changed the ion after it had been followed (or the address was re-used)
+    hit = _followed.end();
+  }
+  if (hit == _followed.end())
+  {
+    if (!followQueued(pka, ion, recoils))
     {
-      _events.resize(std::max(n, 2 * _events.size()));
-      continue; // same stream id: the replay is identical, only the buffer is larger
-    }
-    if (rc != MTB_OK)
-    {
-      std::cerr << "TrimBase::trim: " << mtb_last_error() << std::endl;
+      std::cerr << "TrimBase::trim: " << _error << std::endl;
       std::exit(1);
     }
-    break;
+    hit = _followed.find(pka);
   }
+  _events.swap(hit->second.events);
+  _followed.erase(hit);
+  const size_t n = _events.size();
 
   for (size_t k = 0; k < n; ++k)
   {
@@ -1041,11 +1145,37 @@ TrimBase::trimBatch(std::vector<IonBase *> & primaries, std::vector<mtb_record> 
   std::vector<mtb_record> local;
   std::vector<mtb_record> & rec = records_out ? *records_out : local;
   rec.resize(n);
+  DeviceHooks hooks;
+  deviceHooks(hooks);
+  const size_t chunk = hooks.batch_chunk ? (size_t)hooks.batch_chunk : std::max<size_t>(n, 1);
   const uint64_t first = _simconf->nextStreamId(n);
-  if (mtb_run(_engine, n, ions.data(), _simconf->philoxKey(), first, rec.data()) != MTB_OK)
+  for (size_t lo = 0; lo < n || lo == 0; lo += chunk)
   {
-    _error = mtb_last_error();
-    return false;
+    const size_t m = std::min(chunk, n - lo);
+    if (mtb_run(_engine, m, ions.data() + lo, _simconf->philoxKey(), first + lo, rec.data() + lo) != MTB_OK)
+    {
+      _error = mtb_last_error();
+      return false;
+    }
+    mtb_counters c;
+    if (mtb_get_counters(_engine, &c) != MTB_OK)
+    {
+      _error = mtb_last_error();
+      return false;
+    }
+    _simconf->vacancies_created += (int)(c.vacancies_created - _seen_vac);
+    _simconf->EelTotal += c.EelTotal - _seen_eel;
+    _simconf->EnucTotal += c.EnucTotal - _seen_enuc;
+    _seen_vac = c.vacancies_created;
+    _seen_eel = c.EelTotal;
+    _seen_enuc = c.EnucTotal;
+    _seen_steps = c.steps;
+    _error.clear();
+    collectDeviceTallies();
+    if (!_error.empty())
+      return false;
+    if (n == 0)
+      break;
   }
   for (size_t i = 0; i < n; ++i)
   {
@@ -1053,20 +1183,6 @@ TrimBase::trimBatch(std::vector<IonBase *> & primaries, std::vector<mtb_record> 
     primaries[i]->_E = rec[i].E;
     primaries[i]->_state = (IonBase::StateType)rec[i].state;
   }
-  mtb_counters c;
-  if (mtb_get_counters(_engine, &c) != MTB_OK)
-  {
-    _error = mtb_last_error();
-    return false;
-  }
-  _simconf->vacancies_created += (int)(c.vacancies_created - _seen_vac);
-  _simconf->EelTotal += c.EelTotal - _seen_eel;
-  _simconf->EnucTotal += c.EnucTotal - _seen_enuc;
-  _seen_vac = c.vacancies_created;
-  _seen_eel = c.EelTotal;
-  _seen_enuc = c.EnucTotal;
-  _seen_steps = c.steps;
-  collectDeviceTallies();
   return true;
 }
 
@@ -1564,6 +1680,10 @@ TrimRange::deviceHooks(DeviceHooks & h) const
   h.follow = MTB_FOLLOW_NONE; // _recoil->_gen < 1 never holds (TrimRange.h:16)
   h.vacancy_model = MTB_VAC_NRT;
   h.tally_mask = MTB_TALLY_RANGE;
+  // every sub-threshold recoil of every primary is one list entry (~220 per 150 keV Cu primary): the primaries go
+  // to the device in chunks and the list is drained after each
+  h.batch_chunk = 8192;
+  h.range_capacity = 1ull << 24;
 }
 
 void
@@ -1571,15 +1691,20 @@ TrimRange::collectDeviceTallies()
 {
   size_t n = 0;
   mtb_get_range_list(engine(), nullptr, nullptr, 0, &n);
-  if (n <= _dev_seen)
+  if (n == 0)
     return;
   std::vector<float> x(n);
   std::vector<int32_t> Z(n);
   const int rc = mtb_get_range_list(engine(), x.data(), Z.data(), n, &n);
-  if (rc != MTB_OK && rc != MTB_ECAPACITY)
+  if (rc != MTB_OK)
+  {
+    // an overflowed list would silently truncate <base>_ranges.dat
+    _error = std::string("TrimRange: ") + mtb_last_error();
     return;
-  for (size_t i = _dev_seen; i < std::min(n, x.size()); ++i)
+  }
+  for (size_t i = 0; i < std::min(n, x.size()); ++i)
     if (Z[i] >= 0 && Z[i] < (int)_range.size())
       _range[Z[i]].push_back(x[i]);
-  _dev_seen = n;
+  mtb_clear_lists(engine()); // drained: the next chunk starts an empty list
+  _dev_seen = 0;
 }

@@ -119,6 +119,7 @@ struct HostConfig
   std::vector<double> layer_thickness, cluster_xyzr;
   // (Z, m) of primaries seen so far that are not target atoms: they get projectile classes too
   std::vector<std::pair<int, double>> primary_species;
+  std::vector<int> first_input_material; // set by fold_identical_materials on build_host_tables' private copy
 
   HostConfig()
   {
@@ -146,6 +147,7 @@ struct HostTables
   std::vector<int32_t> tclass_elem;
   std::vector<double> layer_cum;
   std::vector<int32_t> layer_mat, cl_hash, cl_next;
+  std::vector<int> mat_map; // device material of every input material (fold_identical_materials)
   std::vector<uint8_t> cl_dist;
 };
 
@@ -264,16 +266,76 @@ register_primary_species(HostConfig & H, uint64_t n, const mtb_ion * ions, size_
 }
 
 // Fills T and every non-pointer field of P.  Pointer fields of P are left for the caller.
-inline int
-build_host_tables(const HostConfig & H, HostTables & T, LaunchParams & P, std::string & err)
+// Layer stacks repeat materials (inputs/samplelayers_zro2_multilayer.in: 50 layers of one ZrO2): identical materials
+// (density, tag, element list) are folded into one, so that such a stack has ONE material on the device — no layer
+// search at all (LaunchParams::one_material), class tables of one material instead of fifty.  Only for solid/layered
+// samples: in the wire and clusters geometries the material index itself carries meaning.  map[i] = device material
+// of input material i.
+inline std::vector<int>
+fold_identical_materials(HostConfig & H)
 {
-  const mtb_config & c = H.cfg;
+  const int nm = (int)H.materials.size();
+  std::vector<int> map(nm);
+  for (int i = 0; i < nm; ++i)
+    map[i] = i;
+  if (H.geom.kind != MTB_GEOM_SOLID && H.geom.kind != MTB_GEOM_LAYERS)
+    return map;
+  auto same = [&H](const mtb_material & a, const mtb_material & b) {
+    if (a.rho != b.rho || a.tag != b.tag || a.n_elements != b.n_elements)
+      return false;
+    for (int j = 0; j < a.n_elements; ++j)
+    {
+      const mtb_element & x = H.elements[a.first_element + j];
+      const mtb_element & y = H.elements[b.first_element + j];
+      if (x.Z != y.Z || x.m != y.m || x.t != y.t || x.Edisp != y.Edisp || x.Elbind != y.Elbind)
+        return false;
+    }
+    return true;
+  };
+  std::vector<mtb_material> mats;
+  std::vector<mtb_element> els;
+  std::vector<int> first_input; // input index of the first occurrence
+  for (int i = 0; i < nm; ++i)
+  {
+    int found = -1;
+    for (size_t k = 0; k < first_input.size() && found < 0; ++k)
+      if (same(H.materials[first_input[k]], H.materials[i]))
+        found = (int)k;
+    if (found < 0)
+    {
+      found = (int)mats.size();
+      mtb_material m = H.materials[i];
+      m.first_element = (int)els.size();
+      els.insert(els.end(), H.elements.begin() + H.materials[i].first_element,
+                 H.elements.begin() + H.materials[i].first_element + H.materials[i].n_elements);
+      mats.push_back(m);
+      first_input.push_back(i);
+    }
+    map[i] = found;
+  }
+  if ((int)mats.size() < nm)
+  {
+    H.materials.swap(mats);
+    H.elements.swap(els);
+  }
+  else
+    first_input.clear();
+  H.first_input_material = first_input;
+  return map;
+}
+
+inline int
+build_host_tables(const HostConfig & H_in, HostTables & T, LaunchParams & P, std::string & err)
+{
   std::memset(&P, 0, sizeof(P));
-  if (H.materials.empty())
+  if (H_in.materials.empty())
   {
     err = "mtb_set_materials has not been called";
     return MTB_EINVAL;
   }
+  HostConfig H = H_in;
+  T.mat_map = fold_identical_materials(H);
+  const mtb_config & c = H.cfg;
   P.tmin = (float)c.tmin;
   P.tau = (float)c.tau;
   P.cw = (float)c.cw;
@@ -332,7 +394,7 @@ build_host_tables(const HostConfig & H, HostTables & T, LaunchParams & P, std::s
     d.n_elem = m.n_elements;
     d.first_elem = m.first_element;
     d.tag = m.tag;
-    d.user_index = (int32_t)i;
+    d.user_index = H.first_input_material.empty() ? (int32_t)i : (int32_t)H.first_input_material[i];
   }
   T.ionz.assign(MTB_NZ + 1, DevIonZ());
   std::memset(T.ionz.data(), 0, sizeof(DevIonZ) * T.ionz.size());
@@ -438,6 +500,7 @@ build_host_tables(const HostConfig & H, HostTables & T, LaunchParams & P, std::s
   P.n_tclass = (int32_t)nt;
   P.n_elements = (int32_t)T.elements.size();
   P.n_materials = (int32_t)T.materials.size();
+  P.n_input_materials = (int32_t)T.mat_map.size();
   if (P.n_pclass + SPECIES_CLASS0 > SPECIES_MASK)
   {
     err = "too many elements";
@@ -466,7 +529,7 @@ build_host_tables(const HostConfig & H, HostTables & T, LaunchParams & P, std::s
       d += H.layer_thickness[i]; // same running sum as sample_layers.C:32-37
       T.layer_cum.push_back(d);
       // a position beyond the last interface belongs to the last material (sample_layers.C:40-41)
-      T.layer_mat.push_back(std::min(i, P.n_materials - 1));
+      T.layer_mat.push_back(T.mat_map[std::min(i, (int)T.mat_map.size() - 1)]);
     }
     P.n_layers = nl;
     extent = std::max(extent, d);

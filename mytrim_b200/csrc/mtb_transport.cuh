@@ -94,8 +94,10 @@ enum Feature : uint32_t
   F_VACMODEL = 1u << 8,  // vacancy model chosen at run time (else vacancies_created++)
   F_TALLY_RT = 1u << 9,  // tallies switched at run time within kTally (else exactly kTally)
   F_DIAG = 1u << 10,     // stack high-water mark
-  F_MONO = 1u << 11      // the sample is one material made of one element (solid or layers of it): no geometry
+  F_MONO = 1u << 11,     // the sample is one material made of one element (solid or layers of it): no geometry
                          // look-up, no vacuum test, no target pick, no loop over elements in the stopping
+  F_NOREC = 1u << 12     // the launch asked for no per-primary records: the record flag of the ion word, its test on
+                         // every exit of an ion and the record writes are compiled out (3 registers less: 8 CTAs/SM)
 };
 
 template <uint32_t F, uint32_t TALLY>
@@ -120,6 +122,7 @@ typedef TraitsT<kFeatFast, kTallyFast> TraitsFast;
 typedef TraitsT<kFeatFast | F_SHARE, kTallyFast> TraitsFastShare;
 typedef TraitsT<kFeatMono, kTallyFast> TraitsMono;
 typedef TraitsT<kFeatMono | F_SHARE, kTallyFast> TraitsMonoShare;
+typedef TraitsT<kFeatMono | F_NOREC, kTallyFast> TraitsMonoNoRec; // what bench.py times: TrimVacCount tallies only
 typedef TraitsT<kFeatClusters, kTallyClusters> TraitsClusters;
 typedef TraitsT<kFeatClusters | F_SHARE, kTallyClusters> TraitsClustersShare;
 typedef TraitsT<kFeatLayers, kTallyAll> TraitsLayers;
@@ -142,13 +145,14 @@ enum Variant
   VARIANT_LAYERS,
   VARIANT_GENERIC,
   VARIANT_MONO,
+  VARIANT_MONO_NOREC, // chosen per launch (mtb_engine.cu: launch_transport), never by pick_variant
   VARIANT_COUNT
 };
 
 inline uint32_t
 variant_features(Variant v)
 {
-  return v == VARIANT_FAST ? kFeatFast : v == VARIANT_MONO ? kFeatMono : v == VARIANT_CLUSTERS ? kFeatClusters : v == VARIANT_LAYERS ? kFeatLayers : kFeatGeneric;
+  return v == VARIANT_FAST ? kFeatFast : v == VARIANT_MONO ? kFeatMono : v == VARIANT_MONO_NOREC ? (kFeatMono | F_NOREC) : v == VARIANT_CLUSTERS ? kFeatClusters : v == VARIANT_LAYERS ? kFeatLayers : kFeatGeneric;
 }
 
 // Features a configuration needs (F_CUSTOM is decided per primary: variants without it hand
@@ -639,7 +643,10 @@ MTB_HD void
 finish_ion(const LaunchParams & P, const BlockCtx & S, const Lane & L, const float4_t * rows, int state, double x, double y,
            double z)
 {
-  if (L.packed & FLAG_PRIMARY) // set only when records were asked for (one test on every exit of an ion)
+#ifndef MTB_NO_RECORDS
+#define MTB_NO_RECORDS 0 // experiment: per-primary records compiled out (profiles/r02_variant_sweeps.md)
+#endif
+  if (!MTB_NO_RECORDS && !TR::has(F_NOREC) && (L.packed & FLAG_PRIMARY)) // set only when records were asked for (one test on every exit of an ion)
   {
     mtb_record & r = P.records[L.prim];
     r.pos[0] = x;
@@ -751,10 +758,11 @@ vacancy_creation(const LaunchParams & P, const BlockCtx & S, Lane & L, const Dev
 // close a subtree of a cascade (the whole cascade unless lanes shared it): per-primary record and
 // block totals.  Record counters are accumulated atomically because several lanes may have worked
 // on the same primary; records are zeroed before the launch.
+template <class TR>
 MTB_HD void
 close_subtree(const LaunchParams & P, const BlockCtx & S, Lane & L, uint32_t n_prim)
 {
-  if (P.records)
+  if (!TR::has(F_NOREC) && P.records)
   {
     mtb_record & r = P.records[L.prim];
     MTB_ATOMIC_ADD(&r.Eel, L.casEel);
@@ -1045,7 +1053,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       {
         if (open)
         {
-          close_subtree(P, S, L, TR::kShare ? cas_prim : 1u);
+          close_subtree<TR>(P, S, L, TR::kShare ? cas_prim : 1u);
           open = false;
         }
         while (!no_more)
@@ -1053,12 +1061,13 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           unsigned long long idx;
           if (EVENTS)
           {
-            if (started || lane_global != 0)
+            // event mode: lane i follows ion i of the batch (mtb_trim_one: a batch of one)
+            if (started || lane_global >= P.n_primaries)
             {
               no_more = true;
               break;
             }
-            idx = 0;
+            idx = lane_global;
           }
 #if MTB_DEVICE_CODE
           else if (TR::kShare)
@@ -1087,6 +1096,18 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           const mtb_ion & src = P.primaries ? P.primaries[idx] : P.beam;
           const int src_Z = src.Z;
           const float src_m = (float)src.m;
+          {
+            // A primary the tables cannot describe (Z outside 1..92, m <= 0, negative or non-finite energy, no
+            // direction) would index the Z tables out of bounds or fly as NaN: it is skipped and counted in the
+            // upper half of the error word; the run then fails with MTB_EINVAL (mtb_engine.cu: sync_and_check).
+            const double d2 = src.dir[0] * src.dir[0] + src.dir[1] * src.dir[1] + src.dir[2] * src.dir[2];
+            if ((unsigned int)(src_Z - 1) >= (unsigned int)MTB_NZ || !(src_m > 0.0f && src_m < 1.0e6f) ||
+                !(src.E >= 0.0 && src.E <= 1.0e15) || !(d2 > 0.0 && d2 < 1.0e300))
+            {
+              MTB_ATOMIC_ADD(&P.u64[CNT_ERROR], 1ull << 32);
+              continue;
+            }
+          }
           const int cls = find_class(P, S, src_Z, src_m);
           if (!TR::kCustom && cls < 0)
           {
@@ -1112,8 +1133,8 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           L.dsafe = 0.0f;
           L.ic = 0;
           L.prim = (uint32_t)idx;
-          L.uid = EVENTS ? P.single_uid : P.first_index + idx;
-          L.packed = SPECIES_PRIMARY | (((uint32_t)src.gen & GEN_MASK) << GEN_SHIFT) | (P.records ? (uint32_t)FLAG_PRIMARY : 0u);
+          L.uid = EVENTS ? (P.uid_list ? P.uid_list[idx] : P.single_uid + idx) : P.first_index + idx;
+          L.packed = SPECIES_PRIMARY | (((uint32_t)src.gen & GEN_MASK) << GEN_SHIFT) | ((!TR::has(F_NOREC) && P.records) ? (uint32_t)FLAG_PRIMARY : 0u);
           L.tag = src.tag;
           L.pZ = src_Z;
           L.pm = src_m;
@@ -1443,7 +1464,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     {
       if (n_events < P.events_cap)
       {
-        mtb_event & ev = P.events[n_events];
+        mtb_event & ev = P.events[(size_t)lane_global * P.events_cap + n_events];
         ev.pka_pos[0] = MTB_AHEAD_X; ev.pka_pos[1] = MTB_AHEAD_Y; ev.pka_pos[2] = MTB_AHEAD_Z;
         ev.pka_dir[0] = L.dx; ev.pka_dir[1] = L.dy; ev.pka_dir[2] = L.dz;
         ev.pka_E = L.E;
@@ -1456,7 +1477,23 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
         ev.ls = (double)ls;
         ev.dee = dee;
         ev.den = den;
-        ev.material = M.user_index;
+        // the hooks see the MaterialBase object of the LAYER (sample_layers.C:26-49), also where identical
+        // materials of a stack were folded into one on the device
+        int user_material = M.user_index;
+        if (!TR::has(F_MONO) && P.geom_kind == MTB_GEOM_LAYERS && P.n_input_materials != P.n_materials)
+        {
+          int lo = 0, hi = P.n_layers - 1;
+          while (lo < hi)
+          {
+            const int mid = (lo + hi) >> 1;
+            if (L.px < S.layer_cum[mid])
+              hi = mid;
+            else
+              lo = mid + 1;
+          }
+          user_material = lo < P.n_input_materials ? lo : P.n_input_materials - 1;
+        }
+        ev.material = user_material;
         ev.element = nn;
         ev.material_tag = mtag;
         ev.pka_state = state;
@@ -1576,6 +1613,11 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
 
   if (!EVENTS)
     MTB_ATOMIC_MAX(&S.blk_u64[CNT_STACKMAX], (unsigned long long)sp_max);
+  else if (P.event_counts)
+  {
+    if (lane_global < P.n_primaries)
+      P.event_counts[lane_global] = (uint32_t)(n_events < 0xFFFFFFFFull ? n_events : 0xFFFFFFFFull);
+  }
   else if (lane_global == 0)
     P.u64[CNT_EVENTS_N] = n_events;
 }

@@ -245,10 +245,13 @@ struct LaunchParams
   unsigned long long range_cap;
   StackEntry * stacks;          // [lanes][MTB_STACK_DEPTH]
   // single-ion event mode
-  mtb_event * events;
-  unsigned long long events_cap;
-  uint64_t single_uid;
+  mtb_event * events;            // event mode: lane i writes events[i * events_cap ...]
+  unsigned long long events_cap; // per ion
+  uint64_t single_uid;           // event mode: stream id of ion i = single_uid + i
+  const uint64_t * uid_list;     // event mode: explicit stream ids (else single_uid + i)
+  uint32_t * event_counts;       // event mode with several ions (mtb_trim_many): collisions of ion i (may exceed events_cap)
   int32_t one_material;         // solid/layered sample whose layers are all the same material (host flag: no layer search)
+  int32_t n_input_materials;    // materials the caller passed (identical ones are folded on the device, mtb_tables.h)
 };
 
 // offsets inside the u64 block

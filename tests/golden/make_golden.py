@@ -237,7 +237,16 @@ def outputs():
                                 evac=hist[hist[:, 2] > 0].astype(np.int64), shape=hist[:, :2].max(axis=0).astype(np.int64) + 1,
                                 vacancies=int(rec["vacancies"].sum()))
         else:
-            np.savez_compressed(os.path.join(HERE, "ref_output_ranges_%s.npz" % name), n=n, ranges_dat=np.array(hist))
+            # <base>_ranges.dat of 1e5 primaries has 2e5 lines: keep its header, bin geometry, column totals and the
+            # quantiles of every column's distribution
+            rows = [l.split() for l in str(hist).strip().split("\n")]
+            table = np.array([[float(v) for v in r] for r in rows[1:]])
+            probs = (np.arange(2048) + 0.5) / 2048
+            cdf = np.cumsum(table[:, 1:], axis=0) / table[:, 1:].sum(axis=0)
+            q = np.array([table[np.searchsorted(cdf[:, k], probs), 0] for k in range(cdf.shape[1])])
+            np.savez_compressed(os.path.join(HERE, "ref_output_ranges_%s.npz" % name), n=n, header=" ".join(rows[0]),
+                                nbin=len(table), x_min=table[0, 0], bin_width=table[1, 0] - table[0, 0],
+                                totals=table[:, 1:].sum(axis=0), quantiles=q)
 
 
 def published():

@@ -226,7 +226,24 @@ hs_run(hs_engine * e, uint64_t n, const mtb_ion * primaries, uint64_t seed, uint
   else
     run_variant(v);
   hs_flush(e);
-  return P.u64[CNT_ERROR] ? MTB_ESTACK : MTB_OK;
+  const unsigned long long bad = P.u64[CNT_ERROR];
+  P.u64[CNT_ERROR] = 0;
+  if (bad >> 32)
+    e->err = "primaries were skipped";
+  return (bad >> 32) ? MTB_EINVAL : (bad ? MTB_ESTACK : MTB_OK);
+}
+
+// what build_host_tables made of the sample: {device materials, one_material, mono, layers}
+int
+hs_sample_info(hs_engine * e, int32_t * out4)
+{
+  if (int rc = hs_prepare(e))
+    return rc;
+  out4[0] = e->P.n_materials;
+  out4[1] = e->P.one_material;
+  out4[2] = e->P.mono;
+  out4[3] = e->P.n_layers;
+  return MTB_OK;
 }
 
 void
@@ -399,7 +416,7 @@ hs_stopping(hs_engine * e, int material, size_t n, const int32_t * Z1, const dou
   for (size_t i = 0; i < n; ++i)
   {
     const ProjClass pr = make_proj_class(S.ionz[Z1[i]], Z1[i], (float)m1[i]);
-    out[i] = (double)material_stopping(pr, S.lowstop + Z1[i] * e->P.n_zslots, e->P.materials[material], e->P.elements,
+    out[i] = (double)material_stopping(pr, S.lowstop + Z1[i] * e->P.n_zslots, e->P.materials[e->T.mat_map[material]], e->P.elements,
                                        (float)E[i], fsqrt((float)E[i] * pr.inv_km));
   }
   return MTB_OK;

@@ -486,3 +486,56 @@ def test_per_ion_parity_fp32_replay_against_fp64_oracle(name, n):
     assert s["pos_outliers"] <= 2e-4 * s["joined"] + 2 and s["energy_outliers"] == 0, s
     assert s["median_rel_pos"] < 0.1 * TOL, s
     assert r["cascades_identical"] >= 0.9 * r["n"] and r["pos_outliers"] == 0, r
+
+
+def test_identical_layer_materials_are_folded():
+    """inputs/samplelayers_zro2_multilayer.in stacks 50 layers of one ZrO2: the host folds identical materials, the device
+    sees ONE material (no layer search, class tables of one material); a stack of different materials keeps them, and a
+    repeated material in such a stack maps onto its first occurrence (mtb_tables.h: fold_identical_materials)."""
+    import ctypes as C
+    from tests.golden.make_golden import STACK_CASE
+    info = (C.c_int32 * 4)()
+    with util.HostSimEngine(tally_mask=capi.TALLY_VAC_DEPTH) as hs:
+        util.setup_engine(hs, "xe_on_zro2_500keV")
+        assert hs._lib.hs_sample_info(hs._h, info) == 0
+        assert list(info) == [1, 1, 0, 50]
+    with util.HostSimEngine(tally_mask=capi.TALLY_VAC_DEPTH) as hs:
+        util.setup_engine(hs, "cu_on_cu_10keV")
+        assert hs._lib.hs_sample_info(hs._h, info) == 0 and list(info)[:3] == [1, 1, 1]
+    with util.HostSimEngine(tally_mask=capi.TALLY_VAC_DEPTH) as hs:
+        util.setup_engine(hs, STACK_CASE)
+        assert hs._lib.hs_sample_info(hs._h, info) == 0 and list(info) == [4, 0, 0, 4]
+    # A B A B: two device materials, and the same cascades as the unfolded oracle
+    stack = dict(ion=(29, 63.546, 2.0e4), materials=[util.CU, util.FE, util.CU, util.FE], thicknesses=[30.0, 40.0, 30.0, 500.0])
+    cfg = dict(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS)
+    with util.HostSimEngine(**cfg) as hs, util.OracleEngine(util.ORC_RNG_PHILOX, **cfg) as orc:
+        util.setup_engine(hs, stack)
+        util.setup_engine(orc, stack)
+        assert hs._lib.hs_sample_info(hs._h, info) == 0 and list(info) == [2, 0, 0, 4]
+        ions = util.primaries_for(stack, 200)
+        rh, ro = hs.run(ions, seed=4, records=True), orc.run(ions, seed=4, records=True)
+        r = util.compare_records(rh, ro, ions)
+        assert r["cascades_identical"] >= 198 and r["pos_outliers"] == 0, r
+        # getrstop of input material 2 (= the folded Cu) and 3 (= Fe)
+        E = np.array([1e3, 1e5])
+        assert np.allclose(hs.stopping(2, 29, 63.546, E), orc.stopping(2, 29, 63.546, E), rtol=1e-5)
+        assert np.allclose(hs.stopping(3, 29, 63.546, E), orc.stopping(3, 29, 63.546, E), rtol=1e-5)
+
+
+def test_invalid_primaries_are_skipped_and_reported():
+    """Host twin of the device-side validation: Z outside 1..92, m <= 0, NaN energy and a zero direction never reach the
+    Z-indexed tables; the run reports MTB_EINVAL and the other primaries are followed."""
+    bad = capi.make_ions(32, 29, 63.546, 1e3)
+    bad["Z"][3] = 0
+    bad["Z"][7] = 200
+    bad["m"][11] = -1.0
+    bad["E"][13] = np.nan
+    bad["dir"][17] = 0.0
+    with util.HostSimEngine(tally_mask=capi.TALLY_VAC_DEPTH) as hs:
+        util.setup_engine(hs, "cu_on_cu_1keV")
+        with pytest.raises(capi.MytrimError) as e:
+            hs.run(bad, seed=1)
+        assert e.value.code == capi.EINVAL
+        assert hs.counters()["primaries"] == 27
+        hs.run(capi.make_ions(8, 29, 63.546, 1e3), seed=1)
+        assert hs.counters()["primaries"] == 35

@@ -227,3 +227,80 @@ def test_mytrim_uo2_outputs_do_not_depend_on_chunks_or_gpus(tmp_path):
             assert open(str(tmp_path / "one") + "." + ext).read() == open(str(tmp_path / "two") + "." + ext).read(), ext
         assert t_two["collision_steps"] == t_one["collision_steps"]
         assert abs(e_two[0] - e_one[0]) <= 1e-9 * e_one[0]
+
+
+def _runmytrim(apps, tmp_path, base, ion, layer, n, out_type):
+    inp = {"mytrim": {"options": {"seed": 2344}, "ion": dict(ion, number=n), "sample": {"layers": [layer]},
+                      "output": {"base": str(tmp_path / base), "type": out_type}}}
+    out = subprocess.run([os.path.join(apps, "runmytrim")], input=json.dumps(inp), capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return float([l for l in out.stderr.split("\n") if l.startswith("Vacancies/ion")][0].split(":")[1])
+
+
+def test_runmytrim_vacenergycount_file_against_reference_output(tmp_path):
+    """`"type": "vacenergycount"` (validation/c_on_w/input.json: 1 MeV C into W): the <base>_evac.dat the GPU driver's
+    TrimVacEnergyCount::writeOutput writes against the file the UNMODIFIED reference wrote for 2000 primaries
+    (TrimVacEnergyCount.C:70-81; fixture tests/golden/ref_output_evac_c_on_w_1MeV.npz): same line format, vacancies per
+    ion, and the ln(E) x depth histogram through both of its marginals."""
+    apps = _apps()
+    n = 4000
+    vpi = _runmytrim(apps, tmp_path, "cw", {"Z": 6, "mass": 12.0, "energy": 1.0e6},
+                     {"thickness": 10000, "rho": 19.35, "elements": [{"Z": 74, "mass": 183.85, "fraction": 1}]}, n,
+                     "vacenergycount")
+    text = open(tmp_path / "cw_evac.dat").read()
+    rows = [[]]                                                            # "E x count" lines, a blank line closes an E row
+    for l in text.split("\n")[:-1]:
+        if l.strip():
+            rows[-1].append(l.split())
+        else:
+            rows.append([])
+    rows = rows[:-1] if not rows[-1] else rows
+    assert all(len(r) == 3 for b in rows for r in b)
+    assert all(int(r[0]) == e and int(r[1]) == x for e, b in enumerate(rows) for x, r in enumerate(b))
+    assert not any(rows[e] for e in range(3))                             # ln E < 3 cannot displace an atom (Edisp 25 eV)
+    ref = np.load(os.path.join(util.GOLDEN, "ref_output_evac_c_on_w_1MeV.npz"))
+    shape = np.maximum(ref["shape"], [len(rows), max(len(b) for b in rows)]).astype(int)
+    mine = np.zeros(shape, dtype=np.float64)
+    for e, b in enumerate(rows):
+        mine[e, :len(b)] = [float(r[2]) for r in b]
+    theirs = np.zeros(shape, dtype=np.float64)
+    theirs[ref["evac"][:, 0], ref["evac"][:, 1]] = ref["evac"][:, 2]
+    nref = float(ref["n"])
+    assert abs(vpi - float(ref["vacancies"]) / nref) < 0.02 * vpi, (vpi, float(ref["vacancies"]) / nref)
+    assert abs(mine.sum() / n - theirs.sum() / nref) < 0.02 * theirs.sum() / nref
+    # marginal over depth: vacancies per ion in every ln(E) row (rows hold 1e2..5e5 counts)
+    pe_m, pe_t = mine.sum(axis=1) / n, theirs.sum(axis=1) / nref
+    assert np.abs(pe_m - pe_t).sum() < 0.03 * pe_t.sum(), (pe_m, pe_t)
+    # marginal over energy: depth profile in 1000 A slabs
+    slab = 1000
+    k = shape[1] // slab
+    dm = mine[:, :k * slab].sum(axis=0).reshape(k, slab).sum(axis=1) / n
+    dt = theirs[:, :k * slab].sum(axis=0).reshape(k, slab).sum(axis=1) / nref
+    assert np.abs(dm - dt).sum() < 0.06 * dt.sum(), np.abs(dm - dt).sum() / dt.sum()
+
+
+def test_runmytrim_range_file_against_reference_output(tmp_path):
+    """`"type": "range"` (validation/cu_on_cu/cu_on_cu.json: 150 keV Cu into Cu, primaries only, NRT damage): the
+    <base>_ranges.dat of the GPU driver against the file the UNMODIFIED reference wrote for 1e5 primaries
+    (TrimRange.C:66-121; fixture ref_output_ranges_cu_on_cu_150keV.npz): header, the bin-count heuristic, entries per
+    primary and the distribution of the column (KS distance on its quantiles).  20 000 primaries put 4.4e6 entries into
+    the range list: more than one device list holds, i.e. the chunked hand-over of TrimRange is exercised."""
+    apps = _apps()
+    n = 20000
+    vpi = _runmytrim(apps, tmp_path, "cu", {"Z": 29, "mass": 63.546, "energy": 150000},
+                     {"thickness": 1000, "rho": 8.92, "elements": [{"Z": 29, "mass": 63.546, "fraction": 1}]}, n, "range")
+    lines = open(tmp_path / "cu_ranges.dat").read().strip().split("\n")
+    ref = np.load(os.path.join(util.GOLDEN, "ref_output_ranges_cu_on_cu_150keV.npz"))
+    assert lines[0] == str(ref["header"])
+    table = np.array([[float(v) for v in l.split()] for l in lines[1:]])
+    total = table[:, 1].sum()
+    per_primary_ref = float(ref["totals"][0]) / float(ref["n"])
+    assert abs(total / n - per_primary_ref) < 0.01 * per_primary_ref, (total / n, per_primary_ref)
+    assert abs(len(table) - (total / 100.0 + 1)) <= 2            # nbin = xwidth / min(xwidth * 100 / samples, xwidth / 10) + 1
+    cdf = np.cumsum(table[:, 1]) / total
+    q = ref["quantiles"][0]
+    F = np.interp(q, table[:, 0], cdf)
+    D = float(np.abs(F - (np.arange(len(q)) + 0.5) / len(q)).max())
+    print("ranges: %d entries, %.1f per primary (reference %.1f), KS distance %.4f, vacancies/ion %.1f" % (
+        total, total / n, per_primary_ref, D, vpi))
+    assert D < 0.015, D   # the FP64 oracle with 20 000 Philox cascades is at 0.007

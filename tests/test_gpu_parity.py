@@ -309,7 +309,7 @@ def test_statistics_against_reference_golden(name):
 @pytest.mark.parametrize("name", ["cu_on_cu_10keV", "cu_on_cu_1keV", "h_on_fe_100keV", "he_on_fe_100keV", "c_on_w_1MeV",
                                   "xe_on_zro2_500keV"])
 def test_north_star_statistical_criterion(name):
-    """BASELINE.json's statistical criterion at full size — 1e6 Cu->Cu 10 keV cascades, and 4e3..1e6 cascades of the
+    """BASELINE.json's statistical criterion at full size — 1e6 Cu->Cu 10 keV cascades, and 1e5..1e6 cascades of the
     other configurations — on the GPU against as many cascades of the UNMODIFIED reference (distinct 32-bit seeds),
     summarised in tests/golden/ref_stats_<name>.npz (quantiles / exact histograms; tests/util.py::ks_against_summary):
     two-sample KS p > 0.01 and means within 1 % on projected range, lateral range, electronic loss (= energy
@@ -325,9 +325,9 @@ def test_north_star_statistical_criterion(name):
     assert len(res) == 7
     for obs, (mean, ref_mean, D, p) in res.items():
         se = np.sqrt(2.0 * float(summary["m_" + obs][1]) / n)
-        # the north-star level (p > 0.01) for the headline configuration; 0.001 for the other five, whose 35
-        # observable tests would otherwise raise a false alarm once in three runs of an unbiased kernel
-        assert p > (0.01 if name == "cu_on_cu_10keV" else 0.001), (name, obs, D, p)
+        # the north-star level for every configuration (the run is deterministic: fixed seed, scheduling-independent
+        # streams — it either passes always or never)
+        assert p > 0.01, (name, obs, D, p)
         assert abs(mean - ref_mean) <= max(0.01 * abs(ref_mean), 4.0 * se), (name, obs, mean, ref_mean)
 
 
@@ -639,6 +639,22 @@ def test_error_paths_return_status_codes():
         st = C.c_int32()
         rc = lib.mtb_trim_one(eng._h, ion.ctypes.data, 1, 1, C.byref(st), ev.ctypes.data, 2, C.byref(n))
         assert rc == capi.ECAPACITY and n.value > 2
+        # primaries the tables cannot describe are skipped on the device and reported: the good
+        # ones of the batch are followed, the handle stays usable
+        bad = capi.make_ions(64, 29, 63.546, 1e4)
+        bad["Z"][3] = 0
+        bad["Z"][7] = 200
+        bad["m"][11] = -1.0
+        bad["E"][13] = np.nan
+        bad["dir"][17] = 0.0
+        with pytest.raises(capi.MytrimError) as e:
+            eng.run(bad, seed=1)
+        assert e.value.code == capi.EINVAL and "5 primaries were skipped" in str(e.value)
+        assert eng.counters()["primaries"] == 59
+        eng.run(capi.make_ions(64, 29, 63.546, 1e4), seed=1)
+        assert eng.counters()["primaries"] == 59 + 64
+        with pytest.raises(capi.MytrimError):
+            eng.run_beam(8, capi.make_ions(1, 0, 63.546, 1e4)[0], seed=1)     # template ion with Z = 0
     cfg = capi.default_config(potential=9)
     h = C.c_void_p()
     assert lib.mtb_create(C.byref(cfg), C.byref(h)) == capi.EINVAL
@@ -662,3 +678,31 @@ def test_engines_with_different_table_sizes_coexist():
             assert len(ev) > 0
             r1 = big.run(ions, seed=3, records=True)
     assert np.array_equal(r0["steps"], r1["steps"]) and np.array_equal(r0["pos"], r1["pos"])
+
+
+def test_trim_many_equals_trim_one_per_ion():
+    """mtb_trim_many (one launch, one lane per ion: the façade's hand-over of a whole generation of queued ions) reports
+    for every ion exactly the events mtb_trim_one reports for it with the same stream id; ions with more collisions
+    than the buffer holds report their count and a valid prefix."""
+    from tests import parity_cases
+    cfg = dict(tally_mask=0)
+    with capi.Engine(**cfg) as eng:
+        ions = parity_cases.setup_case(eng, "uo2_fission_like", 70)
+        ions["E"][:6] = [30.0, 80.0, 300.0, 2e3, 5e4, 3.0]      # very short and long trajectories in one batch
+        K = 64
+        fin, st, cnt, ev = eng.trim_many(ions, 99, 1000, K)
+        assert (cnt > 0).all() and (cnt > K).any() and (cnt <= K).any()
+        for i in range(len(ions)):
+            f1, s1, e1 = eng.trim_one(ions[i], 99, 1000 + i, capacity=1 << 16)
+            assert len(e1) == cnt[i], i
+            m = min(K, int(cnt[i]))
+            assert ev[i, :m].tobytes() == e1[:m].tobytes(), i      # bit-identical event records
+            if cnt[i] <= K:
+                assert st[i] == s1 and fin[i].tobytes() == f1.tobytes(), i
+        # the long ones again with explicit stream ids and a buffer of the reported size
+        longer = np.nonzero(cnt > K)[0]
+        fin2, st2, cnt2, ev2 = eng.trim_many(ions[longer], 99, 0, int(cnt[longer].max()), uids=1000 + longer)
+        assert np.array_equal(cnt2, cnt[longer])
+        for k, i in enumerate(longer):
+            f1, s1, e1 = eng.trim_one(ions[i], 99, 1000 + i, capacity=1 << 16)
+            assert ev2[k, :cnt2[k]].tobytes() == e1.tobytes() and st2[k] == s1 and fin2[k].tobytes() == f1.tobytes()
