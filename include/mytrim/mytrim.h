@@ -27,6 +27,7 @@
 #include <memory>
 #include <queue>
 #include <random>
+#include <stdexcept>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -79,6 +80,16 @@ pow(const T & x)
 
 namespace MyTRIM_NS
 {
+
+/// Thrown by the façade where the reference signature leaves no room for a status (TrimBase::trim(),
+/// MaterialBase::getrstop(), SimconfType's table reader): no GPU, a sample or hook set the device cannot run, a CUDA
+/// error.  what() carries mtb_last_error().  Nothing in the library calls exit().
+class EngineError : public std::runtime_error
+{
+public:
+  explicit EngineError(const std::string & what) : std::runtime_error(what) {}
+};
+
 
 // ---- functions.h --------------------------------------------------------------------------
 inline void v_cross(const Real * a, const Real * b, Real * c)

@@ -139,8 +139,7 @@ SimconfType::loadTables()
       e >> z >> s.sym >> s.name;
     if (!a || !l)
     {
-      std::cerr << "Error reading ZBL tables from " << _data_dir << std::endl;
-      std::exit(1); // simconf.C:139-148
+      throw EngineError("Error reading ZBL tables from " + _data_dir); // the reference exits here (simconf.C:139-148)
     }
   }
   if (n)
@@ -338,8 +337,7 @@ MaterialBase::getrstop(const IonBase * pka)
     cfg.device = _simconf->device;
     if (mtb_create(&cfg, &_engine) != MTB_OK)
     {
-      std::cerr << "MaterialBase::getrstop: " << mtb_last_error() << std::endl;
-      std::exit(1);
+      throw EngineError(std::string("MaterialBase::getrstop: ") + mtb_last_error());
     }
     pushTables(_engine, _simconf);
     std::vector<mtb_element> els;
@@ -352,8 +350,7 @@ MaterialBase::getrstop(const IonBase * pka)
     m.first_element = 0;
     if (mtb_set_materials(_engine, 1, &m, (int)els.size(), els.data()) != MTB_OK)
     {
-      std::cerr << "MaterialBase::getrstop: " << mtb_last_error() << std::endl;
-      std::exit(1);
+      throw EngineError(std::string("MaterialBase::getrstop: ") + mtb_last_error());
     }
     _engine_elements = _element;
     _engine_rho = _rho;
@@ -363,8 +360,7 @@ MaterialBase::getrstop(const IonBase * pka)
   double out = 0.0;
   if (mtb_stopping(_engine, 0, 1, &Z, &m1, &E, &out) != MTB_OK)
   {
-    std::cerr << "MaterialBase::getrstop: " << mtb_last_error() << std::endl;
-    std::exit(1);
+    throw EngineError(std::string("MaterialBase::getrstop: ") + mtb_last_error());
   }
   return out;
 }
@@ -1037,8 +1033,7 @@ TrimBase::trim(IonBase * pka, std::queue<IonBase *> & recoils)
   recoil_queue_ptr = &recoils;
   if (!ensureEngine(false))
   {
-    std::cerr << "TrimBase::trim: " << _error << std::endl;
-    std::exit(1);
+    throw EngineError("TrimBase::trim: " + _error);
   }
   mtb_ion ion;
   ionToAbi(pka, ion);
@@ -1052,8 +1047,7 @@ TrimBase::trim(IonBase * pka, std::queue<IonBase *> & recoils)
   {
     if (!followQueued(pka, ion, recoils))
     {
-      std::cerr << "TrimBase::trim: " << _error << std::endl;
-      std::exit(1);
+      throw EngineError("TrimBase::trim: " + _error);
     }
     hit = _followed.find(pka);
   }

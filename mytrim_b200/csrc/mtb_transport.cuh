@@ -896,6 +896,21 @@ stack_depth(uint32_t cursor)
   return (int)((cursor & MTB_STACK_DEPTH_BITS) >> 6);
 }
 
+// A primary the tables cannot describe (out of line: the test runs once per cascade and must not disturb the
+// register allocation and the layout of the collision loop).
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+bool
+primary_is_invalid(const mtb_ion & src)
+{
+  const double d2 = src.dir[0] * src.dir[0] + src.dir[1] * src.dir[1] + src.dir[2] * src.dir[2];
+  return (unsigned int)(src.Z - 1) >= (unsigned int)MTB_NZ || !(src.m > 0.0 && src.m < 1.0e6) ||
+         !(src.E >= 0.0 && src.E <= 1.0e15) || !(d2 > 0.0 && d2 < 1.0e300);
+}
+
 // Suspend an ion: on the lane's private stack, or — when lanes are idle — in the shared pool.
 template <class TR>
 MTB_HD void
@@ -1100,9 +1115,9 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
             // A primary the tables cannot describe (Z outside 1..92, m <= 0, negative or non-finite energy, no
             // direction) would index the Z tables out of bounds or fly as NaN: it is skipped and counted in the
             // upper half of the error word; the run then fails with MTB_EINVAL (mtb_engine.cu: sync_and_check).
-            const double d2 = src.dir[0] * src.dir[0] + src.dir[1] * src.dir[1] + src.dir[2] * src.dir[2];
-            if ((unsigned int)(src_Z - 1) >= (unsigned int)MTB_NZ || !(src_m > 0.0f && src_m < 1.0e6f) ||
-                !(src.E >= 0.0 && src.E <= 1.0e15) || !(d2 > 0.0 && d2 < 1.0e300))
+            // (out of line: inlined, the same test cost the north-star kernel 1.9 % — 64 more instructions around the
+            // collision loop and a different register allocation; as a call 0.25 %, profiles/r02_variant_sweeps.md)
+            if (primary_is_invalid(src))
             {
               MTB_ATOMIC_ADD(&P.u64[CNT_ERROR], 1ull << 32);
               continue;

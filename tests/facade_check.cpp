@@ -2,6 +2,9 @@
 // prints one JSON object that tests/test_gpu_facade.py compares with the oracle.  GPU only.
 #include <cstdio>
 #include <queue>
+#include <iostream>
+#include <sstream>
+#include <string>
 #include <vector>
 
 #include "mytrim/simconf.h"
@@ -181,6 +184,98 @@ main()
       delete ion;
     }
   }
+  // --- 3. TrimDefectLog, TrimHistory and SimconfType::fullTraj through the reference's queue loop (trim.h:139-175,
+  // trim.C:370-371, 421-422, 466-481): the hooks see every collision of every ion in the reference's order ---
+  {
+    SimconfType sc3;
+    sc3.seed(4242);
+    SampleSolid solid3(1000.0, 100.0, 100.0);
+    solid3.material.push_back(copper(&sc3));
+    std::ostringstream defects;
+    TrimDefectLog dl(&sc3, &solid3, defects);
+    TrimHistory hist(&sc3, &solid3);
+    const int n3 = 40;
+    long v_lines = 0, i_lines = 0, r_lines = 0, s_lines = 0, ions3 = 0, hist_followed = 0, hist_ions = 0;
+    for (int pass = 0; pass < 2; ++pass)
+    {
+      std::queue<IonBase *> q;
+      for (int i = 0; i < n3; ++i)
+      {
+        IonBase * pka = new IonBase(29, 63.546, 1.0e4);
+        pka->_gen = 0;
+        pka->_dir = Point(1, 0, 0);
+        pka->_pos = Point(0, 50, 50);
+        q.push(pka);
+        while (!q.empty())
+        {
+          IonBase * ion = q.front();
+          q.pop();
+          solid3.averages(ion);
+          if (pass == 0)
+          {
+            dl.trim(ion, q);
+            ++ions3;
+          }
+          else
+          {
+            hist.trim(ion, q);
+            ++hist_ions;
+          }
+          delete ion;
+        }
+      }
+    }
+    hist_followed = (long)hist.getHistory().size();
+    std::istringstream in(defects.str());
+    std::string line;
+    while (std::getline(in, line))
+    {
+      if (line.rfind("V ", 0) == 0) ++v_lines;
+      else if (line.rfind("I ", 0) == 0) ++i_lines;
+      else if (line.rfind("R ", 0) == 0) ++r_lines;
+      else if (line.rfind("S ", 0) == 0) ++s_lines;
+    }
+    // fullTraj: one "spawn" line per followed recoil and one state line per collision on stdout (captured here)
+    SimconfType sc4;
+    sc4.seed(99);
+    sc4.fullTraj = true;
+    SampleSolid solid4(1000.0, 100.0, 100.0);
+    solid4.material.push_back(copper(&sc4));
+    CountingTrim ct4(&sc4, &solid4);
+    std::ostringstream traj;
+    std::streambuf * old = std::cout.rdbuf(traj.rdbuf());
+    long ions4 = 0;
+    {
+      std::queue<IonBase *> q;
+      for (int i = 0; i < 5; ++i)
+      {
+        IonBase * pka = new IonBase(29, 63.546, 1.0e4);
+        pka->_gen = 0;
+        pka->_dir = Point(1, 0, 0);
+        pka->_pos = Point(0, 50, 50);
+        q.push(pka);
+        while (!q.empty())
+        {
+          IonBase * ion = q.front();
+          q.pop();
+          ct4.trim(ion, q);
+          ++ions4;
+          delete ion;
+        }
+      }
+    }
+    std::cout.rdbuf(old);
+    long spawn_lines = 0, state_lines = 0;
+    std::istringstream tin(traj.str());
+    while (std::getline(tin, line))
+      (line.rfind("spawn ", 0) == 0 ? spawn_lines : state_lines)++;
+    std::printf(" \"hooks\": {\"n\": %d, \"V\": %ld, \"I\": %ld, \"R\": %ld, \"S\": %ld, \"ions\": %ld, \"history\": %ld, "
+                "\"history_ions\": %ld, \"spawn_lines\": %ld, \"state_lines\": %ld, \"traj_followed\": %ld, "
+                "\"traj_steps\": %ld, \"traj_ions\": %ld},\n",
+                n3, v_lines, i_lines, r_lines, s_lines, ions3, hist_followed, hist_ions, spawn_lines, state_lines, ct4.followed,
+                ct4.steps, ions4);
+  }
+
   std::printf(" \"single\": {\"n\": %d, \"vac\": %ld, \"repl\": %ld, \"sub\": %ld, \"followed\": %ld, \"steps\": %ld, "
               "\"ions\": %ld, \"Eel\": %.10g, \"simconf_vac\": %d, \"mean_x\": %.10g, \"mean_recoil_E\": %.10g}}\n",
               n2, ct.vac, ct.repl, ct.sub, ct.followed, ct.steps, ions, sc2.EelTotal, sc2.vacancies_created,

@@ -34,7 +34,17 @@ def _worker(rank, world, port, out_dir):
     lo, hi = mdist.shard_range(N_TOTAL, rank, world)
     u, f = _rank_tallies(lo, hi)
     tu, tf = torch.from_numpy(u), torch.from_numpy(f)
-    mdist.reduce_tallies(tu, tf)
+    tu[12] = 1000 + rank            # rank-local bookkeeping slot (list length): must survive the join untouched
+    red = mdist.TallyReducer(tu, tf)
+    before = tu.clone()
+    total_u, total_f = red.reduce(write_back=False)          # out of place: the blocks keep this rank's share
+    assert torch.equal(tu, before)
+    pu, pf = red.per_rank()
+    assert torch.equal(pu[rank], before) and torch.equal(pu[:, :mdist.N_ADDITIVE_COUNTERS].sum(dim=0),
+                                                         total_u[:mdist.N_ADDITIVE_COUNTERS])
+    mdist.reduce_tallies(tu, tf)                             # in place (one collective)
+    assert torch.equal(tu, total_u) and torch.equal(tf, total_f) and int(tu[12]) == 1000 + rank
+    tu[12] = 0
     np.save(os.path.join(out_dir, "u%d.npy" % rank), tu.numpy())
     np.save(os.path.join(out_dir, "f%d.npy" % rank), tf.numpy())
     dist.destroy_process_group()

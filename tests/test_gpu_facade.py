@@ -48,6 +48,16 @@ def test_facade_batch_and_user_subclass():
     assert abs(a["vacancies_after_second"] - 2 * b["vacancies"]) <= 0.03 * 2 * b["vacancies"] + a["single_vac"]
     assert a["hist_vac_after_third"] > a["hist_vac_after_second"]
     assert abs(a["vacancies_third"] - b["vacancies"]) > 0.02 * b["vacancies"]   # tmin = 5 changes the physics
+    # 3. TrimDefectLog / TrimHistory / fullTraj through the queue loop (trim.h:139-175): every ion ends with exactly one
+    # I / R / S line (or leaves no line when it is still MOVING: none in an infinite solid), one V line per vacancy,
+    # TrimHistory records the position of every followed recoil's parent, fullTraj prints one "spawn" line per followed
+    # recoil and one state line per collision
+    h = res["hooks"]
+    assert h["I"] + h["R"] + h["S"] == h["ions"]
+    assert abs(h["V"] / h["n"] - 141.7) < 5.0 and abs(h["R"] / h["n"] - 63.1) < 4.0 and h["S"] == 0
+    assert abs(h["ions"] / h["n"] - 205.9) < 7.0
+    assert h["history"] == h["history_ions"] - h["n"]           # followRecoil() once per followed recoil
+    assert h["spawn_lines"] == h["traj_followed"] == h["traj_ions"] - 5 and h["state_lines"] == h["traj_steps"]
     # 2. per-ion trim() with host hooks: statistically the same physics (different stream ids)
     s = res["single"]
     n = s["n"]

@@ -706,3 +706,34 @@ def test_trim_many_equals_trim_one_per_ion():
         for k, i in enumerate(longer):
             f1, s1, e1 = eng.trim_one(ions[i], 99, 1000 + i, capacity=1 << 16)
             assert ev2[k, :cnt2[k]].tobytes() == e1.tobytes() and st2[k] == s1 and fin2[k].tobytes() == f1.tobytes()
+
+
+@pytest.mark.parametrize("sample", ["wire", "burried_wire"])
+def test_wire_samples_on_the_gpu(sample):
+    """SampleWire (CUT boundaries, vacuum outside the cylinder: sample_wire.C:29-46) and SampleBurriedWire (INF
+    boundaries, cover layer, matrix around the wire: sample_burried_wire.C:29-55) on the GPU (all-options kernel) against
+    the oracle, whose look-ups are pinned bit for bit on the reference's records of the same cases
+    (tests/golden/ref_geometry_*.npz): per-primary state (MOVING on a vacuum exit, LOST on a CUT boundary), end point,
+    counters of every exit."""
+    from tests.golden.make_golden import GEOMETRY_CASES
+    _, box, mats, ion, start, _ = GEOMETRY_CASES[sample]
+    n = 1500
+    cfg = dict(tally_mask=capi.TALLY_RECORDS)
+    with capi.Engine(**cfg) as eng, util.OracleEngine(util.ORC_RNG_PHILOX, **cfg) as orc:
+        for e in (eng, orc):
+            e.set_materials(mats)
+            if sample == "wire":
+                e.set_geometry(capi.GEOM_WIRE, box, bc=(capi.BC_CUT, capi.BC_CUT, capi.BC_PBC))
+            else:
+                e.set_geometry(capi.GEOM_BURIED_WIRE, box, bc=(capi.BC_INF, capi.BC_INF, capi.BC_INF))
+        ions = capi.make_ions(n, ion[0], ion[1], ion[2], pos=start[:3], direction=start[3:])
+        rg = eng.run(ions, seed=303, records=True)
+        ro = orc.run(ions, seed=303, records=True)
+        cg, co = eng.counters(), orc.counters()
+    assert len(set(ro["state"].tolist())) >= 2
+    r = util.compare_records(rg, ro, ions)
+    print("%s: %s" % (sample, r))
+    assert n - r["cascades_identical"] <= max_flipped_cascades(n, co["steps"]), r
+    assert r["pos_outliers"] <= 0.002 * n + 1 and r["median_rel_pos"] < 0.1 * TOL, r
+    for k in ("steps", "ions", "left_sample", "lost", "vacancies_created"):
+        assert abs(cg[k] - co[k]) <= 2e-3 * co[k] + 2, (k, cg[k], co[k])

@@ -1,7 +1,7 @@
 #!/bin/bash
 # compute-sanitizer passes over a small run of every kernel variant (race detection on
 # the tally/queue code).  Usage (under gpurun): bash tools/sanitize.sh [tag]
-TAG=${1:-r01}
+TAG=${1:-r02}
 OUT=gpurun_out
 mkdir -p $OUT
 cat > /tmp/sanitize_run.py <<'PY'
@@ -51,8 +51,25 @@ import os
 os.environ["MYTRIM_B200_NO_SHARE"] = "1"
 with capi.Engine(tally_mask=capi.TALLY_VAC_DEPTH) as eng:
     c = util.setup_engine(eng, "cu_on_cu_1keV")
-    eng.run(util.primaries_for(c, 4096), seed=1)
-    print("plain fast", eng.counters()["steps"])
+    eng.run(util.primaries_for(c, 4096), seed=1)                      # MONO no-records (what bench.py times)
+    print("plain MONO, no records", eng.counters()["steps"])
+    eng.run(util.primaries_for(c, 2048), seed=2, records=True)        # MONO with records
+    print("plain MONO, records", eng.counters()["steps"])
+with capi.Engine(tally_mask=capi.TALLY_VAC_DEPTH) as eng:
+    c = util.setup_engine(eng, "xe_on_zro2_500keV")                   # compound stack folded into one material: FAST
+    ions = util.primaries_for(c, 16)
+    ions["E"] = 2.0e4
+    eng.run(ions, seed=1)
+    print("plain FAST", eng.counters()["steps"])
+del os.environ["MYTRIM_B200_NO_SHARE"]
+with capi.Engine(tally_mask=capi.TALLY_VAC_DEPTH) as eng:
+    c = util.setup_engine(eng, "cu_on_cu_10keV")
+    eng.run(util.primaries_for(c, 512), seed=1)                       # MONO + share
+    print("MONO + share", eng.counters()["steps"])
+with capi.Engine(tally_mask=0) as eng:
+    c = util.setup_engine(eng, "cu_on_cu_10keV")
+    fin, st, cnt, ev = eng.trim_many(util.primaries_for(c, 100), 5, 0, 64)   # event mode, one lane per ion
+    print("trim_many", int(cnt.sum()))
 PY
 for tool in memcheck racecheck initcheck synccheck; do
   echo "== $tool"
