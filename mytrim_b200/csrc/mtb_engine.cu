@@ -354,13 +354,14 @@ struct mtb_handle
   DevBuf<uint32_t> d_deferred;
   bool share_enabled = true;
   uint64_t share_below = 4;  // work sharing for launches with fewer primaries per lane than this
-  float share_min_E = 0.f;   // eV, see suspend_ion()
+  float share_min_E = 300.f; // eV, see suspend_ion(): measured optimum 200-500 eV (profiles/r02_variant_sweeps.md)
   bool deferred_pending = false;
   float extra_ms = 0.f;
   bool fast = false;
   DevBuf<double> d_layer_cum, d_cl_xyzr;
   DevBuf<int32_t> d_layer_mat, d_cl_hash, d_cl_next;
   DevBuf<uint8_t> d_cl_dist;
+  DevBuf<float> d_cl_safe;
   // outputs
   DevBuf<unsigned long long> d_u64;
   DevBuf<double> d_f64;
@@ -431,6 +432,12 @@ build_tables(mtb_handle * h)
     P.cl_xyzr = h->d_cl_xyzr.p;
     MTB_CUDA(h->d_cl_dist.upload(T.cl_dist.data(), T.cl_dist.size(), h->stream));
     P.cl_dist = h->d_cl_dist.p;
+    P.cl_safe = nullptr;
+    if (!T.cl_safe.empty())
+    {
+      MTB_CUDA(h->d_cl_safe.upload(T.cl_safe.data(), T.cl_safe.size(), h->stream));
+      P.cl_safe = h->d_cl_safe.p;
+    }
   }
   MTB_CUDA(cudaStreamSynchronize(h->stream)); // T goes out of scope
 

@@ -147,6 +147,7 @@ struct HostTables
   std::vector<int32_t> tclass_elem;
   std::vector<double> layer_cum;
   std::vector<int32_t> layer_mat, cl_hash, cl_next;
+  std::vector<float> cl_safe; // per hash cell: distance bound to the nearest cluster surface (periodic boxes)
   std::vector<int> mat_map; // device material of every input material (fold_identical_materials)
   std::vector<uint8_t> cl_dist;
 };
@@ -652,6 +653,57 @@ build_host_tables(const HostConfig & H_in, HostTables & T, LaunchParams & P, std
     // seen by the lookup, so skipping is for fully periodic boxes only.
     const bool periodic = g.bc[0] == MTB_BC_PBC && g.bc[1] == MTB_BC_PBC && g.bc[2] == MTB_BC_PBC;
     P.cl_safe_unit = periodic ? (float)(0.999 * std::min(P.kd[0], std::min(P.kd[1], P.kd[2]))) : 0.f;
+    P.cl_inv_safe_unit = P.cl_safe_unit > 0.f ? 1.0f / P.cl_safe_unit : 0.f;
+
+    // Second map, in Angstrom: a lower bound of the distance from ANY point of a cell to the nearest cluster SURFACE.
+    // The cell map above is blind within one scan range of a bubble (distance 0: scan at every step; distance 1: look
+    // up at every step) although most of those cells are several Angstrom away from the sphere itself — and that is
+    // where the recoils of a fission track near a bubble spend their lives.  An ion in such a cell may fly that far
+    // before a look-up can find it inside a cluster, and a cell with a positive bound needs no scan at all.
+    // Clusters whose window (scan range + 3 cells) does not reach a cell are more than 2 cell edges away from it, so
+    // the bound is capped there.  Exact like the first map: only look-ups that return the matrix are skipped.
+    T.cl_safe.clear();
+    if (periodic && ncl > 0)
+    {
+      const double kd_min = std::min(P.kd[0], std::min(P.kd[1], P.kd[2]));
+      T.cl_safe.assign(ncell, (float)(2.0 * kd_min));
+      for (size_t l = 0; l < ncl; ++l)
+      {
+        double ctr[3];
+        int cc[3], half[3];
+        for (int i = 0; i < 3; ++i)
+        {
+          ctr[i] = H.cluster_xyzr[4 * l + i] - std::floor(H.cluster_xyzr[4 * l + i] / g.w[i]) * g.w[i];
+          cc[i] = std::min(g.kn[i] - 1, (int)(ctr[i] / P.kd[i]));
+          half[i] = std::min(P.cl_ks[i] + 3, g.kn[i] / 2);
+        }
+        const double rad = H.cluster_xyzr[4 * l + 3];
+        for (int d0 = -half[0]; d0 <= half[0]; ++d0)
+          for (int d1 = -half[1]; d1 <= half[1]; ++d1)
+            for (int d2 = -half[2]; d2 <= half[2]; ++d2)
+            {
+              const int d[3] = {d0, d1, d2};
+              int k[3];
+              double dist2 = 0.0;
+              for (int i = 0; i < 3; ++i)
+              {
+                k[i] = ((cc[i] + d[i]) % g.kn[i] + g.kn[i]) % g.kn[i];
+                const double a = k[i] * P.kd[i], b = (k[i] + 1) * P.kd[i];
+                double best = 1e300;
+                for (int m = -1; m <= 1; ++m)
+                {
+                  const double x = ctr[i] + m * g.w[i];
+                  best = std::min(best, std::max(0.0, std::max(a - x, x - b)));
+                }
+                dist2 += best * best;
+              }
+              const size_t cell = (size_t)k[0] + (size_t)g.kn[0] * ((size_t)k[1] + (size_t)g.kn[1] * (size_t)k[2]);
+              const float bound = (float)std::max(0.0, 0.999 * (std::sqrt(dist2) - rad) - 1e-4);
+              if (bound < T.cl_safe[cell])
+                T.cl_safe[cell] = bound;
+            }
+      }
+    }
   }
 
   // tally sizes

@@ -28,8 +28,10 @@ namespace mtb
 #define MTB_ATOMIC_MAX(ptr, val) atomicMax((ptr), (val))
 // warp-uniform loop exit: all 32 lanes vote every iteration, which is also where the warp reconverges
 #define MTB_WARP_ALL(pred) __all_sync(0xffffffffu, (pred))
+#define MTB_WARP_ANY(pred) __any_sync(0xffffffffu, (pred))
 #else
 #define MTB_WARP_ALL(pred) (pred)
+#define MTB_WARP_ANY(pred) (pred)
 template <class T, class U>
 inline T
 host_fetch_add(T * p, U v)
@@ -310,12 +312,6 @@ lookup_cluster(const LaunchParams & P, double px, double py, double pz, float * 
       k = (int)r;
     }
     kc[i] = k;
-    k1[i] = k - P.cl_ks[i];
-    k2[i] = k + P.cl_ks[i];
-    if (k1[i] < 0 && P.bc[i] != MTB_BC_PBC)
-      k1[i] = 0;
-    if (k2[i] >= P.kn[i] && P.bc[i] != MTB_BC_PBC)
-      k2[i] = P.kn[i] - 1;
   }
   {
     // distance map (mtb_tables.h): nothing to find around this cell in almost every lookup, and in a
@@ -327,15 +323,29 @@ lookup_cluster(const LaunchParams & P, double px, double py, double pz, float * 
       const uint32_t cell = (uint32_t)kc[0] + (uint32_t)P.kn[0] * ((uint32_t)kc[1] + (uint32_t)P.kn[1] * (uint32_t)kc[2]);
 #if MTB_DEVICE_CODE
       const uint32_t n = __ldg(P.cl_dist + cell);
+      const float bound = P.cl_safe ? __ldg(P.cl_safe + cell) : 0.0f;
 #else
       const uint32_t n = P.cl_dist[cell];
+      const float bound = P.cl_safe ? P.cl_safe[cell] : 0.0f;
 #endif
-      if (n)
+      // cell map: nothing within (n - 1) cell edges of path; surface map: every point of this cell is at least
+      // `bound` away from any cluster (no scan needed even where a scan could see one)
+      if (n || bound > 0.0f)
       {
-        *safe = (float)(n - 1u) * P.cl_safe_unit;
+        *safe = fmax2(n ? (float)(n - 1u) * P.cl_safe_unit : 0.0f, bound);
         return -1;
       }
     }
+  }
+  // the scan range is only needed here: almost every look-up has returned through the distance map above
+  for (int i = 0; i < 3; ++i)
+  {
+    k1[i] = kc[i] - P.cl_ks[i];
+    k2[i] = kc[i] + P.cl_ks[i];
+    if (k1[i] < 0 && P.bc[i] != MTB_BC_PBC)
+      k1[i] = 0;
+    if (k2[i] >= P.kn[i] && P.bc[i] != MTB_BC_PBC)
+      k2[i] = P.kn[i] - 1;
   }
   for (int j0 = k1[0]; j0 <= k2[0]; ++j0)
   {
@@ -531,8 +541,18 @@ current_Z(const Lane & L, const BlockCtx & S, const float4_t * rows)
   return (L.pcls >= 0 || !rows) ? S.pclass[L.pcls].Z : row_class(rows).Z;
 }
 
+// Clusters geometry: what is left of Lane::dsafe travels with a suspended ion (rounded DOWN to whole units, so only
+// look-ups that would have returned the matrix are skipped).  Without it every popped or adopted ion started with a
+// 27-cell look-up: 19 % of the warp instructions of the tests/uo2 workload at 3 active lanes (profiles/r02_ncu_uo2.md).
+MTB_HD uint32_t
+safe_bits_of(const LaunchParams & P, float dsafe)
+{
+  const float q = fmin2(fmax2(dsafe, 0.0f) * P.cl_inv_safe_unit, (float)SAFE_MAX);
+  return (uint32_t)(int)q << SAFE_SHIFT;
+}
+
 MTB_HD void
-stack_store(StackEntry * dst, const Lane & L)
+stack_store(StackEntry * dst, const Lane & L, uint32_t safe_bits = 0u)
 {
 #if MTB_DEVICE_CODE
   // 8-byte stores for the doubles (they sit in aligned register pairs already: a 16-byte store would
@@ -544,7 +564,7 @@ stack_store(StackEntry * dst, const Lane & L)
   dd[3] = L.E;
   uint4 * d = reinterpret_cast<uint4 *>(dst);
   d[2] = make_uint4(__float_as_uint(L.dx), __float_as_uint(L.dy), __float_as_uint(L.dz), L.ic);
-  d[3] = make_uint4((uint32_t)L.uid, (uint32_t)(L.uid >> 32), L.packed, (uint32_t)L.tag);
+  d[3] = make_uint4((uint32_t)L.uid, (uint32_t)(L.uid >> 32), L.packed | safe_bits, (uint32_t)L.tag);
 #else
   StackEntry e;
   e.pos[0] = L.px;
@@ -556,7 +576,7 @@ stack_store(StackEntry * dst, const Lane & L)
   e.dir[2] = L.dz;
   e.ic = L.ic;
   e.uid = L.uid;
-  e.packed = L.packed;
+  e.packed = L.packed | safe_bits;
   e.tag = L.tag;
   *dst = e;
 #endif
@@ -579,7 +599,7 @@ stack_load(const StackEntry * src, Lane & L)
   L.dz = __uint_as_float(c.z);
   L.ic = c.w;
   L.uid = ((uint64_t)d.y << 32) | d.x;
-  L.packed = d.z;
+  L.packed = d.z; // (the caller strips the safe-distance bits of the clusters geometry: restore_safe)
   L.tag = (int32_t)d.w;
 #else
   const StackEntry e = *src;
@@ -597,6 +617,18 @@ stack_load(const StackEntry * src, Lane & L)
   L.packed = e.packed;
   L.tag = e.tag;
 #endif
+}
+
+// after a pop / an adoption in the clusters geometry: Lane::dsafe from the bits the suspended ion carried
+template <class TR>
+MTB_HD void
+restore_safe(const LaunchParams & P, Lane & L)
+{
+  if (TR::has(F_CLUSTERS))
+  {
+    L.dsafe = (float)(L.packed >> SAFE_SHIFT) * P.cl_safe_unit;
+    L.packed &= ~((uint32_t)SAFE_MAX << SAFE_SHIFT);
+  }
 }
 
 // One half of an ion-log entry (birth: state = -1, position/energy at birth; death: final state,
@@ -851,14 +883,14 @@ pool_claim(PoolSlot * pool, unsigned long long * ctl, int which, unsigned long l
 }
 
 MTB_D bool
-pool_try_push(const BlockCtx & S, const Lane & ion, uint64_t prim)
+pool_try_push(const BlockCtx & S, const Lane & ion, uint64_t prim, uint32_t safe_bits)
 {
   unsigned long long pos;
   PoolSlot * slot = pool_claim(S.pool, S.pool_ctl, POOL_ENQ, &pos);
   if (!slot)
     return false;
   slot->prim = prim;
-  stack_store(&slot->e, ion);
+  stack_store(&slot->e, ion, safe_bits);
   store_release(&slot->seq, pos + 1); // publishes the payload
   return true;
 }
@@ -920,14 +952,17 @@ suspend_ion(const LaunchParams & P, const BlockCtx & S, uint32_t & sp, const Lan
   // Donate only when BOTH ions of the pair carry a subtree worth a hand-over (e_small = the smaller of
   // the two energies): a lane that gives its big ion away and keeps a 30 eV recoil is idle itself
   // three steps later, and every adoption costs a few hundred instructions at one active lane.
-  if (TR::kShare && e_small >= P.share_min_E && vload(&S.pool_ctl[POOL_IDLE]) > 0 && pool_try_push(S, ion, prim))
+  const uint32_t safe_bits = TR::has(F_CLUSTERS) ? safe_bits_of(P, ion.dsafe) : 0u;
+  if (TR::kShare && e_small >= P.share_min_E && vload(&S.pool_ctl[POOL_IDLE]) > 0 && pool_try_push(S, ion, prim, safe_bits))
     return;
+#else
+  const uint32_t safe_bits = TR::has(F_CLUSTERS) ? safe_bits_of(P, ion.dsafe) : 0u;
 #endif
   (void)S;
   (void)prim;
   if ((sp & MTB_STACK_DEPTH_BITS) != MTB_STACK_DEPTH_BITS)
   {
-    stack_store(stack_entry(P, sp), ion);
+    stack_store(stack_entry(P, sp), ion, safe_bits);
     sp += (uint32_t)sizeof(StackEntry);
   }
   else
@@ -978,9 +1013,15 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
   uint32_t sw3 = 0, srp = 0;
   int32_t smtag = 0;
   uint32_t iter = 0;
+#ifndef MTB_POLL_EVERY
+#define MTB_POLL_EVERY 1 // power of two
+#endif
+  uint32_t trip = 0;
 
   for (;;)
   {
+    if (TR::kShare && MTB_POLL_EVERY > 1)
+      ++trip;
     bool resolve = true;
 #if MTB_DEVICE_CODE
     if (DEFER)
@@ -1024,6 +1065,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           R.uid = ruid;
           R.packed = srp;
           R.tag = smtag;
+          R.dsafe = sdsafe;
           if (tally_on<TR>(P, MTB_TALLY_IONLOG))
           {
             R.prim = L.prim;
@@ -1061,6 +1103,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       {
         sp -= (uint32_t)sizeof(StackEntry);
         stack_load(stack_entry(P, sp), L);
+        restore_safe<TR>(P, L);
         set_species(L, S);
         active = true;
       }
@@ -1181,10 +1224,14 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
               atomicAdd(&S.pool_ctl[POOL_WORKING], (unsigned long long)-1ll);
             }
             uint64_t aprim;
-            if (pool_try_pop(S, L, &aprim))
+            // (Polling only in every 4th / 16th trip of the warp, -DMTB_POLL_EVERY, to spare the working warp mates
+            // the ~40 instructions of the attempt, was measured 5-14 % SLOWER on the tests/uo2 workload and 5-8 % on
+            // C->W / Xe->ZrO2: how soon an idle lane picks work up matters more.  profiles/r02_variant_sweeps.md)
+            if ((MTB_POLL_EVERY == 1 || (trip & (MTB_POLL_EVERY - 1)) == 0) && pool_try_pop(S, L, &aprim))
             {
               // the entry carried its own count in POOL_WORKING; it now belongs to this lane
               idle = false;
+              restore_safe<TR>(P, L);
               atomicAdd(&S.pool_ctl[POOL_IDLE], (unsigned long long)-1ll);
               const mtb_ion & src = P.primaries ? P.primaries[aprim] : P.beam;
               L.prim = (uint32_t)aprim;
@@ -1229,6 +1276,15 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
       __nanosleep(400); // the whole warp is polling: back off
 #endif
 
+    // Clusters geometry: when ANY lane of the warp has used up its safe distance, every active lane looks its material
+    // up in this trip.  A look-up costs the warp its ~150 instructions whether one lane or thirty-two take part (2 % of
+    // the lane-steps of the tests/uo2 workload needed one, so half of all trips paid for it: 15 % of the warp
+    // instructions at 3 active lanes); taken together, all lanes leave with a fresh safe distance and the next
+    // look-up is tens of trips away.  The extra look-ups return the matrix by construction: no result changes.
+    bool refresh = false;
+    if (TR::has(F_CLUSTERS) && !TR::has(F_MONO))
+      refresh = MTB_WARP_ANY(active && !(L.dsafe > 0.0f));
+
     if (active && !(DEFER && pend))
       do
       {
@@ -1245,7 +1301,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
     int mi = 0;
     if (TR::has(F_MONO))
       ; // material 0 everywhere (sample_solid.C:25-29; sample_layers.C:26-49 never returns vacuum)
-    else if (!(TR::has(F_CLUSTERS) && L.dsafe > 0.0f)) // else: clusters geometry, still provably in the matrix
+    else if (!(TR::has(F_CLUSTERS) && L.dsafe > 0.0f && !refresh)) // else: clusters geometry, still provably in the matrix
     {
       float safe;
       mi = lookup_material<TR>(P, S, L.px, L.py, L.pz, &cluster, &safe);
@@ -1579,6 +1635,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
         R.uid = ruid;
         R.packed = rpacked;
         R.tag = mtag;
+        R.dsafe = dsafe_here;
         if (tally_on<TR>(P, MTB_TALLY_IONLOG))
         {
           R.prim = L.prim;

@@ -123,7 +123,11 @@ enum
   SPECIES_MASK = 0xFFF,
   GEN_SHIFT = 12,
   GEN_MASK = 0xFFFF,
-  FLAG_PRIMARY = 1u << 28
+  FLAG_PRIMARY = 1u << 28,
+  // bits 29..31 of a SUSPENDED ion (stack / sharing pool entry): the path it may still fly before the next cluster
+  // look-up can matter, in whole units of LaunchParams::cl_safe_unit, saturated at 7 (clusters geometry only)
+  SAFE_SHIFT = 29,
+  SAFE_MAX = 7
 };
 
 #define MTB_STACK_DEPTH 32
@@ -221,6 +225,9 @@ struct LaunchParams
   double kn_w[3];               // kn / w: cell index without a division (exact path on near-ties)
   const uint8_t * cl_dist;      // per hash cell: chessboard distance (in cells, capped at 255) to the nearest cell
                                 // whose scan neighbourhood holds a cluster; 0 = scan here
+  const float * cl_safe;        // per hash cell: lower bound of the distance from any point of the cell to the nearest
+                                // cluster surface (fully periodic boxes; else null), mtb_tables.h
+  float cl_inv_safe_unit;       // 1 / cl_safe_unit, 0 when cl_safe_unit is 0
   float cl_safe_unit;           // path length an ion can travel per unit of cl_dist above 1 without meeting a
                                 // cluster (smallest cell edge, with a margin); 0 = no skipping (non-periodic box)
   // primaries

@@ -59,6 +59,7 @@ hs_prepare(hs_engine * e)
   P.cl_hash = e->T.cl_hash.data();
   P.cl_next = e->T.cl_next.data();
   P.cl_dist = e->T.cl_dist.data();
+  P.cl_safe = e->T.cl_safe.empty() ? nullptr : e->T.cl_safe.data();
   P.cl_xyzr = e->host.cluster_xyzr.data();
   e->u64.assign(u64_block_size(P), 0ull);
   e->f64[0] = e->f64[1] = 0.0;
