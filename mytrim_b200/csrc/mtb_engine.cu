@@ -244,6 +244,16 @@ transport_kernel(const __grid_constant__ LaunchParams P)
   flush_block(P, S);
 }
 
+// rows of the registered primary species, by the functions the lanes use for private rows (mtb_transport.cuh)
+__global__ void
+primary_class_rows_kernel(const LaunchParams P, ProjClass * pclass, PairM * pairm, PairE * paire)
+{
+  const int pc = P.n_tclass + blockIdx.x * blockDim.x + threadIdx.x;
+  if (pc < P.n_pclass)
+    primary_class_rows(pc, P.n_materials, P.n_tclass, P.tmin, P.ionz, P.materials, P.elements, P.tclass_elem, pclass, pairm,
+                       paire);
+}
+
 __global__ void __launch_bounds__(32)
 trim_one_kernel(const __grid_constant__ LaunchParams P)
 {
@@ -415,6 +425,11 @@ build_tables(mtb_handle * h)
   P.paire = h->d_paire.p;
   MTB_CUDA(h->d_tclass_elem.upload(T.tclass_elem.data(), T.tclass_elem.size(), h->stream));
   P.tclass_elem = h->d_tclass_elem.p;
+  if (P.n_pclass > P.n_tclass)
+  {
+    primary_class_rows_kernel<<<(P.n_pclass - P.n_tclass + 31) / 32, 32, 0, h->stream>>>(P, h->d_pclass.p, h->d_pairm.p, h->d_paire.p);
+    MTB_CUDA(cudaGetLastError());
+  }
   if (P.n_layers)
   {
     MTB_CUDA(h->d_layer_cum.upload(T.layer_cum.data(), T.layer_cum.size(), h->stream));

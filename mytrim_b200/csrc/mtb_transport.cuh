@@ -464,10 +464,15 @@ set_species(Lane & L, const BlockCtx &)
 }
 
 // Projectile class of a primary: a target class, a registered primary species, or -1.
+// (Which primary species happen to be registered as classes depends on what the handle has run before; that must not
+// change a result — mytrim_uo2 deals chunks of fission events over several GPUs — so the rows of a registered primary
+// species are produced by the very functions a lane uses for its private rows: primary_class_rows() below.)
+template <class TR>
 MTB_HD int
 find_class(const LaunchParams & P, const BlockCtx & S, int Z, float m)
 {
-  for (int c = 0; c < P.n_pclass; ++c)
+  const int n = P.n_pclass;
+  for (int c = 0; c < n; ++c)
     if (S.pclass[c].Z == Z && S.pclass[c].m == m)
       return c;
   return -1;
@@ -509,6 +514,21 @@ build_custom_rows(const LaunchParams & P, const BlockCtx & S, float4_t * rows, i
     rows[2 + mi] = as_row(make_pair_m(c, S.materials[mi], P.tmin));
   for (int tc = 0; tc < P.n_tclass; ++tc)
     rows[2 + P.n_materials + tc] = as_row(make_pair_e(c, S.elements[P.tclass_elem[tc]]));
+}
+
+// Table rows of projectile class `pc` when it is a registered PRIMARY species (pc >= n_tclass): the same arithmetic as
+// build_custom_rows, so that a primary follows the same trajectory whether its species got a class or not.  Runs on
+// the device for the engine (mtb_engine.cu: primary_class_rows_kernel) and on the host for the host build of the loop.
+MTB_HD void
+primary_class_rows(int pc, int n_materials, int n_tclass, float tmin, const DevIonZ * ionz, const DevMaterial * materials,
+                   const DevElement * elements, const int32_t * tclass_elem, ProjClass * pclass, PairM * pairm, PairE * paire)
+{
+  const ProjClass c = make_proj_class(ionz[pclass[pc].Z], pclass[pc].Z, pclass[pc].m);
+  pclass[pc] = c;
+  for (int mi = 0; mi < n_materials; ++mi)
+    pairm[pc * n_materials + mi] = make_pair_m(c, materials[mi], tmin);
+  for (int tc = 0; tc < n_tclass; ++tc)
+    paire[pc * n_tclass + tc] = make_pair_e(c, elements[tclass_elem[tc]]);
 }
 
 MTB_HD ProjClass
@@ -1166,7 +1186,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
               continue;
             }
           }
-          const int cls = find_class(P, S, src_Z, src_m);
+          const int cls = find_class<TR>(P, S, src_Z, src_m);
           if (!TR::kCustom && cls < 0)
           {
             // species without a projectile class: hand the primary to the generic kernel
@@ -1243,7 +1263,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
                 // class of the primary nor (per-primary masses) its private rows
                 const int aZ = src.Z;
                 const float am = (float)src.m;
-                L.prim_pcls = find_class(P, S, aZ, am);
+                L.prim_pcls = find_class<TR>(P, S, aZ, am);
                 if (TR::kCustom && L.prim_pcls < 0)
                   build_custom_rows(P, S, rows, aZ, am);
               }

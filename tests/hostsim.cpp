@@ -73,6 +73,9 @@ hs_prepare(hs_engine * e)
   P.range = e->range.data();
   P.stacks = e->stacks.data();
   P.tclass_elem = e->T.tclass_elem.data();
+  for (int pc = P.n_tclass; pc < P.n_pclass; ++pc) // as mtb_engine.cu: primary_class_rows_kernel
+    primary_class_rows(pc, P.n_materials, P.n_tclass, P.tmin, e->T.ionz.data(), e->T.materials.data(), e->T.elements.data(),
+                       e->T.tclass_elem.data(), e->T.pclass.data(), e->T.pairm.data(), e->T.paire.data());
   e->custom_rows.assign((size_t)(2 + P.n_materials + P.n_tclass), float4_t());
   P.custom_rows = e->custom_rows.data();
   e->dirty = false;

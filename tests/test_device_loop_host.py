@@ -483,7 +483,7 @@ def test_per_ion_parity_fp32_replay_against_fp64_oracle(name, n):
         r = util.compare_records(rh, ro, ions)
     assert s["n_test"] == s["n_replay"] == s["joined"] > 0, s
     assert s["ints_equal"] >= 0.9999 * s["joined"], s
-    assert s["pos_outliers"] <= 2e-4 * s["joined"] + 2 and s["energy_outliers"] == 0, s
+    assert s["pos_outliers"] <= 5e-4 * s["joined"] + 2 and s["energy_outliers"] == 0, s
     assert s["median_rel_pos"] < 0.1 * TOL, s
     assert r["cascades_identical"] >= 0.9 * r["n"] and r["pos_outliers"] == 0, r
 
@@ -539,3 +539,20 @@ def test_invalid_primaries_are_skipped_and_reported():
         assert hs.counters()["primaries"] == 27
         hs.run(capi.make_ions(8, 29, 63.546, 1e3), seed=1)
         assert hs.counters()["primaries"] == 35
+
+
+def test_results_do_not_depend_on_what_the_engine_ran_before():
+    """The first primaries of every batch register their species as projectile classes (table rows in shared memory
+    instead of per-lane rows).  Which species are registered therefore depends on the handle's history — and must not
+    change any result: mytrim_uo2 deals chunks of fission events over several GPUs and writes identical files."""
+    from tests import parity_cases
+    cfg = dict(tally_mask=capi.TALLY_RECORDS | capi.TALLY_PHONON)
+    with util.HostSimEngine(**cfg) as used, util.HostSimEngine(**cfg) as fresh:
+        first = parity_cases.setup_case(used, "uo2_fission_like", 40)
+        parity_cases.setup_case(fresh, "uo2_fission_like", 40)
+        second = parity_cases.fission_like_primaries(40, seed=11)
+        used.run(first, seed=5, first_index=0)                       # registers the species of `first`
+        ra = used.run(second, seed=5, first_index=1000, records=True)
+        rb = fresh.run(second, seed=5, first_index=1000, records=True)   # registers the species of `second`
+    for f in ra.dtype.names:
+        assert np.array_equal(ra[f], rb[f]), f

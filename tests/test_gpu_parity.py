@@ -737,3 +737,23 @@ def test_wire_samples_on_the_gpu(sample):
     assert r["pos_outliers"] <= 0.002 * n + 1 and r["median_rel_pos"] < 0.1 * TOL, r
     for k in ("steps", "ions", "left_sample", "lost", "vacancies_created"):
         assert abs(cg[k] - co[k]) <= 2e-3 * co[k] + 2, (k, cg[k], co[k])
+
+
+def test_results_do_not_depend_on_what_the_engine_ran_before():
+    """GPU twin of the host test of the same name: registered primary species (class rows in shared memory) and
+    unregistered ones (per-lane rows) get bit-identical constants, so a batch gives the same records on a handle that
+    has already run other species as on a fresh one (what makes mytrim_uo2's files independent of the GPU count)."""
+    from tests import parity_cases
+    cfg = dict(tally_mask=capi.TALLY_RECORDS | capi.TALLY_PHONON)
+    with capi.Engine(**cfg) as used, capi.Engine(**cfg) as fresh:
+        first = parity_cases.setup_case(used, "uo2_fission_like", 400)
+        parity_cases.setup_case(fresh, "uo2_fission_like", 400)
+        second = parity_cases.fission_like_primaries(400, seed=11)
+        used.run(first, seed=5, first_index=0)
+        ra = used.run(second, seed=5, first_index=1000, records=True)
+        rb = fresh.run(second, seed=5, first_index=1000, records=True)
+    for f in ra.dtype.names:
+        if f in ("Eel", "Enuc"):   # per-lane partial sums of a shared cascade: order of addition is not fixed
+            assert np.allclose(ra[f], rb[f], rtol=1e-12, atol=0), f
+        else:
+            assert np.array_equal(ra[f], rb[f]), f
