@@ -341,6 +341,10 @@ def main():
     wall_resident = time.perf_counter() - t_wall0
     clocks = sampler.stop()
     counters = eng.counters()  # this rank's tallies over the timed steps
+    # All ranks enter the join together: stopping the clock sampler (a subprocess) and reading the counters takes
+    # rank-dependent tens of milliseconds of host time, which a rank that arrives early would otherwise sit out inside
+    # the collective and report as "reduction time" (round 1: 50 ms at N = 2 and 4 against 0.25 ms at N = 8).
+    barrier()
     red_ms = reduce_tallies()  # whole-job tallies (one join per job, as in runmytrim's threadJoin)
     total = eng.counters() if world > 1 else counters
     reduction_check = None

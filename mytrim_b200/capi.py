@@ -107,6 +107,18 @@ def load_library():
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+        if "MYTRIM_B200_NCCL_LIB" not in os.environ:
+            # mtb_allreduce dlopens NCCL: in a Python process it has to be the one torch is built against
+            try:
+                import importlib.util
+                spec = importlib.util.find_spec("nvidia.nccl")
+                for d in (spec.submodule_search_locations if spec else []):
+                    cand = os.path.join(d, "lib", "libnccl.so.2")
+                    if os.path.exists(cand):
+                        os.environ["MYTRIM_B200_NCCL_LIB"] = cand
+                        break
+            except (ImportError, ValueError, AttributeError):
+                pass
         _lib = C.CDLL(LIB_PATH)  # RTLD_LOCAL: its C++ symbols must not interpose other libraries
         declare(_lib, "mtb_")
         _lib.mtb_version.restype = C.c_char_p

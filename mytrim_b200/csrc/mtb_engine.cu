@@ -1457,9 +1457,17 @@ struct NcclApi
   {
     if (lib)
       return true;
-    for (const char * name : {"libnccl.so.2", "libnccl.so"})
-      if ((lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL)))
-        break;
+    // An NCCL the process has already loaded wins (a later `import torch` must not find an older libnccl.so.2 under
+    // the same soname than the one it was built against); then $MYTRIM_B200_NCCL_LIB (capi.py points it at the NCCL
+    // bundled with torch); then the system library.
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!lib)
+      if (const char * env = std::getenv("MYTRIM_B200_NCCL_LIB"))
+        lib = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    if (!lib)
+      for (const char * name : {"libnccl.so.2", "libnccl.so"})
+        if ((lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL)))
+          break;
     if (!lib)
       return false;
     CommInitAll = (int (*)(void **, int, const int *))dlsym(lib, "ncclCommInitAll");
