@@ -1320,6 +1320,8 @@ mtb_trim_many(mtb_handle * h, size_t n, mtb_ion * ions, uint64_t seed, uint64_t 
   const size_t lanes = (n + 31) / 32 * 32;
   MTB_CUDA(h->d_events.ensure(n * events_per_ion));
   MTB_CUDA(h->d_event_counts.ensure(n));
+  // the event block comes back in one copy, slots past an ion's last event included: keep them defined
+  MTB_CUDA(cudaMemsetAsync(h->d_events.p, 0, n * events_per_ion * sizeof(mtb_event), h->stream));
   MTB_CUDA(h->d_primaries.upload(ions, n, h->stream));
   h->n_resident = 0; // the resident primaries of mtb_upload_primaries were replaced
   LaunchParams P = h->P;

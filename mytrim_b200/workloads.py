@@ -49,7 +49,7 @@ BENCH_WORKLOADS = {
                         desc="C->W 1 MeV, full cascades, TrimVacEnergyCount tallies (validation/c_on_w/input.json)"),
     "xe_on_zro2_500keV": dict(primaries=1 << 16, tally=capi.TALLY_VAC_DEPTH,
                               desc="Xe->ZrO2 500 keV, 50 x 10 A layers (inputs/samplelayers_zro2_multilayer.in), full cascades"),
-    "uo2_fission": dict(primaries=1 << 14, tally=capi.TALLY_IONLOG, ionlog_z=54,
+    "uo2_fission": dict(primaries=1 << 15, tally=capi.TALLY_IONLOG, ionlog_z=54,
                         desc="fission-fragment pairs in UO2 with Xe bubbles (tests/uo2), Xe ion log"),
 }
 
