@@ -67,7 +67,10 @@ constexpr int kBlock = MTB_BLOCK;
 #define MTB_MIN_BLOCKS_FAST_SHARE 6
 #endif
 #ifndef MTB_MIN_BLOCKS_CLUSTERS_SHARE
-#define MTB_MIN_BLOCKS_CLUSTERS_SHARE 6
+#define MTB_MIN_BLOCKS_CLUSTERS_SHARE 5 // 93 registers, no spills: -4.5..-7 % on the tests/uo2 workload against 6 (80 registers, spills), r02l
+#endif
+#ifndef MTB_MIN_BLOCKS_LAYERS_SHARE
+#define MTB_MIN_BLOCKS_LAYERS_SHARE 6 // C->W vacenergycount: 5 CTAs/SM measured 9 % slower (r02m)
 #endif
 #ifndef MTB_MIN_BLOCKS_GENERIC_SHARE
 #define MTB_MIN_BLOCKS_GENERIC_SHARE 6
@@ -79,7 +82,8 @@ min_blocks()
   return (TR::kF & F_NOREC)                 ? MTB_MIN_BLOCKS_MONO_NOREC
          : (TR::kF & F_MONO) && !TR::kShare ? MTB_MIN_BLOCKS_MONO
          : TR::kF & F_GEOM_ANY ? (TR::kShare ? MTB_MIN_BLOCKS_GENERIC_SHARE : MTB_MIN_BLOCKS_GENERIC)
-         : TR::kF & (F_CLUSTERS | F_FOLLOW) ? (TR::kShare ? MTB_MIN_BLOCKS_CLUSTERS_SHARE : MTB_MIN_BLOCKS_CLUSTERS)
+         : TR::kF & F_CLUSTERS ? (TR::kShare ? MTB_MIN_BLOCKS_CLUSTERS_SHARE : MTB_MIN_BLOCKS_CLUSTERS)
+         : TR::kF & F_FOLLOW   ? (TR::kShare ? MTB_MIN_BLOCKS_LAYERS_SHARE : MTB_MIN_BLOCKS_CLUSTERS)
                                             : (TR::kShare ? MTB_MIN_BLOCKS_FAST_SHARE : MTB_MIN_BLOCKS_FAST);
 }
 
