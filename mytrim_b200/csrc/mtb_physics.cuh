@@ -22,14 +22,15 @@ namespace mtb
 MTB_HD float
 proton_stopping(const DevElement & el, float e)
 {
-  const float pe = fmax2(25.0f, e);
+  // below 25 keV/amu: the element's value at 25 (host table, double precision) times (e / 25)^velpwr — the ten
+  // MUFU operations of the full expression are the same for every such call
+  if (e <= 25.0f)
+    return el.sp25 * fpow(e * 0.04f, el.velpwr);
+  const float pe = e;
   const float l2 = flog2(pe);
   const float sl = el.pc[0] * fexp2(el.pc[1] * l2) + el.pc[2] * fexp2(el.pc[3] * l2);
   const float sh = el.pc[4] * fexp2(-el.pc[5] * l2) * flog(fdiv(el.pc[6], pe) + el.pc[7] * pe);
-  float sp = fdiv(sl * sh, sl + sh);
-  if (e <= 25.0f)
-    sp *= fpow(e * 0.04f, el.velpwr);
-  return sp;
+  return fdiv(sl * sh, sl + sh);
 }
 
 // MaterialBase::rstop outside the tabulated velocity-proportional regime — material.C:187-279.

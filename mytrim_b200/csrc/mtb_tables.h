@@ -386,6 +386,14 @@ build_host_tables(const HostConfig & H_in, HostTables & T, LaunchParams & P, std
         d.pc[k] = (float)row.pcoef[k];
       d.Z = e.Z;
       d.velpwr = e.Z <= 6 ? 0.25f : 0.45f;
+      {
+        // rpstop at pe = 25 keV/amu (material.C:137-150): below that energy the reference evaluates the same
+        // expression at 25 and scales it with (e / 25)^velpwr, so the value is a constant of the element
+        const double * pc = row.pcoef;
+        const double sl = pc[0] * std::pow(25.0, pc[1]) + pc[2] * std::pow(25.0, pc[3]);
+        const double sh = pc[4] / std::pow(25.0, pc[5]) * std::log(pc[6] / 25.0 + pc[7] * 25.0);
+        d.sp25 = (float)(sl * sh / (sl + sh));
+      }
     }
     DevMaterial & d = T.materials[i];
     d.arho = (float)(m.rho * 0.6022 / am);
