@@ -29,8 +29,10 @@ struct DevElement
   float velpwr; // 0.25 (Z<=6) or 0.45: rpstop low-energy exponent (material.C:151-155)
   int32_t zslot; // column of this element's Z in the low-velocity stopping table
   int32_t tcls;  // target class: index of this element's (Z, m) among the distinct target atoms
+  float sp25;    // proton stopping at 25 keV/amu, the value rpstop scales below 25 keV/amu (material.C:137-157)
+  float _pad[3];
 };
-static_assert(sizeof(DevElement) == 80, "DevElement layout");
+static_assert(sizeof(DevElement) == 96, "DevElement layout");
 
 // One material (prepare() results, material.C:36-74).
 struct DevMaterial
