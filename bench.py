@@ -219,7 +219,9 @@ def c_abi_allreduce_check(timeout=120):
     except subprocess.TimeoutExpired:
         return "timeout"
     last = p.stdout.strip().split("\n")[-1] if p.stdout.strip() else ""
-    return last if p.returncode == 0 and last.startswith("ok") else "failed: " + (last or p.stderr.strip()[-200:])
+    if p.returncode == 0 and (last.startswith("ok") or last.startswith("skipped")):
+        return last
+    return "failed: " + (last or p.stderr.strip()[-200:])
 
 
 def main():

@@ -314,3 +314,24 @@ def test_runmytrim_range_file_against_reference_output(tmp_path):
     print("ranges: %d entries, %.1f per primary (reference %.1f), KS distance %.4f, vacancies/ion %.1f" % (
         total, total / n, per_primary_ref, D, vpi))
     assert D < 0.015, D   # the FP64 oracle with 20 000 Philox cascades is at 0.007
+
+
+def test_runmytrim_shards_over_two_gpus(tmp_path):
+    """`options.gpus` of apps/runmytrim.cpp: contiguous index ranges per GPU, one host thread each, tallies joined with
+    threadJoin like the reference joins its threads (runmytrim.C:291-323).  Philox stream ids are global primary
+    indices, so the output file does not depend on the number of GPUs (needs two devices)."""
+    if capi.load_library().mtb_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    apps = _apps()
+    outs = []
+    for gpus in (1, 2):
+        inp = {"mytrim": {"options": {"seed": 2344, "gpus": gpus},
+                          "ion": {"Z": 29, "mass": 63.546, "energy": 10000, "number": 20001},
+                          "sample": {"layers": [{"thickness": 1000, "rho": 8.92,
+                                                 "elements": [{"Z": 29, "mass": 63.546, "fraction": 1}]}]},
+                          "output": {"base": str(tmp_path / ("g%d" % gpus)), "type": "vaccount"}}}
+        out = subprocess.run([os.path.join(apps, "runmytrim")], input=json.dumps(inp), capture_output=True, text=True,
+                             timeout=600)
+        assert out.returncode == 0, out.stderr
+        outs.append(open(tmp_path / ("g%d_vac.dat" % gpus)).read())
+    assert outs[0] == outs[1] and len(outs[0]) > 1000
