@@ -727,6 +727,19 @@ sync_and_check(mtb_handle * h)
 // Everything an asynchronous mtb_launch_resident left behind — the launch of the deferred (class-less) primaries and
 // the stack-overflow check — has to happen before tallies are read, reduced or reset and before the next launch
 // re-uses the deferral list.
+// event mode (mtb_trim_one / mtb_trim_many): an ion the tables cannot describe was skipped on the device
+int
+check_skipped_ions(mtb_handle * h)
+{
+  unsigned long long err = 0;
+  MTB_CUDA(cudaMemcpy(&err, h->d_u64.p + CNT_ERROR, sizeof(err), cudaMemcpyDeviceToHost));
+  if (!err)
+    return MTB_OK;
+  MTB_CUDA(cudaMemset(h->d_u64.p + CNT_ERROR, 0, sizeof(err)));
+  return fail(MTB_EINVAL, std::to_string(err >> 32) + " ion(s) were skipped: Z outside 1..92, mass <= 0, negative or non-finite "
+                                                      "energy, or no direction");
+}
+
 int
 drain(mtb_handle * h)
 {
@@ -1278,6 +1291,8 @@ mtb_trim_one(mtb_handle * h, mtb_ion * ion, uint64_t seed, uint64_t uid, int32_t
   unsigned long long cnt = 0;
   MTB_CUDA(cudaMemcpyAsync(&cnt, h->d_u64.p + CNT_EVENTS_N, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
   MTB_CUDA(cudaStreamSynchronize(h->stream));
+  if (int rc = check_skipped_ions(h))
+    return rc;
   const size_t take = (size_t)std::min<unsigned long long>(cnt, P.events_cap);
   mtb_event last;
   bool have_last = false;
@@ -1356,6 +1371,8 @@ mtb_trim_many(mtb_handle * h, size_t n, mtb_ion * ions, uint64_t seed, uint64_t 
   MTB_CUDA(cudaGetLastError());
   MTB_CUDA(cudaMemcpyAsync(counts, h->d_event_counts.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   MTB_CUDA(cudaStreamSynchronize(h->stream));
+  if (int rc = check_skipped_ions(h))
+    return rc;
   // one copy of the used part of the event block: up to the last ion that has any event
   size_t last = 0;
   for (size_t i = 0; i < n; ++i)

@@ -655,6 +655,13 @@ def test_error_paths_return_status_codes():
         assert eng.counters()["primaries"] == 59 + 64
         with pytest.raises(capi.MytrimError):
             eng.run_beam(8, capi.make_ions(1, 0, 63.546, 1e4)[0], seed=1)     # template ion with Z = 0
+        with pytest.raises(capi.MytrimError) as e:
+            eng.trim_one(capi.make_ions(1, 200, 63.546, 1e4)[0], 1, 1)        # event mode validates too
+        assert e.value.code == capi.EINVAL
+        with pytest.raises(capi.MytrimError) as e:
+            eng.trim_many(bad[:20], 1, 0, 16)
+        assert e.value.code == capi.EINVAL
+        eng.trim_one(capi.make_ions(1, 29, 63.546, 1e4)[0], 1, 1)             # and the handle stays usable
     cfg = capi.default_config(potential=9)
     h = C.c_void_p()
     assert lib.mtb_create(C.byref(cfg), C.byref(h)) == capi.EINVAL
