@@ -132,7 +132,7 @@ def reference_uo2_primaries_per_s(events_per_proc, procs, timeout=900):
 
 # reference cascades per core and step (a step of the reference arm is ~2-20 s of wall time on all cores)
 REF_PER_CORE = {"cu_on_cu_10keV": 400, "h_on_fe_100keV": 2000, "he_on_fe_100keV": 100, "c_on_w_1MeV": 8,
-                "xe_on_zro2_500keV": 2, "uo2_fission": 2}
+                "xe_on_zro2_500keV": 2, "uo2_fission": 2, "cu_on_cu_150keV": 20, "h_on_fe_1MeV": 1000, "xe_on_uo2_10MeV": 1}
 
 
 def run_reference_arm(args):

@@ -49,6 +49,13 @@ BENCH_WORKLOADS = {
                         desc="C->W 1 MeV, full cascades, TrimVacEnergyCount tallies (validation/c_on_w/input.json)"),
     "xe_on_zro2_500keV": dict(primaries=1 << 16, tally=capi.TALLY_VAC_DEPTH,
                               desc="Xe->ZrO2 500 keV, 50 x 10 A layers (inputs/samplelayers_zro2_multilayer.in), full cascades"),
+    # the file-energy / long-cascade variants of configurations 1 and 2
+    "cu_on_cu_150keV": dict(primaries=1 << 17, tally=capi.TALLY_VAC_DEPTH,
+                            desc="Cu->Cu 150 keV, full cascades, TrimVacCount tallies (tests/json/cu_on_cu.json)"),
+    "h_on_fe_1MeV": dict(primaries=1 << 22, tally=capi.TALLY_VAC_DEPTH,
+                         desc="H->Fe 1 MeV, full cascades, TrimVacCount tallies (validation/h_on_fe at 1 MeV)"),
+    "xe_on_uo2_10MeV": dict(primaries=1 << 13, tally=capi.TALLY_VAC_DEPTH,
+                            desc="Xe->UO2 10 MeV, full cascades, TrimVacCount tallies (tests/json/xe_on_uo2.json)"),
     "uo2_fission": dict(primaries=1 << 15, tally=capi.TALLY_IONLOG, ionlog_z=54,
                         desc="fission-fragment pairs in UO2 with Xe bubbles (tests/uo2), Xe ion log"),
 }

@@ -205,7 +205,10 @@ def stack():
 # samples of the north-star statistical criterion: cascades of the unmodified reference with distinct 32-bit seeds
 # (SURVEY.md §8c), summarised (tests/util.py::summarize_records).  1e6 Cu->Cu 10 keV cascades take ~4 min on 8 cores.
 STATISTICS_CASES = {"cu_on_cu_10keV": 1000000, "cu_on_cu_1keV": 1000000, "h_on_fe_100keV": 500000,
-                    "he_on_fe_100keV": 100000, "c_on_w_1MeV": 100000, "xe_on_zro2_500keV": 100000}
+                    "he_on_fe_100keV": 100000, "c_on_w_1MeV": 100000, "xe_on_zro2_500keV": 100000,
+                    # the file-energy / long-cascade configurations (tests/json/cu_on_cu.json, H->Fe at 1 MeV,
+                    # tests/json/xe_on_uo2.json)
+                    "cu_on_cu_150keV": 100000, "h_on_fe_1MeV": 200000, "xe_on_uo2_10MeV": 10000}
 
 
 def statistics(only=None):

@@ -307,7 +307,7 @@ def test_statistics_against_reference_golden(name):
 
 
 @pytest.mark.parametrize("name", ["cu_on_cu_10keV", "cu_on_cu_1keV", "h_on_fe_100keV", "he_on_fe_100keV", "c_on_w_1MeV",
-                                  "xe_on_zro2_500keV"])
+                                  "xe_on_zro2_500keV", "cu_on_cu_150keV", "h_on_fe_1MeV", "xe_on_uo2_10MeV"])
 def test_north_star_statistical_criterion(name):
     """BASELINE.json's statistical criterion at full size — 1e6 Cu->Cu 10 keV cascades, and 1e5..1e6 cascades of the
     other configurations — on the GPU against as many cascades of the UNMODIFIED reference (distinct 32-bit seeds),
