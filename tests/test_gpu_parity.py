@@ -84,7 +84,7 @@ def test_per_ion_parity_with_fp32_host_replay(name, n):
     on the device, libm on the host; FMA contraction), so a threshold test can flip; the allowances are the
     measured levels, not slack."""
     from tests import parity_cases
-    cfg = dict(tally_mask=capi.TALLY_IONLOG | capi.TALLY_RECORDS, ionlog_capacity=1 << 21)
+    cfg = dict(tally_mask=capi.TALLY_IONLOG | capi.TALLY_RECORDS, ionlog_capacity=1 << 21, **parity_cases.case_options(name))
     with capi.Engine(**cfg) as eng, util.HostSimEngine(**cfg) as hs, util.OracleEngine(util.ORC_RNG_PHILOX, **cfg) as orc:
         ions = parity_cases.setup_case(eng, name, n)
         parity_cases.setup_case(hs, name, n)

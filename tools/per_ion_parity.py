@@ -11,7 +11,7 @@ scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 tot = {}
 for name, n in parity_cases.PER_ION_CASES:
     n = max(1, int(n * scale))
-    cfg = dict(tally_mask=capi.TALLY_IONLOG | capi.TALLY_RECORDS, ionlog_capacity=1 << 23)
+    cfg = dict(tally_mask=capi.TALLY_IONLOG | capi.TALLY_RECORDS, ionlog_capacity=1 << 23, **parity_cases.case_options(name))
     with capi.Engine(**cfg) as eng, util.HostSimEngine(**cfg) as hs, util.OracleEngine(util.ORC_RNG_PHILOX, **cfg) as orc:
         ions = parity_cases.setup_case(eng, name, n)
         parity_cases.setup_case(hs, name, n)
