@@ -870,8 +870,8 @@ store_release(unsigned long long * p, unsigned long long v)
 }
 
 // Claim a ring slot for writing (which = POOL_ENQ) or reading (which = POOL_DEQ): the ticket dance of the
-// bounded MPMC queue.  A real call with scalar arguments only: inlined into the suspend / refill paths
-// it cost the sharing kernels 19 registers, i.e. two resident CTAs per SM.
+// bounded MPMC queue.  Inlined: as a real call (-DMTB_POOL_NOINLINE) the tests/uo2 workload was measured 9 % slower
+// in round 2 (profiles/r02_variant_sweeps.md), although the inlined form costs the sharing kernels registers.
 MTB_POOL_FN PoolSlot *
 pool_claim(PoolSlot * pool, unsigned long long * ctl, int which, unsigned long long * ticket)
 {
