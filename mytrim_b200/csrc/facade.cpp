@@ -937,6 +937,10 @@ bool
 TrimBase::followQueued(IonBase * pka, const mtb_ion & ion, std::queue<IonBase *> & recoils)
 {
   const size_t kMaxBatch = 8192, kFirstEvents = 32, kMaxEventsPerLaunch = 1u << 20;
+  // ions that were followed ahead of time but never asked for (an app that drops part of its queue) must not pile up:
+  // forgetting them only costs a repeated launch if they are asked for after all
+  if (_followed.size() > 4 * kMaxBatch)
+    _followed.clear();
   std::vector<const IonBase *> who(1, pka);
   std::vector<mtb_ion> ions(1, ion);
   for (IonBase * q : queueContainer(recoils))
