@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <iostream>
@@ -132,6 +133,12 @@ main(int argc, char * argv[])
   int ngpu = std::getenv("MYTRIM_GPUS") ? std::max(1, std::atoi(std::getenv("MYTRIM_GPUS"))) : 1;
   ngpu = std::min(ngpu, std::max(1, mtb_device_count()));
   const int n_chunks = (Nev + chunk_events - 1) / chunk_events;
+  // Two engines (own streams) per GPU by default: a launch of this workload ends in a tail in which a few CTAs finish
+  // the last heavy cascades while most SMs idle (work is shared inside a CTA only); with a second engine the CTAs of
+  // the next chunk's launch move onto the idle SMs.  Measured -5.5 % per chunk (profiles/r02_variant_sweeps.md).
+  const int engines_per_gpu =
+      std::getenv("MYTRIM_ENGINES_PER_GPU") ? std::max(1, std::min(4, std::atoi(std::getenv("MYTRIM_ENGINES_PER_GPU")))) : 2;
+  const int nworkers = std::min(ngpu * engines_per_gpu, std::max(n_chunks, 1));
 
   struct Chunk
   {
@@ -149,12 +156,12 @@ main(int argc, char * argv[])
     std::string error;
   };
   std::vector<Chunk> chunks(n_chunks);
-  std::vector<Device> devices(ngpu);
-  for (int d = 0; d < ngpu; ++d)
+  std::vector<Device> devices(nworkers); // one engine each; engine d runs on GPU d % ngpu
+  for (int d = 0; d < nworkers; ++d)
   {
     devices[d].simconf.reset(new SimconfType);
     devices[d].simconf->seed(seed < 0 ? -seed : seed); // same Philox key on every device
-    devices[d].simconf->device = d;
+    devices[d].simconf->device = d % ngpu;
     devices[d].trim.reset(new TrimXeLog(devices[d].simconf.get(), sample, 1ull << 22));
   }
   std::mutex mtx;
@@ -241,8 +248,9 @@ main(int argc, char * argv[])
     }
   };
   std::vector<std::thread> threads;
-  for (int d = 0; d < ngpu; ++d)
+  for (int d = 0; d < nworkers; ++d)
     threads.emplace_back(worker, d);
+  const auto t_transport0 = std::chrono::steady_clock::now();
 
   MassInverter mass;
   EnergyInverter energy;
@@ -306,9 +314,9 @@ main(int argc, char * argv[])
       std::unique_lock<std::mutex> lk(mtx);
       cv.wait(lk, [&] {
         flush_done(lk);
-        return failed || c - next_to_write < 2 * ngpu;
+        return failed || c - next_to_write < 2 * nworkers;
       });
-      devices[c % ngpu].todo.push_back(c);
+      devices[c % nworkers].todo.push_back(c);
     }
     cv.notify_all();
   }
@@ -324,6 +332,7 @@ main(int argc, char * argv[])
   cv.notify_all();
   for (auto & t : threads)
     t.join();
+  const double wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_transport0).count();
   std::fclose(erec);
   std::fclose(rdist);
   if (failed)
@@ -335,7 +344,7 @@ main(int argc, char * argv[])
   }
 
   // join the per-GPU totals (the analogue of threadJoin)
-  double kernel_ms = 0.0; // slowest GPU: the devices run concurrently
+  double kernel_ms = 0.0; // slowest engine: the devices run concurrently (engines of one GPU overlap: see wall_ms)
   unsigned long long steps = 0, ions = 0;
   for (auto & dev : devices)
   {
@@ -353,8 +362,11 @@ main(int argc, char * argv[])
   if (std::getenv("MYTRIM_TIMING") && kernel_ms > 0.0)
     std::fprintf(stderr,
                  "{\"workload\": \"uo2_fission\", \"gpus\": %d, \"primaries\": %llu, \"collision_steps\": %llu, "
-                 "\"ions\": %llu, \"kernel_ms\": %.3f, \"primaries_per_s\": %.4g, \"collision_steps_per_s\": %.4g}\n",
-                 ngpu, n_primaries, steps, ions, kernel_ms, n_primaries / (kernel_ms * 1e-3), steps / (kernel_ms * 1e-3));
+                 "\"ions\": %llu, \"kernel_ms\": %.3f, \"primaries_per_s\": %.4g, \"collision_steps_per_s\": %.4g, "
+                 "\"engines_per_gpu\": %d, \"wall_ms\": %.3f, \"primaries_per_s_wall\": %.4g, "
+                 "\"collision_steps_per_s_wall\": %.4g}\n",
+                 ngpu, n_primaries, steps, ions, kernel_ms, n_primaries / (kernel_ms * 1e-3), steps / (kernel_ms * 1e-3),
+                 (nworkers + ngpu - 1) / ngpu, wall_ms, n_primaries / (wall_ms * 1e-3), steps / (wall_ms * 1e-3));
 
   // energy accounting of the whole run (the reference prints it per event, mytrim_uo2.C:345-349)
   std::cout << simconf->EelTotal << std::endl;

@@ -35,6 +35,8 @@ FLOP_PER_STEP = 930.0  # FP32-equivalent flops per collision step, SURVEY.md §8
 HEADLINE = "cu_on_cu_10keV"
 MASTER_SEED = 2344
 FP32_LANES = 148 * 128  # FP32 lanes of a B200: 148 SMs x 4 sub-partitions x 32
+# configurations whose launches have few primaries per lane (work-sharing kernels): also timed with two engines per GPU
+PIPELINED_CONFIGS = ("c_on_w_1MeV", "xe_on_zro2_500keV", "xe_on_uo2_10MeV", "uo2_fission")
 
 
 class ClockSampler:
@@ -440,8 +442,38 @@ def main():
                 e2.launch_resident(MASTER_SEED, (world + rank) * n)
                 e2.synchronize()
                 ms, st = e2.last_kernel_ms(), e2.counters()["steps"]
+                pipelined = None
+                if cname in PIPELINED_CONFIGS:
+                    # The same launches alternating over TWO engines (own streams) of this GPU, as apps/mytrim_uo2 runs
+                    # its chunks: the CTAs of the next launch take the SMs that the tail of the previous one leaves idle
+                    # (work is shared inside a CTA only).  Host clock around asynchronous launches + synchronize.
+                    e3, host3 = make_engine(cname, n)
+                    e3.upload_primaries_ptr(n, host3.data_ptr())
+                    e3.launch_resident(MASTER_SEED, rank * n)      # warm-up
+                    e3.synchronize()
+                    pair, n_l = (e2, e3), 4
+                    for e in pair:
+                        e.reset_tallies()
+                        if cw["tally"] & capi.TALLY_IONLOG:
+                            lib.mtb_clear_lists(e._h)
+                    flush.zero_()
+                    torch.cuda.synchronize()
+                    tp = time.perf_counter()
+                    for i in range(n_l):
+                        e = pair[i % 2]
+                        if i >= 2:
+                            e.synchronize()
+                            if cw["tally"] & capi.TALLY_IONLOG:
+                                lib.mtb_clear_lists(e._h)
+                        e.launch_resident(MASTER_SEED, ((2 + i) * world + rank) * n)
+                    for e in pair:
+                        e.synchronize()
+                    pipelined = [(time.perf_counter() - tp) * 1e3 / n_l, float(sum(e.counters()["steps"] for e in pair)) / n_l]
+                    e3.close()
                 e2.close()
-            v = torch.tensor([ms, float(st)], dtype=torch.float64, device="cuda")
+            if cname == name or cname not in PIPELINED_CONFIGS:
+                pipelined = None
+            v = torch.tensor([ms, float(st)] + (pipelined or [0.0, 0.0]), dtype=torch.float64, device="cuda")
             if world > 1:
                 vmax, vsum = v.clone(), v.clone()
                 dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
@@ -452,6 +484,11 @@ def main():
             configs[cname] = {"cascades_per_s": n * world / t, "collision_steps_per_s": float(vsum[1]) / t,
                               "steps_per_cascade": float(vsum[1]) / (n * world), "primaries_per_gpu": n,
                               "kernel_ms": float(vmax[0]), "what": cw["desc"]}
+            if pipelined:
+                tp2 = float(vmax[2]) * 1e-3
+                configs[cname]["two_engines_per_gpu"] = {
+                    "cascades_per_s": n * world / tp2, "collision_steps_per_s": float(vsum[3]) / tp2, "ms_per_launch": float(vmax[2]),
+                    "launches": 4, "clock": "host clock around asynchronous launches alternating over two engines + synchronize"}
 
     if world > 1:
         barrier()

@@ -501,8 +501,13 @@ build_tables(mtb_handle * h)
   // process (a Trim object's batch and single-ion engines, one engine per configuration in bench.py), so it is set to
   // the device limit once and for all; the occupancy query and the launches use the handle's own size.
   const int smem_limit = h->smem_optin;
+  int carveout = -1;
+  if (const char * env = std::getenv("MYTRIM_B200_CARVEOUT")) // tuning knob: shared-memory share of the L1 array, percent
+    carveout = std::atoi(env);
 #define MTB_SETUP_KERNEL(TRAITS, V, SH)                                                                                     \
   MTB_CUDA(cudaFuncSetAttribute(transport_kernel<TRAITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit)); \
+  if (carveout >= 0)                                                                                                        \
+    MTB_CUDA(cudaFuncSetAttribute(transport_kernel<TRAITS>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));   \
   MTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->bps[V][SH], transport_kernel<TRAITS>, kBlock, h->smem_bytes));  \
   h->bps[V][SH] = std::max(h->bps[V][SH], 1);
   MTB_SETUP_KERNEL(TraitsFast, VARIANT_FAST, 0)
@@ -513,6 +518,10 @@ build_tables(mtb_handle * h)
   h->bps[VARIANT_MONO_NOREC][1] = h->bps[VARIANT_MONO][1]; // small launches share through the MONO twin
   MTB_SETUP_KERNEL(TraitsClusters, VARIANT_CLUSTERS, 0)
   MTB_SETUP_KERNEL(TraitsClustersShare, VARIANT_CLUSTERS, 1)
+  MTB_SETUP_KERNEL(TraitsMonoEvac, VARIANT_MONO_EVAC, 0)
+  MTB_SETUP_KERNEL(TraitsMonoEvacShare, VARIANT_MONO_EVAC, 1)
+  MTB_SETUP_KERNEL(TraitsClustersLog, VARIANT_CLUSTERS_LOG, 0)
+  MTB_SETUP_KERNEL(TraitsClustersLogShare, VARIANT_CLUSTERS_LOG, 1)
   MTB_SETUP_KERNEL(TraitsLayers, VARIANT_LAYERS, 0)
   MTB_SETUP_KERNEL(TraitsLayersShare, VARIANT_LAYERS, 1)
   MTB_SETUP_KERNEL(TraitsGeneric, VARIANT_GENERIC, 0)
@@ -566,6 +575,18 @@ launch_kernel(mtb_handle * h, const LaunchParams & P, unsigned blocks, Variant v
         transport_kernel<TraitsClustersShare><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
       else
         transport_kernel<TraitsClusters><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+      break;
+    case VARIANT_MONO_EVAC:
+      if (share)
+        transport_kernel<TraitsMonoEvacShare><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+      else
+        transport_kernel<TraitsMonoEvac><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+      break;
+    case VARIANT_CLUSTERS_LOG:
+      if (share)
+        transport_kernel<TraitsClustersLogShare><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+      else
+        transport_kernel<TraitsClustersLog><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
       break;
     case VARIANT_LAYERS:
       if (share)

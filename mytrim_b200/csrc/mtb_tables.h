@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -720,7 +721,10 @@ build_host_tables(const HostConfig & H_in, HostTables & T, LaunchParams & P, std
     bins = (int)std::min<double>(std::max(16384.0, 4.0 * std::ceil(extent) + 1.0), 1 << 20);
   P.hist_bins = bins;
   P.evac_rows = c.evac_rows > 0 ? c.evac_rows : 32;
-  P.smem_hist_bins = (c.tally_mask & MTB_TALLY_VAC_DEPTH) ? std::min(bins, kSmemHistMax) : 0;
+  int smem_hist_max = kSmemHistMax;
+  if (const char * env = std::getenv("MYTRIM_B200_SMEM_HIST")) // tuning knob: depth bins mirrored in shared memory
+    smem_hist_max = std::max(0, std::min(std::atoi(env), 8192));
+  P.smem_hist_bins = (c.tally_mask & MTB_TALLY_VAC_DEPTH) ? std::min(bins, smem_hist_max) : 0;
   P.one_material = (P.n_materials == 1 && (P.geom_kind == MTB_GEOM_SOLID || P.geom_kind == MTB_GEOM_LAYERS)) ? 1 : 0;
   P.mono = (P.one_material && P.n_elements == 1) ? 1 : 0;
   P.ionlog_cap = (c.tally_mask & MTB_TALLY_IONLOG) ? (c.ionlog_capacity ? c.ionlog_capacity : (1ull << 20)) : 0;

@@ -115,6 +115,10 @@ constexpr uint32_t kTallyFast = MTB_TALLY_VAC_DEPTH;
 constexpr uint32_t kFeatMono = F_MONO;
 constexpr uint32_t kFeatClusters = F_CUSTOM | F_CLUSTERS | F_TALLY_RT;
 constexpr uint32_t kTallyClusters = MTB_TALLY_IONLOG | MTB_TALLY_PHONON;
+// the tests/uo2 driver itself asks for the ion log and nothing else: tallies fixed at compile time (no run-time
+// tally tests on the hand-over paths, no energy-partition sums), measured -3.6 % on the uo2 workload (r02v)
+constexpr uint32_t kFeatClustersLog = F_CUSTOM | F_CLUSTERS;
+constexpr uint32_t kTallyClustersLog = MTB_TALLY_IONLOG;
 constexpr uint32_t kFeatLayers = F_FOLLOW | F_VACMODEL | F_TALLY_RT;
 constexpr uint32_t kFeatGeneric =
     F_CUSTOM | F_CLUSTERS | F_GEOM_ANY | F_CUT | F_POTENTIAL | F_FOLLOW | F_VACMODEL | F_TALLY_RT | F_DIAG;
@@ -125,8 +129,13 @@ typedef TraitsT<kFeatFast | F_SHARE, kTallyFast> TraitsFastShare;
 typedef TraitsT<kFeatMono, kTallyFast> TraitsMono;
 typedef TraitsT<kFeatMono | F_SHARE, kTallyFast> TraitsMonoShare;
 typedef TraitsT<kFeatMono | F_NOREC, kTallyFast> TraitsMonoNoRec; // what bench.py times: TrimVacCount tallies only
+// MONO with the TrimVacEnergyCount tally instead (validation/c_on_w/input.json: "type": "vacenergycount")
+typedef TraitsT<kFeatMono, MTB_TALLY_VAC_ENERGY> TraitsMonoEvac;
+typedef TraitsT<kFeatMono | F_SHARE, MTB_TALLY_VAC_ENERGY> TraitsMonoEvacShare;
 typedef TraitsT<kFeatClusters, kTallyClusters> TraitsClusters;
 typedef TraitsT<kFeatClusters | F_SHARE, kTallyClusters> TraitsClustersShare;
+typedef TraitsT<kFeatClustersLog, kTallyClustersLog> TraitsClustersLog;
+typedef TraitsT<kFeatClustersLog | F_SHARE, kTallyClustersLog> TraitsClustersLogShare;
 typedef TraitsT<kFeatLayers, kTallyAll> TraitsLayers;
 typedef TraitsT<kFeatLayers | F_SHARE, kTallyAll> TraitsLayersShare;
 typedef TraitsT<kFeatGeneric, kTallyAll> TraitsGeneric;
@@ -148,13 +157,15 @@ enum Variant
   VARIANT_GENERIC,
   VARIANT_MONO,
   VARIANT_MONO_NOREC, // chosen per launch (mtb_engine.cu: launch_transport), never by pick_variant
+  VARIANT_CLUSTERS_LOG,
+  VARIANT_MONO_EVAC,
   VARIANT_COUNT
 };
 
 inline uint32_t
 variant_features(Variant v)
 {
-  return v == VARIANT_FAST ? kFeatFast : v == VARIANT_MONO ? kFeatMono : v == VARIANT_MONO_NOREC ? (kFeatMono | F_NOREC) : v == VARIANT_CLUSTERS ? kFeatClusters : v == VARIANT_LAYERS ? kFeatLayers : kFeatGeneric;
+  return v == VARIANT_FAST ? kFeatFast : (v == VARIANT_MONO || v == VARIANT_MONO_EVAC) ? kFeatMono : v == VARIANT_MONO_NOREC ? (kFeatMono | F_NOREC) : v == VARIANT_CLUSTERS ? kFeatClusters : v == VARIANT_CLUSTERS_LOG ? kFeatClustersLog : v == VARIANT_LAYERS ? kFeatLayers : kFeatGeneric;
 }
 
 // Features a configuration needs (F_CUSTOM is decided per primary: variants without it hand
@@ -195,6 +206,10 @@ pick_variant(const LaunchParams & P, bool custom)
 {
   if (!custom && variant_covers(kFeatFast, kTallyFast, P))
     return P.mono ? VARIANT_MONO : VARIANT_FAST;
+  if (!custom && P.mono && variant_covers(kFeatMono & ~(uint32_t)F_MONO, MTB_TALLY_VAC_ENERGY, P))
+    return VARIANT_MONO_EVAC;
+  if (P.geom_kind == MTB_GEOM_CLUSTERS && variant_covers(kFeatClustersLog, kTallyClustersLog, P))
+    return VARIANT_CLUSTERS_LOG;
   if (variant_covers(kFeatClusters, kTallyClusters, P))
     return VARIANT_CLUSTERS;
   if (!custom && variant_covers(kFeatLayers, kTallyAll, P))

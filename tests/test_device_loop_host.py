@@ -217,11 +217,14 @@ def test_dense_clusters_neighbourhood_filter(bc, ncl, kn, radii):
     assert np.abs(ho - hh).sum() <= 0.02 * ho.sum() + 2, (ho.sum(), hh.sum(), np.abs(ho - hh).sum())
 
 
-def test_clusters_variant_equals_generic():
-    """The lean clusters variant of the lane loop (sampleClusters geometry, per-primary species, ion log /
-    energy partition compiled in; everything else compiled out) against the all-options loop: identical."""
+@pytest.mark.parametrize("phonon", [True, False])
+def test_clusters_variant_equals_generic(phonon):
+    """The lean clusters variants of the lane loop (sampleClusters geometry, per-primary species, ion log /
+    energy partition compiled in; everything else compiled out) against the all-options loop: identical.
+    phonon=False is the mask of the tests/uo2 driver itself (ion log only): the CLUSTERS-LOG variant, tallies
+    fixed at compile time."""
     cl = np.loadtxt(os.path.join(util.GOLDEN, "uo2_out.clcoor"))[:, :4]
-    cfg = dict(tally_mask=capi.TALLY_RECORDS | capi.TALLY_PHONON | capi.TALLY_IONLOG, ionlog_z=54)
+    cfg = dict(tally_mask=capi.TALLY_RECORDS | (capi.TALLY_PHONON if phonon else 0) | capi.TALLY_IONLOG, ionlog_z=54)
     ions = _fission_like_primaries(40)
     ions["pos"][:8] = cl[np.arange(8) % len(cl), :3] + 2.0   # some start inside a bubble
     with util.HostSimEngine(**cfg) as a, util.HostSimEngine(**cfg) as b:
@@ -272,6 +275,28 @@ def test_layers_variant_equals_generic(cfg):
             xa, za = a.range_list()
             xb, zb = b.range_list()
             assert np.array_equal(np.sort(xa), np.sort(xb)) and len(xa) > 0
+
+
+def test_mono_evac_variant_equals_generic():
+    """Single-element sample + TrimVacEnergyCount tally (validation/c_on_w/input.json) selects the MONO-EVAC
+    variant: identical to the all-options loop, 2-D tally included."""
+    cfg = dict(tally_mask=capi.TALLY_VAC_ENERGY | capi.TALLY_RECORDS)
+    with util.HostSimEngine(**cfg) as a, util.HostSimEngine(**cfg) as b:
+        for e in (a, b):
+            c = util.setup_engine(e, "c_on_w_1MeV")
+        b._lib.hs_force_generic(b._h, 1)
+        ions = util.primaries_for(c, 6)
+        ions["E"] = 1.0e5
+        ra = a.run(ions, seed=21, records=True)
+        rb = b.run(ions, seed=21, records=True)
+        for f in ra.dtype.names:
+            assert np.array_equal(ra[f], rb[f]), f
+        ca, cb = a.counters(), b.counters()
+        for k in ca:
+            if k != "stack_max":
+                assert abs(ca[k] - cb[k]) <= 1e-12 * abs(cb[k]), k
+        ea, eb = a.vac_energy(), b.vac_energy()
+        assert np.array_equal(ea, eb) and ea.sum() > 0
 
 
 def test_fast_kernel_defers_unknown_species():

@@ -437,9 +437,9 @@ def test_fast_kernel_defers_unknown_species():
         assert abs(ca["steps"] - cb["steps"]) <= 1e-3 * cb["steps"] and ca["primaries"] == cb["primaries"] == len(ions)
 
 
-@pytest.mark.parametrize("which", ["mono", "fast", "clusters", "layers"])
+@pytest.mark.parametrize("which", ["mono", "fast", "clusters", "layers", "clusters_log", "mono_evac"])
 def test_lean_variants_agree_with_generic_kernel(which):
-    """Every lean kernel variant (mtb_transport.cuh: MONO / FAST / CLUSTERS / LAYERS) against the all-options
+    """Every lean kernel variant (mtb_transport.cuh: MONO / FAST / CLUSTERS / LAYERS / CLUSTERS-LOG / MONO-EVAC) against the all-options
     kernel on the same primaries and seeds.  Different instantiations contract FMAs differently, so agreement is
     to the trajectory tolerance; the integer tallies agree for all cascades without a branch flip.  (A
     single-element sample takes MONO by default; MYTRIM_B200_NO_MONO routes it through FAST.)"""
@@ -449,6 +449,12 @@ def test_lean_variants_agree_with_generic_kernel(which):
         def setup(e):
             c = util.setup_engine(e, "cu_on_cu_10keV")
             return util.primaries_for(c, 4000)
+    elif which == "mono_evac":
+        # validation/c_on_w/input.json: TrimVacEnergyCount on a single-element sample
+        cfg = dict(tally_mask=capi.TALLY_VAC_ENERGY | capi.TALLY_RECORDS)
+        def setup(e):
+            c = util.setup_engine(e, "c_on_w_1MeV")
+            return util.primaries_for(c, 1500)
     elif which == "layers":
         cfg = dict(tally_mask=capi.TALLY_VAC_ENERGY | capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS, follow=capi.FOLLOW_GEN_LT,
                    follow_max_gen=2, vacancy_model=capi.VAC_KP)
@@ -456,7 +462,8 @@ def test_lean_variants_agree_with_generic_kernel(which):
             c = util.setup_engine(e, "xe_on_zro2_500keV")
             return util.primaries_for(c, 600)
     else:
-        cfg = dict(tally_mask=capi.TALLY_PHONON | capi.TALLY_RECORDS | capi.TALLY_IONLOG, ionlog_z=54)
+        # "clusters": ion log + energy partition (run-time tallies); "clusters_log": the tests/uo2 driver's own mask
+        cfg = dict(tally_mask=(capi.TALLY_PHONON if which == "clusters" else 0) | capi.TALLY_RECORDS | capi.TALLY_IONLOG, ionlog_z=54)
         cl = np.loadtxt(os.path.join(util.GOLDEN, "uo2_out.clcoor"))[:, :4]
         def setup(e):
             from tests.test_device_loop_host import _fission_like_primaries
@@ -472,7 +479,8 @@ def test_lean_variants_agree_with_generic_kernel(which):
             ions = setup(a)
             ra = a.run(ions, seed=31, records=True)
             ca = a.counters()
-            la = len(a.ion_log()) if which == "clusters" else 0
+            la = len(a.ion_log()) if which.startswith("clusters") else 0
+            ea = a.vac_energy(rows=32, bins=16384) if which == "mono_evac" else None
     finally:
         if knob:
             os.environ.pop(knob)
@@ -482,7 +490,8 @@ def test_lean_variants_agree_with_generic_kernel(which):
             setup(b)
             rb = b.run(ions, seed=31, records=True)
             cb = b.counters()
-            lb = len(b.ion_log()) if which == "clusters" else 0
+            lb = len(b.ion_log()) if which.startswith("clusters") else 0
+            eb = b.vac_energy(rows=32, bins=16384) if which == "mono_evac" else None
     finally:
         os.environ.pop("MYTRIM_B200_VARIANT")
     same = (ra["steps"] == rb["steps"]) & (ra["vacancies"] == rb["vacancies"]) & (ra["ions"] == rb["ions"])
@@ -494,6 +503,11 @@ def test_lean_variants_agree_with_generic_kernel(which):
     assert abs(ca["steps"] - cb["steps"]) <= 2e-3 * cb["steps"] and ca["primaries"] == cb["primaries"] == len(ions)
     assert abs(ca["vacancies_created"] - cb["vacancies_created"]) <= 2e-3 * cb["vacancies_created"]
     assert abs(la - lb) <= 0.02 * lb + 4
+    if ea is not None:
+        # the 2-D tally of TrimVacEnergyCount: row sums (energy decades) and depth profile agree to the flip level
+        assert ea.sum() > 0
+        assert abs(int(ea.sum()) - int(eb.sum())) <= 2e-3 * eb.sum()
+        assert np.abs(ea.sum(axis=1).astype(float) - eb.sum(axis=1)).max() <= 5e-3 * eb.sum(axis=1).max() + 4
 
 
 def test_work_sharing_pool_is_result_neutral():
