@@ -103,8 +103,9 @@ def reference_cascades_per_s(workload, n, threads, timeout=900):
     """Times oracle/_ref/ref_driver (the unmodified reference library, runmytrim-equivalent set-up)."""
     from mytrim_b200 import workloads
     from tests import util
-    c = workloads.CONFIGS[workload]
-    tally = REF_TALLY.get(workloads.BENCH_WORKLOADS[workload]["tally"], "vaccount")
+    wl = workloads.BENCH_WORKLOADS[workload]
+    c = workloads.CONFIGS[wl.get("config", workload)]
+    tally = wl.get("ref_tally") or REF_TALLY.get(wl["tally"], "vaccount")
     lines = util.reference_script(c["ion"], c["materials"], c["thicknesses"], n=n, tally=tally,
                                   threads=threads, master=MASTER_SEED, box=c.get("box"))
     lines.append("run")
@@ -134,7 +135,7 @@ def reference_uo2_primaries_per_s(events_per_proc, procs, timeout=900):
 
 # reference cascades per core and step (a step of the reference arm is ~2-20 s of wall time on all cores)
 REF_PER_CORE = {"cu_on_cu_10keV": 400, "h_on_fe_100keV": 2000, "he_on_fe_100keV": 100, "c_on_w_1MeV": 8,
-                "xe_on_zro2_500keV": 2, "uo2_fission": 2, "cu_on_cu_150keV": 20, "h_on_fe_1MeV": 1000, "xe_on_uo2_10MeV": 1}
+                "xe_on_zro2_500keV": 2, "xe_on_zro2_500keV_trimrecoils": 40, "uo2_fission": 2, "cu_on_cu_150keV": 20, "h_on_fe_1MeV": 1000, "xe_on_uo2_10MeV": 1}
 
 
 def run_reference_arm(args):
@@ -277,6 +278,7 @@ def main():
     def make_engine(wname, n):
         w = workloads.BENCH_WORKLOADS[wname]
         kw = dict(tally_mask=w["tally"], device=local_rank)
+        kw.update(w.get("engine", {}))
         if w["tally"] & capi.TALLY_IONLOG:
             kw.update(ionlog_z=w.get("ionlog_z", 0), ionlog_capacity=max(1 << 20, 64 * n))
         e = capi.Engine(**kw)

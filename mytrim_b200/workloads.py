@@ -49,6 +49,12 @@ BENCH_WORKLOADS = {
                         desc="C->W 1 MeV, full cascades, TrimVacEnergyCount tallies (validation/c_on_w/input.json)"),
     "xe_on_zro2_500keV": dict(primaries=1 << 16, tally=capi.TALLY_VAC_DEPTH,
                               desc="Xe->ZrO2 500 keV, 50 x 10 A layers (inputs/samplelayers_zro2_multilayer.in), full cascades"),
+    # configuration 4 as the reference's own driver runs it (apps/mytrim_layers.C:72,116-117: TrimRecoils = primaries and
+    # first-generation recoils, Kinchin-Pease estimate for the rest)
+    "xe_on_zro2_500keV_trimrecoils": dict(primaries=1 << 20, tally=0, config="xe_on_zro2_500keV", ref_tally="recoils",
+                                          engine=dict(follow=capi.FOLLOW_GEN_LT, follow_max_gen=2, vacancy_model=capi.VAC_KP),
+                                          desc="Xe->ZrO2 500 keV, 50 x 10 A layers, TrimRecoils as in apps/mytrim_layers.C "
+                                               "(recoils of generation < 2 followed, Kinchin-Pease for generation 2)"),
     # the file-energy / long-cascade variants of configurations 1 and 2
     "cu_on_cu_150keV": dict(primaries=1 << 17, tally=capi.TALLY_VAC_DEPTH,
                             desc="Cu->Cu 150 keV, full cascades, TrimVacCount tallies (tests/json/cu_on_cu.json)"),
@@ -93,5 +99,5 @@ def setup_workload(eng, name, n, first_primary=0):
         setup_uo2(eng)
         assert n % 2 == 0 and first_primary % 2 == 0
         return capi.fission_pairs(UO2_SEED, first_primary // 2, n // 2, UO2_BOX)
-    c = setup_engine(eng, name)
+    c = setup_engine(eng, BENCH_WORKLOADS.get(name, {}).get("config", name))
     return primaries_for(c, n)
