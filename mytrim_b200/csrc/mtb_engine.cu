@@ -518,6 +518,8 @@ build_tables(mtb_handle * h)
   h->bps[VARIANT_MONO_NOREC][1] = h->bps[VARIANT_MONO][1]; // small launches share through the MONO twin
   MTB_SETUP_KERNEL(TraitsClusters, VARIANT_CLUSTERS, 0)
   MTB_SETUP_KERNEL(TraitsClustersShare, VARIANT_CLUSTERS, 1)
+  MTB_SETUP_KERNEL(TraitsFastPhonon, VARIANT_FAST_PHONON, 0)
+  MTB_SETUP_KERNEL(TraitsFastPhononShare, VARIANT_FAST_PHONON, 1)
   MTB_SETUP_KERNEL(TraitsMonoEvac, VARIANT_MONO_EVAC, 0)
   MTB_SETUP_KERNEL(TraitsMonoEvacShare, VARIANT_MONO_EVAC, 1)
   MTB_SETUP_KERNEL(TraitsClustersLog, VARIANT_CLUSTERS_LOG, 0)
@@ -575,6 +577,12 @@ launch_kernel(mtb_handle * h, const LaunchParams & P, unsigned blocks, Variant v
         transport_kernel<TraitsClustersShare><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
       else
         transport_kernel<TraitsClusters><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+      break;
+    case VARIANT_FAST_PHONON:
+      if (share)
+        transport_kernel<TraitsFastPhononShare><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+      else
+        transport_kernel<TraitsFastPhonon><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
       break;
     case VARIANT_MONO_EVAC:
       if (share)

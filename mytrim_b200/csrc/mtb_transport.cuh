@@ -132,6 +132,9 @@ typedef TraitsT<kFeatMono | F_NOREC, kTallyFast> TraitsMonoNoRec; // what bench.
 // MONO with the TrimVacEnergyCount tally instead (validation/c_on_w/input.json: "type": "vacenergycount")
 typedef TraitsT<kFeatMono, MTB_TALLY_VAC_ENERGY> TraitsMonoEvac;
 typedef TraitsT<kFeatMono | F_SHARE, MTB_TALLY_VAC_ENERGY> TraitsMonoEvacShare;
+// FAST with the energy partition of TrimPhononOut instead of the depth histograms
+typedef TraitsT<kFeatFast, MTB_TALLY_PHONON> TraitsFastPhonon;
+typedef TraitsT<kFeatFast | F_SHARE, MTB_TALLY_PHONON> TraitsFastPhononShare;
 typedef TraitsT<kFeatClusters, kTallyClusters> TraitsClusters;
 typedef TraitsT<kFeatClusters | F_SHARE, kTallyClusters> TraitsClustersShare;
 typedef TraitsT<kFeatClustersLog, kTallyClustersLog> TraitsClustersLog;
@@ -159,13 +162,14 @@ enum Variant
   VARIANT_MONO_NOREC, // chosen per launch (mtb_engine.cu: launch_transport), never by pick_variant
   VARIANT_CLUSTERS_LOG,
   VARIANT_MONO_EVAC,
+  VARIANT_FAST_PHONON,
   VARIANT_COUNT
 };
 
 inline uint32_t
 variant_features(Variant v)
 {
-  return v == VARIANT_FAST ? kFeatFast : (v == VARIANT_MONO || v == VARIANT_MONO_EVAC) ? kFeatMono : v == VARIANT_MONO_NOREC ? (kFeatMono | F_NOREC) : v == VARIANT_CLUSTERS ? kFeatClusters : v == VARIANT_CLUSTERS_LOG ? kFeatClustersLog : v == VARIANT_LAYERS ? kFeatLayers : kFeatGeneric;
+  return (v == VARIANT_FAST || v == VARIANT_FAST_PHONON) ? kFeatFast : (v == VARIANT_MONO || v == VARIANT_MONO_EVAC) ? kFeatMono : v == VARIANT_MONO_NOREC ? (kFeatMono | F_NOREC) : v == VARIANT_CLUSTERS ? kFeatClusters : v == VARIANT_CLUSTERS_LOG ? kFeatClustersLog : v == VARIANT_LAYERS ? kFeatLayers : kFeatGeneric;
 }
 
 // Features a configuration needs (F_CUSTOM is decided per primary: variants without it hand
@@ -208,6 +212,8 @@ pick_variant(const LaunchParams & P, bool custom)
     return P.mono ? VARIANT_MONO : VARIANT_FAST;
   if (!custom && P.mono && variant_covers(kFeatMono & ~(uint32_t)F_MONO, MTB_TALLY_VAC_ENERGY, P))
     return VARIANT_MONO_EVAC;
+  if (!custom && variant_covers(kFeatFast, MTB_TALLY_PHONON, P))
+    return VARIANT_FAST_PHONON;
   if (P.geom_kind == MTB_GEOM_CLUSTERS && variant_covers(kFeatClustersLog, kTallyClustersLog, P))
     return VARIANT_CLUSTERS_LOG;
   if (variant_covers(kFeatClusters, kTallyClusters, P))

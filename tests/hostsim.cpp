@@ -205,6 +205,8 @@ hs_run(hs_engine * e, uint64_t n, const mtb_ion * primaries, uint64_t seed, uint
       lane_loop<TraitsMono>(P, S, 0);
     else if (which == VARIANT_CLUSTERS)
       lane_loop<TraitsClusters>(P, S, 0);
+    else if (which == VARIANT_FAST_PHONON)
+      lane_loop<TraitsFastPhonon>(P, S, 0);
     else if (which == VARIANT_MONO_EVAC)
       lane_loop<TraitsMonoEvac>(P, S, 0);
     else if (which == VARIANT_CLUSTERS_LOG)

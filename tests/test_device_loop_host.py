@@ -299,6 +299,28 @@ def test_mono_evac_variant_equals_generic():
         assert np.array_equal(ea, eb) and ea.sum() > 0
 
 
+def test_fast_phonon_variant_equals_generic():
+    """Layered compound sample + the energy partition of TrimPhononOut selects the FAST-PHONON variant: identical
+    to the all-options loop, and the partition closes (Eel + Enuc = energy of the primaries)."""
+    cfg = dict(tally_mask=capi.TALLY_PHONON | capi.TALLY_RECORDS)
+    with util.HostSimEngine(**cfg) as a, util.HostSimEngine(**cfg) as b:
+        for e in (a, b):
+            c = util.setup_engine(e, "xe_on_zro2_500keV")
+        b._lib.hs_force_generic(b._h, 1)
+        ions = util.primaries_for(c, 4)
+        ions["E"] = 6.0e4
+        ra = a.run(ions, seed=13, records=True)
+        rb = b.run(ions, seed=13, records=True)
+        for f in ra.dtype.names:
+            assert np.array_equal(ra[f], rb[f]), f
+        ca, cb = a.counters(), b.counters()
+        for k in ca:
+            if k != "stack_max":
+                assert abs(ca[k] - cb[k]) <= 1e-12 * abs(cb[k]), k
+        E0 = ions["E"].sum()
+        assert ca["EnucTotal"] > 0 and abs(ca["EelTotal"] + ca["EnucTotal"] - E0) < 1e-6 * E0
+
+
 def test_fast_kernel_defers_unknown_species():
     """Layered sample + TrimVacCount tallies selects the compile-time fast loop; primaries whose
     species has no class are handed to the generic loop and the union equals a generic-only run."""

@@ -437,7 +437,7 @@ def test_fast_kernel_defers_unknown_species():
         assert abs(ca["steps"] - cb["steps"]) <= 1e-3 * cb["steps"] and ca["primaries"] == cb["primaries"] == len(ions)
 
 
-@pytest.mark.parametrize("which", ["mono", "fast", "clusters", "layers", "clusters_log", "mono_evac"])
+@pytest.mark.parametrize("which", ["mono", "fast", "clusters", "layers", "clusters_log", "mono_evac", "fast_phonon"])
 def test_lean_variants_agree_with_generic_kernel(which):
     """Every lean kernel variant (mtb_transport.cuh: MONO / FAST / CLUSTERS / LAYERS / CLUSTERS-LOG / MONO-EVAC) against the all-options
     kernel on the same primaries and seeds.  Different instantiations contract FMAs differently, so agreement is
@@ -455,6 +455,12 @@ def test_lean_variants_agree_with_generic_kernel(which):
         def setup(e):
             c = util.setup_engine(e, "c_on_w_1MeV")
             return util.primaries_for(c, 1500)
+    elif which == "fast_phonon":
+        # TrimPhononOut's energy partition on a layered compound sample
+        cfg = dict(tally_mask=capi.TALLY_PHONON | capi.TALLY_RECORDS)
+        def setup(e):
+            c = util.setup_engine(e, "xe_on_zro2_500keV")
+            return util.primaries_for(c, 600)
     elif which == "layers":
         cfg = dict(tally_mask=capi.TALLY_VAC_ENERGY | capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS, follow=capi.FOLLOW_GEN_LT,
                    follow_max_gen=2, vacancy_model=capi.VAC_KP)
@@ -503,6 +509,10 @@ def test_lean_variants_agree_with_generic_kernel(which):
     assert abs(ca["steps"] - cb["steps"]) <= 2e-3 * cb["steps"] and ca["primaries"] == cb["primaries"] == len(ions)
     assert abs(ca["vacancies_created"] - cb["vacancies_created"]) <= 2e-3 * cb["vacancies_created"]
     assert abs(la - lb) <= 0.02 * lb + 4
+    if which == "fast_phonon":
+        E0 = ions["E"].sum()
+        assert abs(ca["EelTotal"] + ca["EnucTotal"] - E0) < 1e-6 * E0
+        assert abs(ca["EnucTotal"] - cb["EnucTotal"]) < 2e-3 * cb["EnucTotal"]
     if ea is not None:
         # the 2-D tally of TrimVacEnergyCount: row sums (energy decades) and depth profile agree to the flip level
         assert ea.sum() > 0
