@@ -255,7 +255,7 @@ main(int argc, char * argv[])
   MassInverter mass;
   EnergyInverter energy;
   Real Efiss = 0.0;
-  unsigned long long n_primaries = 0;
+  unsigned long long n_primaries = 0, n_degenerate = 0;
   int next_to_write = 0;
   auto flush_done = [&](std::unique_lock<std::mutex> &) {
     while (next_to_write < n_chunks && chunks[next_to_write].done)
@@ -304,6 +304,17 @@ main(int argc, char * argv[])
       ff2->_m = A2;
       ff2->_E = E2 * 1.0e6;
       ff2->setEf();
+      for (IonMDTag * ff : {ff1, ff2})
+        if (ff->_Z < 1 || ff->_Z > 92)
+        {
+          // About one draw in 1e6 ends the bisection of Inverter::x at A = 235 * 2^-33, i.e. Z = 0: the reference
+          // then reads scoef[-1] (undefined behaviour).  The fragment keeps its place (its index is its Philox
+          // stream) but carries no energy and stops where it starts.
+          ff->_Z = ff->_Z < 1 ? 1 : 92;
+          ff->_m = std::max(ff->_m, 1.0);
+          ff->_E = 0.0;
+          ++n_degenerate;
+        }
       ch.primaries.push_back(ff1);
       ch.primaries.push_back(ff2);
       Efiss += ff1->_E + ff2->_E;
@@ -368,6 +379,8 @@ main(int argc, char * argv[])
                  ngpu, n_primaries, steps, ions, kernel_ms, n_primaries / (kernel_ms * 1e-3), steps / (kernel_ms * 1e-3),
                  (nworkers + ngpu - 1) / ngpu, wall_ms, n_primaries / (wall_ms * 1e-3), steps / (wall_ms * 1e-3));
 
+  if (n_degenerate)
+    std::cerr << "WARNING: " << n_degenerate << " fragment(s) with Z outside 1..92 were emitted without energy" << std::endl;
   // energy accounting of the whole run (the reference prints it per event, mytrim_uo2.C:345-349)
   std::cout << simconf->EelTotal << std::endl;
   std::cout << simconf->EnucTotal << std::endl;

@@ -290,6 +290,9 @@ int mtb_allreduce(mtb_handle ** handles, int n_handles);
  * the cumulative fission yield (MassInverter, invert.C:30-56), total kinetic energy (EnergyInverter, invert.C:59-78),
  * Z1 = round(92 A1 / 235), isotropic back-to-back directions, uniform origin in the box w.  Writes 2 n_events
  * primaries (gen 0, tag -1, Ef = 3 eV as IonBase::setEf gives them) and returns their summed energy in *e_total.
+ * About one draw in 1e6 ends the reference's 32-step bisection at A1 = 235 * 2^-33, i.e. Z1 = 0, for which the
+ * reference's stopping reads scoef[-1] (undefined behaviour): such a fragment keeps its place in the list (its index is
+ * its Philox stream) with Z = 1, m = 1 and NO energy — it stops where it starts — and a note goes to stderr.
  * Host only; sharding a run = giving every GPU its own event range. */
 int mtb_fission_pairs(uint32_t seed, uint64_t first_event, uint64_t n_events, const double w[3], mtb_ion * out,
                       double * e_total);

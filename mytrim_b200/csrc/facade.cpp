@@ -1372,6 +1372,7 @@ mtb_fission_pairs(uint32_t seed, uint64_t first_event, uint64_t n_events, const 
   MyTRIM_NS::MassInverter mass;
   MyTRIM_NS::EnergyInverter energy;
   double sum = 0.0;
+  uint64_t degenerate = 0;
   for (uint64_t ev = 0; ev < first_event + n_events; ++ev)
   {
     // same draw order as apps/mytrim_uo2.C:226-262: mass, energy, direction (rejection), origin
@@ -1408,11 +1409,25 @@ mtb_fission_pairs(uint32_t seed, uint64_t first_event, uint64_t n_events, const 
       o[k].Ef = 3.0;
       o[k].gen = 0;
       o[k].tag = -1;
+      if (o[k].Z < 1 || o[k].Z > 92)
+      {
+        // About one draw in 1e6 falls so far into the tail of the mass distribution that the 32-step bisection of
+        // Inverter::x ends at A = 235 * 2^-33 and the fragment gets Z = 0.  The reference then reads scoef[-1]
+        // (material.C:163-187): undefined behaviour.  Here the fragment keeps its place in the list (its index is its
+        // Philox stream) but carries no energy, so it stops where it starts; *n_degenerate counts them.
+        o[k].Z = o[k].Z < 1 ? 1 : 92;
+        o[k].m = std::max(o[k].m, 1.0);
+        o[k].E = 0.0;
+        ++degenerate;
+      }
       sum += o[k].E;
     }
   }
   if (e_total)
     *e_total = sum;
+  if (degenerate)
+    std::fprintf(stderr, "mtb_fission_pairs: %llu fragment(s) with Z outside 1..92 emitted without energy\n",
+                 (unsigned long long)degenerate);
   return MTB_OK;
 }
 

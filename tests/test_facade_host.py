@@ -109,3 +109,19 @@ def test_inverters_match_oracle(res):
 def test_ion_spawn_recoil_semantics(res):
     # gen+1, position and Ef inherited, tag reset, IonMDTag type propagates with md = 0, state MOVING
     assert res["ion"] == [4, 3.0, 7.0, -1, 0, 0]
+
+
+def test_fission_source_never_emits_an_unrepresentable_fragment():
+    """mtb_fission_pairs over 2e5 events of the tests/uo2 seed: event 156 507 draws a mass in the far tail, the
+    reference's bisection ends at A1 = 235 * 2^-33 and Z1 = round(92 A1 / 235) = 0, for which the reference reads
+    scoef[-1].  The fragment keeps its index (= its Philox stream) but carries no energy; every primary of the list is
+    one the engine accepts (a 1e8-primary run must not stop at such an event), and the sharded form of the source
+    (first_event > 0) yields the same fragments."""
+    from mytrim_b200 import capi, workloads
+    ions = capi.fission_pairs(workloads.UO2_SEED, 0, 200000, workloads.UO2_BOX)
+    assert ((ions["Z"] >= 1) & (ions["Z"] <= 92) & (ions["m"] > 0) & (ions["E"] >= 0) & np.isfinite(ions["E"])).all()
+    null = np.nonzero(ions["E"] == 0.0)[0]
+    assert list(null) == [2 * 156507]
+    assert ions["Z"][null[0]] == 1 and ions["Z"][null[0] + 1] == 92
+    shard = capi.fission_pairs(workloads.UO2_SEED, 156500, 16, workloads.UO2_BOX)
+    assert np.array_equal(shard, ions[2 * 156500:2 * 156516])
