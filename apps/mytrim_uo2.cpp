@@ -199,7 +199,7 @@ main(int argc, char * argv[])
         if (n && mtb_get_ion_log(dev.trim->engine(), log.data(), n, &n) != MTB_OK)
         {
           ok = false;
-          dev.error = mtb_last_error();
+          dev.error = std::string(mtb_last_error()) + " (fewer fission events per launch: MYTRIM_UO2_CHUNK=<events>)";
         }
         mtb_clear_lists(dev.trim->engine());
       }

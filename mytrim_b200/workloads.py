@@ -62,7 +62,7 @@ BENCH_WORKLOADS = {
                          desc="H->Fe 1 MeV, full cascades, TrimVacCount tallies (validation/h_on_fe at 1 MeV)"),
     "xe_on_uo2_10MeV": dict(primaries=1 << 13, tally=capi.TALLY_VAC_DEPTH,
                             desc="Xe->UO2 10 MeV, full cascades, TrimVacCount tallies (tests/json/xe_on_uo2.json)"),
-    "uo2_fission": dict(primaries=1 << 15, tally=capi.TALLY_IONLOG, ionlog_z=54,
+    "uo2_fission": dict(primaries=1 << 16, tally=capi.TALLY_IONLOG, ionlog_z=54,
                         desc="fission-fragment pairs in UO2 with Xe bubbles (tests/uo2), Xe ion log"),
 }
 
