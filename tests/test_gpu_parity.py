@@ -233,6 +233,57 @@ def test_follow_policies_and_vacancy_models():
         eng.close()
 
 
+@pytest.mark.parametrize("name,n,cfg", [
+    ("cu_on_cu_10keV", 1500, dict(tally_mask=capi.TALLY_VAC_DEPTH)),                                   # MONO
+    ("c_on_w_1MeV", 150, dict(tally_mask=capi.TALLY_VAC_ENERGY)),                                      # MONO-EVAC
+    ("xe_on_zro2_500keV", 40, dict(tally_mask=capi.TALLY_PHONON)),                                     # FAST-PHONON
+    ("cu_on_cu_10keV", 1500, dict(tally_mask=capi.TALLY_VAC_ENERGY | capi.TALLY_VAC_DEPTH | capi.TALLY_VACMAP,
+                                  vmap_z=(29, 8, -1))),                                                # LAYERS
+    ("cu_on_cu_10keV", 3000, dict(follow=capi.FOLLOW_NONE, vacancy_model=capi.VAC_NRT, tally_mask=capi.TALLY_RANGE)),
+    ("xe_on_zro2_500keV", 400, dict(follow=capi.FOLLOW_GEN_LT, follow_max_gen=2, vacancy_model=capi.VAC_KP)),
+])
+def test_tally_bins_against_fp32_host_replay(name, n, cfg):
+    """Every tally of the in-tree classes BIN BY BIN (not by sums) against the FP32 host replay of the device loop on the
+    same primaries and Philox streams: depth histograms of TrimVacCount, the 2-D histogram of TrimVacEnergyCount, the
+    TrimVacMap grid, TrimRange's list, TrimPhononOut's energy partition and the Kinchin-Pease counters of
+    TrimPrimaries/TrimRecoils.  The two sides differ by the rare threshold flips of the two FP32 arithmetics
+    (~1e-6 per collision step; a flip moves the events of one sub-cascade): the allowance is
+    8 + 2e-5 events per collision step — a few dozen events out of ~1e5, never a systematic shift of a bin."""
+    with capi.Engine(**cfg) as eng, util.HostSimEngine(**cfg) as hs:
+        for e in (eng, hs):
+            c = util.setup_engine(e, name)
+        ions = util.primaries_for(c, n)
+        eng.run(ions, seed=41)
+        hs.run(ions, seed=41)
+        cg, ch = eng.counters(), hs.counters()
+        steps = ch["steps"]
+        allow = 8 + 2e-5 * steps            # events that may move between bins / appear / vanish
+        for k in ("steps", "ions", "replacements", "recoils_queued", "vacancies_created"):
+            assert abs(cg[k] - ch[k]) <= allow * (40 if k == "steps" else 1), (k, cg[k], ch[k])
+        mask = cfg.get("tally_mask", 0)
+        if mask & capi.TALLY_VAC_DEPTH:
+            for hg, hh in zip(eng.vac_depth(), hs.vac_depth()):
+                m = max(len(hg), len(hh))
+                hg, hh = np.pad(hg, (0, m - len(hg))).astype(np.int64), np.pad(hh, (0, m - len(hh))).astype(np.int64)
+                assert hh.sum() > 0 and np.abs(hg - hh).sum() <= 2 * allow, (np.abs(hg - hh).sum(), hh.sum())
+        if mask & capi.TALLY_VAC_ENERGY:
+            eg, eh = eng.vac_energy(rows=32, bins=16384).astype(np.int64), hs.vac_energy(rows=32, bins=16384).astype(np.int64)
+            assert eh.sum() > 0 and np.abs(eg - eh).sum() <= 2 * allow, (np.abs(eg - eh).sum(), eh.sum())
+        if mask & capi.TALLY_VACMAP:
+            vg, vh = eng.vacmap().astype(np.int64), hs.vacmap().astype(np.int64)
+            assert vh.sum() > 0 and np.abs(vg - vh).sum() <= 2 * allow, (np.abs(vg - vh).sum(), vh.sum())
+        if mask & capi.TALLY_RANGE:
+            (xg, zg), (xh, zh) = eng.range_list(), hs.range_list()
+            assert abs(len(xg) - len(xh)) <= allow and len(xh) > 0
+            if len(xg) == len(xh):
+                assert np.abs(np.sort(xg) - np.sort(xh)).max() <= 1e-3 * np.abs(xh).max() or \
+                    (np.abs(np.sort(xg) - np.sort(xh)) > 1e-3 * np.abs(xh).max()).sum() <= allow
+        if mask & capi.TALLY_PHONON:
+            E0 = ions["E"].sum()
+            assert abs(cg["EelTotal"] + cg["EnucTotal"] - E0) < 1e-6 * E0
+            assert abs(cg["EnucTotal"] - ch["EnucTotal"]) <= 2e-5 * E0 and abs(cg["EelTotal"] - ch["EelTotal"]) <= 2e-5 * E0
+
+
 def test_ion_log_and_single_ion_events():
     cfg = dict(tally_mask=capi.TALLY_IONLOG, ionlog_z=8)
     eng, orc, c = _pair(cfg, "xe_on_zro2_500keV")
