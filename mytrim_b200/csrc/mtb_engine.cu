@@ -135,7 +135,7 @@ smem_layout(const LaunchParams & P)
   L.pool = o = align_up(o, 16);
   o += MTB_POOL_SLOTS * sizeof(PoolSlot);
   L.pool_ctl = o;
-  o += POOL_CTL_WORDS * sizeof(unsigned long long); // + the CTA-local primary counter and the exit flag
+  o += (POOL_CTL_COUNT + 1) * sizeof(unsigned long long); // + the CTA-local primary counter
   L.total = align_up(o, 16);
   return L;
 }
@@ -191,7 +191,7 @@ stage_block(const LaunchParams & P, unsigned char * smem)
   unsigned long long * pctl = reinterpret_cast<unsigned long long *>(smem + L.pool_ctl);
   if (threadIdx.x < MTB_POOL_SLOTS)
     pool[threadIdx.x].seq = threadIdx.x;
-  if (threadIdx.x < POOL_CTL_WORDS)
+  if (threadIdx.x <= POOL_CTL_COUNT)
     pctl[threadIdx.x] = threadIdx.x == POOL_WORKING ? (unsigned long long)blockDim.x : 0ull;
   __syncthreads();
   S.elements = el;
@@ -244,22 +244,8 @@ transport_kernel(const __grid_constant__ LaunchParams P)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   const BlockCtx S = stage_block(P, smem);
-  if (TR::kShare && P.gpool && threadIdx.x == 0)
-    atomicAdd(&P.gctl[POOL_WORKING], 1ull); // this CTA holds work until its lanes have all run dry (lane_loop)
   lane_loop<TR>(P, S, blockIdx.x * blockDim.x + threadIdx.x);
   flush_block(P, S);
-}
-
-// the device-wide work-sharing ring before a launch: empty.  Every CTA counts itself as working when it STARTS
-// (transport_kernel), not here: the idle CTAs then never wait for a CTA that has no SM yet — e.g. because a kernel of
-// another engine on the same GPU holds the slots — which would be a deadlock; they retire, and a late CTA works alone.
-__global__ void
-gpool_init_kernel(PoolSlot * gpool, unsigned long long * gctl)
-{
-  for (unsigned int i = threadIdx.x; i < MTB_GPOOL_SLOTS; i += blockDim.x)
-    gpool[i].seq = i;
-  if (threadIdx.x < POOL_CTL_COUNT)
-    gctl[threadIdx.x] = 0ull;
 }
 
 // rows of the registered primary species, by the functions the lanes use for private rows (mtb_transport.cuh)
@@ -383,8 +369,6 @@ struct mtb_handle
   bool share_enabled = true;
   uint64_t share_below = 4;  // work sharing for launches with fewer primaries per lane than this
   float share_min_E = 300.f; // eV, see suspend_ion(): measured optimum 200-500 eV (profiles/r02_variant_sweeps.md)
-  bool gshare_enabled = true;  // CTAs that run dry adopt work of other CTAs through a device-wide ring
-  float gshare_min_E = 2000.f; // eV, smallest energy of a pair one of which may be donated to another CTA
   bool deferred_pending = false;
   float extra_ms = 0.f;
   bool fast = false;
@@ -399,8 +383,6 @@ struct mtb_handle
   DevBuf<mtb_ion_log> d_ionlog;
   DevBuf<RangeEntry> d_range;
   DevBuf<StackEntry> d_stacks;
-  DevBuf<PoolSlot> d_gpool;            // device-wide work-sharing ring (share kernels)
-  DevBuf<unsigned long long> d_gctl;
   DevBuf<mtb_ion> d_primaries;
   DevBuf<mtb_event> d_events;
   DevBuf<uint32_t> d_event_counts;
@@ -640,24 +622,6 @@ launch_grid(const mtb_handle * h, Variant v, uint64_t n, bool * share)
 
 int drain(mtb_handle * h);
 
-// Device-wide ring of the work-sharing kernels: (re)initialised on the launch stream.
-int
-arm_global_pool(mtb_handle * h, LaunchParams & P, bool share)
-{
-  P.gpool = nullptr;
-  P.gctl = nullptr;
-  P.gshare_min_E = h->gshare_min_E;
-  if (!share || !h->gshare_enabled)
-    return MTB_OK;
-  MTB_CUDA(h->d_gpool.ensure(MTB_GPOOL_SLOTS));
-  MTB_CUDA(h->d_gctl.ensure(POOL_CTL_COUNT));
-  gpool_init_kernel<<<1, 256, 0, h->stream>>>(h->d_gpool.p, h->d_gctl.p);
-  MTB_CUDA(cudaGetLastError());
-  P.gpool = h->d_gpool.p;
-  P.gctl = h->d_gctl.p;
-  return MTB_OK;
-}
-
 int
 launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, const mtb_ion * beam, uint64_t seed,
                  uint64_t first_index, bool want_records)
@@ -712,8 +676,6 @@ launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, cons
   }
   MTB_CUDA(cudaMemsetAsync(&P.u64[CNT_NEXT_PRIMARY], 0, sizeof(unsigned long long), h->stream));
   MTB_CUDA(cudaMemsetAsync(&P.u64[CNT_DEFERRED], 0, sizeof(unsigned long long), h->stream));
-  if (int rc = arm_global_pool(h, P, share))
-    return rc;
   MTB_CUDA(cudaEventRecord(h->ev0, h->stream));
   launch_kernel(h, P, blocks, v, share);
   MTB_CUDA(cudaGetLastError());
@@ -747,8 +709,6 @@ run_deferred(mtb_handle * h)
   MTB_CUDA(h->d_custom_rows.ensure((size_t)blocks * kBlock * (size_t)(2 + P.n_materials + P.n_tclass)));
   P.custom_rows = h->d_custom_rows.p;
   MTB_CUDA(cudaMemsetAsync(&P.u64[CNT_NEXT_PRIMARY], 0, sizeof(unsigned long long), h->stream));
-  if (int rc = arm_global_pool(h, P, share))
-    return rc;
   cudaEvent_t e0, e1;
   MTB_CUDA(cudaEventCreate(&e0));
   MTB_CUDA(cudaEventCreate(&e1));
@@ -877,10 +837,6 @@ mtb_create(const mtb_config * cfg, mtb_handle ** out)
     h->share_enabled = env[0] == '0';
   if (const char * env = std::getenv("MYTRIM_B200_SHARE_MIN_E")) // tuning knob: eV
     h->share_min_E = (float)std::atof(env);
-  if (const char * env = std::getenv("MYTRIM_B200_NO_GLOBAL_SHARE")) // tuning knob: work sharing inside a CTA only
-    h->gshare_enabled = env[0] == '0';
-  if (const char * env = std::getenv("MYTRIM_B200_GSHARE_MIN_E")) // tuning knob: eV
-    h->gshare_min_E = (float)std::atof(env);
   if (const char * env = std::getenv("MYTRIM_B200_SHARE_BELOW")) // tuning knob: primaries per lane
     h->share_below = std::strtoull(env, nullptr, 10);
   h->sm_count = prop.multiProcessorCount;

@@ -875,44 +875,34 @@ vload(const unsigned long long * p)
   return *reinterpret_cast<const volatile unsigned long long *>(p);
 }
 
-// sequence numbers of the ring slots carry the hand-over of the payload: acquire / release at CTA scope (the rings in
-// shared memory) or GPU scope (the device-wide ring)
-template <bool GLOBAL>
+// sequence numbers of the ring slots carry the hand-over of the payload: acquire / release at CTA scope
 MTB_D unsigned long long
 load_acquire(const unsigned long long * p)
 {
   unsigned long long v;
-  if (GLOBAL)
-    asm volatile("ld.acquire.gpu.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  else
-    asm volatile("ld.acquire.cta.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.acquire.cta.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 
-template <bool GLOBAL>
 MTB_D void
 store_release(unsigned long long * p, unsigned long long v)
 {
-  if (GLOBAL)
-    asm volatile("st.release.gpu.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-  else
-    asm volatile("st.release.cta.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  asm volatile("st.release.cta.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // Claim a ring slot for writing (which = POOL_ENQ) or reading (which = POOL_DEQ): the ticket dance of the
 // bounded MPMC queue.  Inlined: as a real call (-DMTB_POOL_NOINLINE) the tests/uo2 workload was measured 9 % slower
 // in round 2 (profiles/r02_variant_sweeps.md), although the inlined form costs the sharing kernels registers.
-template <bool GLOBAL>
 MTB_POOL_FN PoolSlot *
 pool_claim(PoolSlot * pool, unsigned long long * ctl, int which, unsigned long long * ticket)
 {
-  const unsigned long long mask = (GLOBAL ? MTB_GPOOL_SLOTS : MTB_POOL_SLOTS) - 1;
+  const unsigned long long mask = MTB_POOL_SLOTS - 1;
   const unsigned long long want = which == POOL_ENQ ? 0ull : 1ull; // slot sequence relative to the ticket
   unsigned long long pos = vload(&ctl[which]);
   for (int tries = 0; tries < 4; ++tries)
   {
     PoolSlot * slot = pool + (pos & mask);
-    const long long dif = (long long)(load_acquire<GLOBAL>(&slot->seq) - (pos + want));
+    const long long dif = (long long)(load_acquire(&slot->seq) - (pos + want));
     if (dif == 0)
     {
       const unsigned long long seen = atomicCAS(&ctl[which], pos, pos + 1);
@@ -937,12 +927,12 @@ MTB_D bool
 pool_try_push(const BlockCtx & S, const Lane & ion, uint64_t prim, uint32_t safe_bits)
 {
   unsigned long long pos;
-  PoolSlot * slot = pool_claim<false>(S.pool, S.pool_ctl, POOL_ENQ, &pos);
+  PoolSlot * slot = pool_claim(S.pool, S.pool_ctl, POOL_ENQ, &pos);
   if (!slot)
     return false;
   slot->prim = prim;
   stack_store(&slot->e, ion, safe_bits);
-  store_release<false>(&slot->seq, pos + 1); // publishes the payload
+  store_release(&slot->seq, pos + 1); // publishes the payload
   return true;
 }
 
@@ -950,44 +940,12 @@ MTB_D bool
 pool_try_pop(const BlockCtx & S, Lane & ion, uint64_t * prim)
 {
   unsigned long long pos;
-  PoolSlot * slot = pool_claim<false>(S.pool, S.pool_ctl, POOL_DEQ, &pos);
+  PoolSlot * slot = pool_claim(S.pool, S.pool_ctl, POOL_DEQ, &pos);
   if (!slot)
     return false;
   *prim = slot->prim;
   stack_load(&slot->e, ion);
-  store_release<false>(&slot->seq, pos + MTB_POOL_SLOTS); // hands the slot back to the producers
-  return true;
-}
-
-// The device-wide ring behind the CTA rings: a CTA whose lanes have all run dry does not retire, it registers as idle
-// (gctl[POOL_IDLE]) and its thread 0 polls this ring; busy lanes of other CTAs donate into it when they see an idle CTA
-// and no idle lane in their own.  The adopted sub-cascade then fans out over the adopting CTA through its own ring.
-// gctl[POOL_WORKING] = CTAs that hold work + entries of this ring (an entry is counted before it is published), so
-// "0" means nothing is left anywhere and the idle CTAs may retire.  Without it a launch with few primaries per lane
-// ends in a tail in which a few CTAs finish the last heavy cascades while most SMs idle.
-MTB_D bool
-gpool_try_push(const LaunchParams & P, const Lane & ion, uint64_t prim, uint32_t safe_bits)
-{
-  unsigned long long pos;
-  PoolSlot * slot = pool_claim<true>(P.gpool, P.gctl, POOL_ENQ, &pos);
-  if (!slot)
-    return false;
-  slot->prim = prim;
-  stack_store(&slot->e, ion, safe_bits);
-  store_release<true>(&slot->seq, pos + 1);
-  return true;
-}
-
-MTB_D bool
-gpool_try_pop(const LaunchParams & P, Lane & ion, uint64_t * prim)
-{
-  unsigned long long pos;
-  PoolSlot * slot = pool_claim<true>(P.gpool, P.gctl, POOL_DEQ, &pos);
-  if (!slot)
-    return false;
-  *prim = slot->prim;
-  stack_load(&slot->e, ion);
-  store_release<true>(&slot->seq, pos + MTB_GPOOL_SLOTS);
+  store_release(&slot->seq, pos + MTB_POOL_SLOTS); // hands the slot back to the producers
   return true;
 }
 #endif
@@ -1036,16 +994,8 @@ suspend_ion(const LaunchParams & P, const BlockCtx & S, uint32_t & sp, const Lan
   // the two energies): a lane that gives its big ion away and keeps a 30 eV recoil is idle itself
   // three steps later, and every adoption costs a few hundred instructions at one active lane.
   const uint32_t safe_bits = TR::has(F_CLUSTERS) ? safe_bits_of(P, ion.dsafe) : 0u;
-  if (TR::kShare && e_small >= P.share_min_E)
-  {
-    if (vload(&S.pool_ctl[POOL_IDLE]) > 0)
-    {
-      if (pool_try_push(S, ion, prim, safe_bits))
-        return;
-    }
-    else if (P.gpool && e_small >= P.gshare_min_E && vload(&P.gctl[POOL_IDLE]) > 0 && gpool_try_push(P, ion, prim, safe_bits))
-      return;
-  }
+  if (TR::kShare && e_small >= P.share_min_E && vload(&S.pool_ctl[POOL_IDLE]) > 0 && pool_try_push(S, ion, prim, safe_bits))
+    return;
 #else
   const uint32_t safe_bits = TR::has(F_CLUSTERS) ? safe_bits_of(P, ion.dsafe) : 0u;
 #endif
@@ -1315,31 +1265,10 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
               atomicAdd(&S.pool_ctl[POOL_WORKING], (unsigned long long)-1ll);
             }
             uint64_t aprim;
-            bool adopted = false;
-            const unsigned long long cta_working = vload(&S.pool_ctl[POOL_WORKING]);
             // (Polling only in every 4th / 16th trip of the warp, -DMTB_POLL_EVERY, to spare the working warp mates
             // the ~40 instructions of the attempt, was measured 5-14 % SLOWER on the tests/uo2 workload and 5-8 % on
             // C->W / Xe->ZrO2: how soon an idle lane picks work up matters more.  profiles/r02_variant_sweeps.md)
-            if (cta_working != MTB_POOL_CTA_IDLE)
-              adopted = (MTB_POLL_EVERY == 1 || (trip & (MTB_POLL_EVERY - 1)) == 0) && pool_try_pop(S, L, &aprim);
-            else if (threadIdx.x == 0)
-            {
-              // this CTA has run dry: its thread 0 polls the device-wide ring (one poller per CTA, with a back-off: a
-              // hundred thousand lanes polling one L2 line made a device-wide ring 50x slower in round 1)
-              if (gpool_try_pop(P, L, &aprim))
-              {
-                // the entry's count in gctl[POOL_WORKING] becomes this CTA's; nobody else touches the CTA's own
-                // counter while it reads MTB_POOL_CTA_IDLE
-                atomicExch(&S.pool_ctl[POOL_WORKING], 1ull);
-                atomicAdd(&P.gctl[POOL_IDLE], (unsigned long long)-1ll);
-                adopted = true;
-              }
-              else if (vload(&P.gctl[POOL_WORKING]) == 0)
-                atomicExch(&S.pool_ctl[POOL_EXIT], 1ull); // nothing left anywhere: the CTA retires
-              else
-                __nanosleep(2000);
-            }
-            if (adopted)
+            if ((MTB_POLL_EVERY == 1 || (trip & (MTB_POLL_EVERY - 1)) == 0) && pool_try_pop(S, L, &aprim))
             {
               // the entry carried its own count in POOL_WORKING; it now belongs to this lane
               idle = false;
@@ -1366,19 +1295,7 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
               open = true;
               active = true;
             }
-            else if (cta_working == 0)
-            {
-              // no lane of this CTA holds work and its ring is empty
-              if (!P.gpool)
-                done = true;
-              else if (atomicCAS(&S.pool_ctl[POOL_WORKING], 0ull, MTB_POOL_CTA_IDLE) == 0ull)
-              {
-                // this lane turns the CTA idle (only the first one gets here: the others find the mark)
-                atomicAdd(&P.gctl[POOL_IDLE], 1ull);
-                atomicAdd(&P.gctl[POOL_WORKING], (unsigned long long)-1ll);
-              }
-            }
-            else if (cta_working == MTB_POOL_CTA_IDLE && vload(&S.pool_ctl[POOL_EXIT]) != 0)
+            else if (vload(&S.pool_ctl[POOL_WORKING]) == 0)
               done = true;
             else if (++idle_polls > (1ull << 26))
             {

@@ -178,17 +178,9 @@ enum
   POOL_DEQ = 1,     // dequeue ticket
   POOL_WORKING = 2, // lanes that hold work + entries in the pool; 0 <=> nothing left anywhere
   POOL_IDLE = 3,    // lanes polling the pool
-  POOL_CTL_COUNT = 4,
-  // (index POOL_CTL_COUNT of a CTA's control block is its local primary counter)
-  POOL_EXIT = 5,    // CTA block only: set by thread 0 of an idle CTA when nothing is left on the whole device
-  POOL_CTL_WORDS = 6
+  POOL_CTL_COUNT = 4
 };
 #define MTB_POOL_SLOTS 32 // per CTA, power of two
-// Device-wide ring behind the per-CTA rings (LaunchParams::gpool / gctl, same slot and control layout; in gctl
-// POOL_WORKING counts the CTAs that still hold work plus the entries of the device ring, POOL_IDLE the CTAs that have
-// run dry and poll it).  POOL_WORKING of a CTA's own block holds MTB_POOL_CTA_IDLE while the CTA is in that state.
-#define MTB_GPOOL_SLOTS 2048
-#define MTB_POOL_CTA_IDLE (1ull << 62)
 
 struct RangeEntry
 {
@@ -248,9 +240,6 @@ struct LaunchParams
   uint32_t * deferred;          // fast kernel: indices of primaries without a projectile class
   uint32_t key0, key1;
   float share_min_E; // work sharing: smallest energy [eV] of a pair of ions one of which may be donated
-  float gshare_min_E;           // the same for a donation into the device-wide ring
-  PoolSlot * gpool;             // [MTB_GPOOL_SLOTS] device-wide ring (nullptr: CTAs share among their own lanes only)
-  unsigned long long * gctl;    // [POOL_CTL_COUNT]
   uint32_t rk[20]; // Philox round keys (philox_round_keys): the key schedule is a launch constant
   // outputs
   unsigned long long * u64;     // counter + histogram block
