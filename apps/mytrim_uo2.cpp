@@ -153,6 +153,7 @@ main(int argc, char * argv[])
     std::unique_ptr<TrimXeLog> trim;
     std::deque<int> todo;
     double kernel_ms = 0.0;
+    double t_batch = 0.0, t_log = 0.0, t_format = 0.0, t_wait = 0.0; // host seconds per phase (MYTRIM_TIMING)
     std::string error;
   };
   std::vector<Chunk> chunks(n_chunks);
@@ -162,7 +163,9 @@ main(int argc, char * argv[])
     devices[d].simconf.reset(new SimconfType);
     devices[d].simconf->seed(seed < 0 ? -seed : seed); // same Philox key on every device
     devices[d].simconf->device = d % ngpu;
-    devices[d].trim.reset(new TrimXeLog(devices[d].simconf.get(), sample, 1ull << 22));
+    // ion log: a birth and a death entry per Xe ion, ~16 entries per fragment in the gold geometry; 64 per fragment reserved
+    devices[d].trim.reset(new TrimXeLog(devices[d].simconf.get(), sample,
+                                        std::max<unsigned long long>(1ull << 22, 128ull * (unsigned long long)chunk_events)));
   }
   std::mutex mtx;
   std::condition_variable cv;
@@ -175,6 +178,11 @@ main(int argc, char * argv[])
     for (;;)
     {
       int c;
+      auto now = [] { return std::chrono::steady_clock::now(); };
+      auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double>(b - a).count();
+      };
+      const auto t0 = now();
       {
         std::unique_lock<std::mutex> lk(mtx);
         cv.wait(lk, [&] { return !dev.todo.empty() || no_more || failed; });
@@ -184,8 +192,12 @@ main(int argc, char * argv[])
         dev.todo.pop_front();
       }
       Chunk & ch = chunks[c];
+      const auto t1 = now();
+      dev.t_wait += secs(t0, t1);
       dev.simconf->setStreamId(ch.first_stream);
       bool ok = dev.trim->trimBatch(ch.primaries);
+      const auto t2 = now();
+      dev.t_batch += secs(t1, t2);
       if (!ok)
         dev.error = dev.trim->lastError();
       size_t n = 0;
@@ -206,6 +218,8 @@ main(int argc, char * argv[])
       for (auto * p : ch.primaries)
         delete p;
       ch.primaries.clear();
+      const auto t3 = now();
+      dev.t_log += secs(t2, t3);
       if (ok)
       {
         // the device appends log entries in scheduling order: sort by fragment, then ion id
@@ -238,6 +252,7 @@ main(int argc, char * argv[])
           }
         }
       }
+      dev.t_format += secs(t3, now());
       {
         std::lock_guard<std::mutex> lk(mtx);
         ch.done = true;
@@ -370,6 +385,10 @@ main(int argc, char * argv[])
       ions += cnt.ions;
     }
   }
+  if (std::getenv("MYTRIM_TIMING"))
+    for (size_t d = 0; d < devices.size(); ++d)
+      std::fprintf(stderr, "engine %zu: waiting for chunks %.2f s, trimBatch %.2f s (kernels %.2f s), ion log %.2f s, sort + format %.2f s\n", d,
+                   devices[d].t_wait, devices[d].t_batch, devices[d].kernel_ms * 1e-3, devices[d].t_log, devices[d].t_format);
   if (std::getenv("MYTRIM_TIMING") && kernel_ms > 0.0)
     std::fprintf(stderr,
                  "{\"workload\": \"uo2_fission\", \"gpus\": %d, \"primaries\": %llu, \"collision_steps\": %llu, "

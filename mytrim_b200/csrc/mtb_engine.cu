@@ -383,6 +383,7 @@ struct mtb_handle
   DevBuf<mtb_ion_log> d_ionlog;
   DevBuf<RangeEntry> d_range;
   DevBuf<StackEntry> d_stacks;
+  void * zero_pinned = nullptr; // page-locked block of zeros (see launch_transport)
   DevBuf<mtb_ion> d_primaries;
   DevBuf<mtb_event> d_events;
   DevBuf<uint32_t> d_event_counts;
@@ -621,6 +622,7 @@ launch_grid(const mtb_handle * h, Variant v, uint64_t n, bool * share)
 }
 
 int drain(mtb_handle * h);
+constexpr size_t kZeroBlock = 4u << 20;
 
 int
 launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, const mtb_ion * beam, uint64_t seed,
@@ -645,7 +647,6 @@ launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, cons
   {
     MTB_CUDA(h->d_records.ensure(n));
     P.records = h->d_records.p;
-    MTB_CUDA(cudaMemsetAsync(h->d_records.p, 0, n * sizeof(mtb_record), h->stream)); // lanes accumulate into them
   }
   h->records_valid = want_records;
   h->last_n = n;
@@ -659,6 +660,28 @@ launch_transport(mtb_handle * h, uint64_t n, const mtb_ion * primaries_dev, cons
   const unsigned blocks = launch_grid(h, v, n, &share);
   if ((uint64_t)blocks * kBlock * MTB_STACK_DEPTH * sizeof(StackEntry) > 0xFFFFFFFFull)
     return fail(MTB_EINVAL, "grid too large for 32-bit stack cursors");
+  if (want_records)
+  {
+    // lanes accumulate into the records: they start from zero.  A launch of a work-sharing kernel zeroes them with the
+    // copy engine (from a page-locked block of zeros) instead of a memset KERNEL: when a second engine of the same GPU
+    // still runs its persistent kernel, a memset kernel finds no free registers on any SM and this stream — and the host
+    // thread behind it — would wait for that kernel's last CTA (measured in apps/mytrim_uo2: launches of two engines
+    // never overlapped).  Large launches keep the memset kernel (3 TB/s instead of PCIe).
+    const size_t bytes = n * sizeof(mtb_record);
+    if (share && bytes <= (256u << 20))
+    {
+      if (!h->zero_pinned)
+      {
+        MTB_CUDA(cudaHostAlloc(&h->zero_pinned, kZeroBlock, cudaHostAllocDefault));
+        std::memset(h->zero_pinned, 0, kZeroBlock);
+      }
+      for (size_t off = 0; off < bytes; off += kZeroBlock)
+        MTB_CUDA(cudaMemcpyAsync(reinterpret_cast<char *>(h->d_records.p) + off, h->zero_pinned, std::min(kZeroBlock, bytes - off),
+                                 cudaMemcpyHostToDevice, h->stream));
+    }
+    else
+      MTB_CUDA(cudaMemsetAsync(h->d_records.p, 0, bytes, h->stream));
+  }
   MTB_CUDA(h->d_stacks.ensure((size_t)blocks * kBlock * MTB_STACK_DEPTH));
   P.stacks = h->d_stacks.p;
   MTB_CUDA(h->d_custom_rows.ensure((size_t)blocks * kBlock * (size_t)(2 + P.n_materials + P.n_tclass)));
@@ -865,6 +888,8 @@ mtb_destroy(mtb_handle * h)
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
   cudaStreamDestroy(h->stream);
+  if (h->zero_pinned)
+    cudaFreeHost(h->zero_pinned);
   delete h;
   return MTB_OK;
 }
