@@ -514,7 +514,11 @@ as_row(const PairE & v)
 
 // A primary whose (Z, m) has no class (e.g. a fission fragment with its own mass) gets private rows
 // [ProjClass | PairM per material | PairE per target class] in the lane's scratch area.
+#if defined(MTB_ROWS_NOINLINE) && MTB_DEVICE_CODE
+__device__ __noinline__ void
+#else
 MTB_HD_COLD void
+#endif
 build_custom_rows(const LaunchParams & P, const BlockCtx & S, float4_t * rows, int Z, float m)
 {
   const ProjClass c = make_proj_class(S.ionz[Z], Z, m);
@@ -832,7 +836,11 @@ vacancy_creation(const LaunchParams & P, const BlockCtx & S, Lane & L, const Dev
 // block totals.  Record counters are accumulated atomically because several lanes may have worked
 // on the same primary; records are zeroed before the launch.
 template <class TR>
+#if defined(MTB_CLOSE_NOINLINE) && MTB_DEVICE_CODE
+__device__ __noinline__ void
+#else
 MTB_HD void
+#endif
 close_subtree(const LaunchParams & P, const BlockCtx & S, Lane & L, uint32_t n_prim)
 {
   if (!TR::has(F_NOREC) && P.records)
@@ -1155,6 +1163,9 @@ lane_loop(const LaunchParams & P, const BlockCtx & S, uint32_t lane_global)
           close_subtree<TR>(P, S, L, TR::kShare ? cas_prim : 1u);
           open = false;
         }
+#ifdef MTB_REFILL_UNROLL1
+#pragma unroll 1
+#endif
         while (!no_more)
         {
           unsigned long long idx;
