@@ -218,8 +218,8 @@ def _run_uo2(apps, base, nev, env_extra, cbf="1.0"):
 
 
 def test_mytrim_uo2_outputs_do_not_depend_on_chunks_or_gpus(tmp_path):
-    """apps/mytrim_uo2.cpp deals chunks of fission events over MYTRIM_GPUS devices and writes the output lines in event
-    order: .Erec / .dist / .clcoor are byte-identical for any chunk size and any number of GPUs (Philox stream id of a
+    """apps/mytrim_uo2.cpp deals chunks of fission events over MYTRIM_GPUS devices x MYTRIM_ENGINES_PER_GPU engines and writes
+    the output lines in event order: .Erec / .dist / .clcoor are byte-identical for any chunk size, number of GPUs and engines (Philox stream id of a
     fragment = its global index; reference loop apps/mytrim_uo2.C:226-342)."""
     apps = _apps()
     nev = 24
@@ -230,6 +230,12 @@ def test_mytrim_uo2_outputs_do_not_depend_on_chunks_or_gpus(tmp_path):
     assert t_one["collision_steps"] == t_chk["collision_steps"] and t_one["primaries"] == 2 * nev
     assert abs(e_one[0] - e_chk[0]) <= 1e-9 * e_one[0]
     assert len(open(tmp_path / "one.Erec").read().strip().split("\n")) > 100
+    # engines per GPU (two by default: the launches of consecutive chunks overlap on one device)
+    for epg in ("1", "3"):
+        e_e, t_e = _run_uo2(apps, tmp_path / ("e" + epg), nev, {"MYTRIM_UO2_CHUNK": "5", "MYTRIM_ENGINES_PER_GPU": epg})
+        assert t_e["engines_per_gpu"] == int(epg) and t_e["collision_steps"] == t_one["collision_steps"]
+        for ext in ("Erec", "dist"):
+            assert open(str(tmp_path / "one") + "." + ext).read() == open(str(tmp_path / ("e" + epg)) + "." + ext).read(), (epg, ext)
     if capi.load_library().mtb_device_count() >= 2:
         e_two, t_two = _run_uo2(apps, tmp_path / "two", nev, {"MYTRIM_UO2_CHUNK": "5", "MYTRIM_GPUS": "2"})
         assert t_two["gpus"] == 2

@@ -40,6 +40,7 @@ ions["pos"] = rng.uniform(0, 400, (24, 3))
 ions["pos"][:6] = cl[np.arange(6) % len(cl), :3] + 1.0
 d = rng.normal(size=(24, 3))
 ions["dir"] = d / np.linalg.norm(d, axis=1)[:, None]
+ions_cl = ions.copy()
 for bc in ((capi.BC_PBC,) * 3, (capi.BC_CUT, capi.BC_PBC, capi.BC_INF)):
     with capi.Engine(tally_mask=capi.TALLY_PHONON | capi.TALLY_RECORDS | capi.TALLY_IONLOG, ionlog_z=54) as eng:
         eng.set_materials([util.UO2, util.XE_GAS])
@@ -66,6 +67,24 @@ with capi.Engine(tally_mask=capi.TALLY_VAC_DEPTH) as eng:
     c = util.setup_engine(eng, "cu_on_cu_10keV")
     eng.run(util.primaries_for(c, 512), seed=1)                       # MONO + share
     print("MONO + share", eng.counters()["steps"])
+# compile-time tally variants: MONO-EVAC (+share), FAST-PHONON (+share), CLUSTERS-LOG (+share)
+with capi.Engine(tally_mask=capi.TALLY_VAC_ENERGY) as eng:
+    c = util.setup_engine(eng, "c_on_w_1MeV")
+    ions = util.primaries_for(c, 64)
+    ions["E"] = 5.0e4
+    eng.run(ions, seed=3)
+    print("MONO-EVAC + share", eng.counters()["steps"], int(eng.vac_energy().sum()))
+with capi.Engine(tally_mask=capi.TALLY_PHONON) as eng:
+    c = util.setup_engine(eng, "xe_on_zro2_500keV")
+    ions = util.primaries_for(c, 16)
+    ions["E"] = 2.0e4
+    eng.run(ions, seed=3)
+    print("FAST-PHONON + share", eng.counters()["steps"], eng.counters()["EnucTotal"])
+with capi.Engine(tally_mask=capi.TALLY_IONLOG, ionlog_z=54) as eng:
+    eng.set_materials([util.UO2, util.XE_GAS])
+    eng.set_geometry(capi.GEOM_CLUSTERS, (400.0, 400.0, 400.0), kn=(39, 39, 39), clusters=cl)
+    eng.run(ions_cl, seed=3)
+    print("CLUSTERS-LOG + share", eng.counters()["steps"], len(eng.ion_log()))
 with capi.Engine(tally_mask=0) as eng:
     c = util.setup_engine(eng, "cu_on_cu_10keV")
     fin, st, cnt, ev = eng.trim_many(util.primaries_for(c, 100), 5, 0, 64)   # event mode, one lane per ion
