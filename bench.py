@@ -290,6 +290,7 @@ def main():
         return e, host
 
     eng, pinned = make_engine(name, B)
+    variants = {name: eng.kernel_variant()}
 
     def barrier():
         if world > 1:
@@ -435,6 +436,7 @@ def main():
                 n = B
             else:
                 e2, host2 = make_engine(cname, n)
+                variants[cname] = e2.kernel_variant()
                 e2.upload_primaries_ptr(n, host2.data_ptr())
                 e2.launch_resident(MASTER_SEED, rank * n)          # warm-up
                 e2.synchronize()
@@ -485,7 +487,9 @@ def main():
             t = float(vmax[0]) * 1e-3
             configs[cname] = {"cascades_per_s": n * world / t, "collision_steps_per_s": float(vsum[1]) / t,
                               "steps_per_cascade": float(vsum[1]) / (n * world), "primaries_per_gpu": n,
-                              "kernel_ms": float(vmax[0]), "what": cw["desc"]}
+                              "kernel_ms": float(vmax[0]), "what": cw["desc"],
+                              "kernel_variant": variants.get(cname, "") + (" (launches without records: MONO-NOREC)"
+                                                                           if variants.get(cname) == "MONO" else "")}
             if pipelined:
                 tp2 = float(vmax[2]) * 1e-3
                 configs[cname]["two_engines_per_gpu"] = {

@@ -261,6 +261,10 @@ int mtb_launch_resident(mtb_handle * h, uint64_t seed, uint64_t first_index); /*
 int mtb_synchronize(mtb_handle * h);
 /* Device time of the most recent transport kernel launch(es) of mtb_run/mtb_launch_resident, in ms. */
 int mtb_last_kernel_ms(mtb_handle * h, float * ms);
+/* Name of the compile-time kernel variant the handle's configuration selects: "MONO" (a launch
+ * without per-primary records runs its "MONO-NOREC" twin), "FAST", "MONO-EVAC", "FAST-PHONON", "CLUSTERS-LOG",
+ * "CLUSTERS", "LAYERS" or "GENERIC"; "" on error.  Diagnostic: the reference has no counterpart. */
+const char * mtb_kernel_variant(mtb_handle * h);
 int mtb_fetch_records(mtb_handle * h, uint64_t n, mtb_record * records);
 
 /* Tally read-back (replaces threadJoin + the accessors writeOutput uses). */

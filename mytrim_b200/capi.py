@@ -408,6 +408,13 @@ class Engine(EngineBase):
     def synchronize(self):
         self._check(self._lib.mtb_synchronize(self._h))
 
+    def kernel_variant(self):
+        """Name of the compile-time kernel variant this configuration selects (mtb_kernel_variant)."""
+        fn = self._lib.mtb_kernel_variant
+        fn.argtypes = [C.c_void_p]
+        fn.restype = C.c_char_p
+        return fn(self._h).decode()
+
     def last_kernel_ms(self):
         ms = C.c_float()
         self._check(self._lib.mtb_last_kernel_ms(self._h, C.byref(ms)))

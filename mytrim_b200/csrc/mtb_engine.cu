@@ -1015,6 +1015,14 @@ mtb_last_kernel_ms(mtb_handle * h, float * ms)
   return MTB_OK;
 }
 
+const char *
+mtb_kernel_variant(mtb_handle * h)
+{
+  if (ensure_ready(h))
+    return "";
+  return variant_name(h->variant);
+}
+
 int
 mtb_fetch_records(mtb_handle * h, uint64_t n, mtb_record * records)
 {

@@ -166,6 +166,24 @@ enum Variant
   VARIANT_COUNT
 };
 
+inline const char *
+variant_name(Variant v)
+{
+  switch (v)
+  {
+    case VARIANT_FAST: return "FAST";
+    case VARIANT_CLUSTERS: return "CLUSTERS";
+    case VARIANT_LAYERS: return "LAYERS";
+    case VARIANT_GENERIC: return "GENERIC";
+    case VARIANT_MONO: return "MONO";
+    case VARIANT_MONO_NOREC: return "MONO-NOREC";
+    case VARIANT_CLUSTERS_LOG: return "CLUSTERS-LOG";
+    case VARIANT_MONO_EVAC: return "MONO-EVAC";
+    case VARIANT_FAST_PHONON: return "FAST-PHONON";
+    default: return "?";
+  }
+}
+
 inline uint32_t
 variant_features(Variant v)
 {

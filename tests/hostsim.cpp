@@ -256,6 +256,15 @@ hs_sample_info(hs_engine * e, int32_t * out4)
   return MTB_OK;
 }
 
+// the variant pick_variant() selects for the configuration (same function as mtb_engine.cu: mtb_kernel_variant)
+const char *
+hs_variant(hs_engine * e)
+{
+  if (hs_prepare(e))
+    return "";
+  return variant_name(e->force_generic ? VARIANT_GENERIC : pick_variant(e->P, false));
+}
+
 void
 hs_force_generic(hs_engine * e, int on)
 {

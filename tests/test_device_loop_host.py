@@ -2,6 +2,7 @@
 (tests/hostsim.cpp) against the double-precision oracle with the same Philox streams.  This checks
 the FP32 reformulations, the depth-first stack traversal and the tallies without a GPU; the GPU
 tests repeat it through the real kernels."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -603,3 +604,40 @@ def test_results_do_not_depend_on_what_the_engine_ran_before():
         rb = fresh.run(second, seed=5, first_index=1000, records=True)   # registers the species of `second`
     for f in ra.dtype.names:
         assert np.array_equal(ra[f], rb[f]), f
+
+
+VARIANT_CASES = [
+    # (sample / workload, engine configuration, variant pick_variant() must select)
+    ("cu_on_cu_10keV", dict(tally_mask=capi.TALLY_VAC_DEPTH), "MONO"),
+    ("h_on_fe_100keV", dict(tally_mask=capi.TALLY_VAC_DEPTH | capi.TALLY_RECORDS), "MONO"),
+    ("c_on_w_1MeV", dict(tally_mask=capi.TALLY_VAC_ENERGY), "MONO-EVAC"),                      # validation/c_on_w/input.json
+    ("xe_on_zro2_500keV", dict(tally_mask=capi.TALLY_VAC_DEPTH), "FAST"),                       # compound stack, folded
+    ("xe_on_zro2_500keV", dict(tally_mask=capi.TALLY_PHONON | capi.TALLY_RECORDS), "FAST-PHONON"),
+    ("xe_on_zro2_500keV", dict(follow=capi.FOLLOW_GEN_LT, follow_max_gen=2, vacancy_model=capi.VAC_KP), "LAYERS"),   # mytrim_layers
+    ("cu_on_cu_10keV", dict(follow=capi.FOLLOW_NONE, vacancy_model=capi.VAC_NRT, tally_mask=capi.TALLY_RANGE), "LAYERS"),
+    ("cu_on_cu_10keV", dict(tally_mask=capi.TALLY_VAC_ENERGY | capi.TALLY_VAC_DEPTH), "LAYERS"),
+    ("cu_on_cu_10keV", dict(tally_mask=capi.TALLY_VAC_DEPTH, potential=capi.POT_MOLIERE), "GENERIC"),
+    ("uo2", dict(tally_mask=capi.TALLY_IONLOG, ionlog_z=54), "CLUSTERS-LOG"),                     # apps/mytrim_uo2
+    ("uo2", dict(tally_mask=capi.TALLY_IONLOG | capi.TALLY_PHONON | capi.TALLY_RECORDS, ionlog_z=54), "CLUSTERS"),
+    ("uo2", dict(tally_mask=capi.TALLY_VAC_DEPTH), "GENERIC"),
+]
+
+
+def setup_variant_case(e, sample):
+    if sample == "uo2":
+        cl = np.loadtxt(os.path.join(util.GOLDEN, "uo2_out.clcoor"))[:, :4]
+        e.set_materials([util.UO2, util.XE_GAS])
+        e.set_geometry(capi.GEOM_CLUSTERS, (400.0, 400.0, 400.0), kn=(39, 39, 39), clusters=cl)
+    else:
+        util.setup_engine(e, sample)
+
+
+@pytest.mark.parametrize("sample,cfg,want", VARIANT_CASES)
+def test_configurations_select_their_kernel_variant(sample, cfg, want):
+    """pick_variant() (mtb_transport.cuh; the same function the CUDA engine calls) on the BASELINE.json configurations and
+    on the shapes of the in-tree drivers: each selects the leanest compile-time variant that covers it."""
+    with util.HostSimEngine(**cfg) as hs:
+        setup_variant_case(hs, sample)
+        hs._lib.hs_variant.argtypes = [C.c_void_p]
+        hs._lib.hs_variant.restype = C.c_char_p
+        assert hs._lib.hs_variant(hs._h).decode() == want

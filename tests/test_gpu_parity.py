@@ -841,3 +841,13 @@ def test_results_do_not_depend_on_what_the_engine_ran_before():
             assert np.allclose(ra[f], rb[f], rtol=1e-12, atol=0), f
         else:
             assert np.array_equal(ra[f], rb[f]), f
+
+
+def test_engine_reports_the_variant_it_selects():
+    """mtb_kernel_variant (C ABI) agrees with the host build of pick_variant() on every case of
+    tests/test_device_loop_host.py::VARIANT_CASES."""
+    from tests.test_device_loop_host import VARIANT_CASES, setup_variant_case
+    for sample, cfg, want in VARIANT_CASES:
+        with capi.Engine(**cfg) as eng:
+            setup_variant_case(eng, sample)
+            assert eng.kernel_variant() == want, (sample, cfg)
