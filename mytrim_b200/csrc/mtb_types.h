@@ -180,7 +180,9 @@ enum
   POOL_IDLE = 3,    // lanes polling the pool
   POOL_CTL_COUNT = 4
 };
+#ifndef MTB_POOL_SLOTS
 #define MTB_POOL_SLOTS 32 // per CTA, power of two
+#endif
 
 struct RangeEntry
 {

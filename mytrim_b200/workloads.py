@@ -56,7 +56,7 @@ BENCH_WORKLOADS = {
                                           desc="Xe->ZrO2 500 keV, 50 x 10 A layers, TrimRecoils as in apps/mytrim_layers.C "
                                                "(recoils of generation < 2 followed, Kinchin-Pease for generation 2)"),
     # the file-energy / long-cascade variants of configurations 1 and 2
-    "cu_on_cu_150keV": dict(primaries=1 << 17, tally=capi.TALLY_VAC_DEPTH,
+    "cu_on_cu_150keV": dict(primaries=1 << 19, tally=capi.TALLY_VAC_DEPTH,
                             desc="Cu->Cu 150 keV, full cascades, TrimVacCount tallies (tests/json/cu_on_cu.json)"),
     "h_on_fe_1MeV": dict(primaries=1 << 22, tally=capi.TALLY_VAC_DEPTH,
                          desc="H->Fe 1 MeV, full cascades, TrimVacCount tallies (validation/h_on_fe at 1 MeV)"),
