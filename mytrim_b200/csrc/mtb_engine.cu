@@ -525,6 +525,8 @@ build_tables(mtb_handle * h)
   MTB_SETUP_KERNEL(TraitsMonoEvacShare, VARIANT_MONO_EVAC, 1)
   MTB_SETUP_KERNEL(TraitsClustersLog, VARIANT_CLUSTERS_LOG, 0)
   MTB_SETUP_KERNEL(TraitsClustersLogShare, VARIANT_CLUSTERS_LOG, 1)
+  MTB_SETUP_KERNEL(TraitsLayersPlain, VARIANT_LAYERS_PLAIN, 0)
+  MTB_SETUP_KERNEL(TraitsLayersPlainShare, VARIANT_LAYERS_PLAIN, 1)
   MTB_SETUP_KERNEL(TraitsLayers, VARIANT_LAYERS, 0)
   MTB_SETUP_KERNEL(TraitsLayersShare, VARIANT_LAYERS, 1)
   MTB_SETUP_KERNEL(TraitsGeneric, VARIANT_GENERIC, 0)
@@ -596,6 +598,12 @@ launch_kernel(mtb_handle * h, const LaunchParams & P, unsigned blocks, Variant v
         transport_kernel<TraitsClustersLogShare><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
       else
         transport_kernel<TraitsClustersLog><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+      break;
+    case VARIANT_LAYERS_PLAIN:
+      if (share)
+        transport_kernel<TraitsLayersPlainShare><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
+      else
+        transport_kernel<TraitsLayersPlain><<<blocks, kBlock, h->smem_bytes, h->stream>>>(P);
       break;
     case VARIANT_LAYERS:
       if (share)

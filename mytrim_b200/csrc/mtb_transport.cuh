@@ -139,6 +139,10 @@ typedef TraitsT<kFeatClusters, kTallyClusters> TraitsClusters;
 typedef TraitsT<kFeatClusters | F_SHARE, kTallyClusters> TraitsClustersShare;
 typedef TraitsT<kFeatClustersLog, kTallyClustersLog> TraitsClustersLog;
 typedef TraitsT<kFeatClustersLog | F_SHARE, kTallyClustersLog> TraitsClustersLogShare;
+// LAYERS without any tally beyond counters and records: what TrimPrimaries / TrimRecoils (apps/mytrim_layers.C) ask for
+constexpr uint32_t kFeatLayersPlain = F_FOLLOW | F_VACMODEL;
+typedef TraitsT<kFeatLayersPlain, 0u> TraitsLayersPlain;
+typedef TraitsT<kFeatLayersPlain | F_SHARE, 0u> TraitsLayersPlainShare;
 typedef TraitsT<kFeatLayers, kTallyAll> TraitsLayers;
 typedef TraitsT<kFeatLayers | F_SHARE, kTallyAll> TraitsLayersShare;
 typedef TraitsT<kFeatGeneric, kTallyAll> TraitsGeneric;
@@ -163,6 +167,7 @@ enum Variant
   VARIANT_CLUSTERS_LOG,
   VARIANT_MONO_EVAC,
   VARIANT_FAST_PHONON,
+  VARIANT_LAYERS_PLAIN,
   VARIANT_COUNT
 };
 
@@ -180,6 +185,7 @@ variant_name(Variant v)
     case VARIANT_CLUSTERS_LOG: return "CLUSTERS-LOG";
     case VARIANT_MONO_EVAC: return "MONO-EVAC";
     case VARIANT_FAST_PHONON: return "FAST-PHONON";
+    case VARIANT_LAYERS_PLAIN: return "LAYERS-PLAIN";
     default: return "?";
   }
 }
@@ -187,7 +193,7 @@ variant_name(Variant v)
 inline uint32_t
 variant_features(Variant v)
 {
-  return (v == VARIANT_FAST || v == VARIANT_FAST_PHONON) ? kFeatFast : (v == VARIANT_MONO || v == VARIANT_MONO_EVAC) ? kFeatMono : v == VARIANT_MONO_NOREC ? (kFeatMono | F_NOREC) : v == VARIANT_CLUSTERS ? kFeatClusters : v == VARIANT_CLUSTERS_LOG ? kFeatClustersLog : v == VARIANT_LAYERS ? kFeatLayers : kFeatGeneric;
+  return (v == VARIANT_FAST || v == VARIANT_FAST_PHONON) ? kFeatFast : (v == VARIANT_MONO || v == VARIANT_MONO_EVAC) ? kFeatMono : v == VARIANT_MONO_NOREC ? (kFeatMono | F_NOREC) : v == VARIANT_CLUSTERS ? kFeatClusters : v == VARIANT_CLUSTERS_LOG ? kFeatClustersLog : v == VARIANT_LAYERS ? kFeatLayers : v == VARIANT_LAYERS_PLAIN ? kFeatLayersPlain : kFeatGeneric;
 }
 
 // Features a configuration needs (F_CUSTOM is decided per primary: variants without it hand
@@ -236,6 +242,8 @@ pick_variant(const LaunchParams & P, bool custom)
     return VARIANT_CLUSTERS_LOG;
   if (variant_covers(kFeatClusters, kTallyClusters, P))
     return VARIANT_CLUSTERS;
+  if (!custom && variant_covers(kFeatLayersPlain, 0u, P))
+    return VARIANT_LAYERS_PLAIN;
   if (!custom && variant_covers(kFeatLayers, kTallyAll, P))
     return VARIANT_LAYERS;
   return VARIANT_GENERIC;

@@ -211,6 +211,8 @@ hs_run(hs_engine * e, uint64_t n, const mtb_ion * primaries, uint64_t seed, uint
       lane_loop<TraitsMonoEvac>(P, S, 0);
     else if (which == VARIANT_CLUSTERS_LOG)
       lane_loop<TraitsClustersLog>(P, S, 0);
+    else if (which == VARIANT_LAYERS_PLAIN)
+      lane_loop<TraitsLayersPlain>(P, S, 0);
     else if (which == VARIANT_LAYERS)
       lane_loop<TraitsLayers>(P, S, 0);
     else

@@ -613,7 +613,9 @@ VARIANT_CASES = [
     ("c_on_w_1MeV", dict(tally_mask=capi.TALLY_VAC_ENERGY), "MONO-EVAC"),                      # validation/c_on_w/input.json
     ("xe_on_zro2_500keV", dict(tally_mask=capi.TALLY_VAC_DEPTH), "FAST"),                       # compound stack, folded
     ("xe_on_zro2_500keV", dict(tally_mask=capi.TALLY_PHONON | capi.TALLY_RECORDS), "FAST-PHONON"),
-    ("xe_on_zro2_500keV", dict(follow=capi.FOLLOW_GEN_LT, follow_max_gen=2, vacancy_model=capi.VAC_KP), "LAYERS"),   # mytrim_layers
+    ("xe_on_zro2_500keV", dict(follow=capi.FOLLOW_GEN_LT, follow_max_gen=2, vacancy_model=capi.VAC_KP), "LAYERS-PLAIN"),   # mytrim_layers
+    ("xe_on_zro2_500keV", dict(follow=capi.FOLLOW_GEN_LT, follow_max_gen=2, vacancy_model=capi.VAC_KP,
+                               tally_mask=capi.TALLY_RECORDS | capi.TALLY_VACMAP), "LAYERS"),
     ("cu_on_cu_10keV", dict(follow=capi.FOLLOW_NONE, vacancy_model=capi.VAC_NRT, tally_mask=capi.TALLY_RANGE), "LAYERS"),
     ("cu_on_cu_10keV", dict(tally_mask=capi.TALLY_VAC_ENERGY | capi.TALLY_VAC_DEPTH), "LAYERS"),
     ("cu_on_cu_10keV", dict(tally_mask=capi.TALLY_VAC_DEPTH, potential=capi.POT_MOLIERE), "GENERIC"),
