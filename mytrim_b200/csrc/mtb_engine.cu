@@ -66,6 +66,9 @@ constexpr int kBlock = MTB_BLOCK;
 #ifndef MTB_MIN_BLOCKS_FAST_SHARE
 #define MTB_MIN_BLOCKS_FAST_SHARE 6
 #endif
+#ifndef MTB_MIN_BLOCKS_MONO_SHARE
+#define MTB_MIN_BLOCKS_MONO_SHARE 7 // 72 registers: C->W -1..-2 %, Cu->Cu 150 keV -4.7 % against 6 (the FAST + share kernel keeps 6), visit o
+#endif
 #ifndef MTB_MIN_BLOCKS_CLUSTERS_SHARE
 #define MTB_MIN_BLOCKS_CLUSTERS_SHARE 5 // 93 registers, no spills: -4.5..-7 % on the tests/uo2 workload against 6 (80 registers, spills), r02l
 #endif
@@ -81,6 +84,7 @@ min_blocks()
 {
   return (TR::kF & F_NOREC)                 ? MTB_MIN_BLOCKS_MONO_NOREC
          : (TR::kF & F_MONO) && !TR::kShare ? MTB_MIN_BLOCKS_MONO
+         : (TR::kF & F_MONO)                ? MTB_MIN_BLOCKS_MONO_SHARE
          : TR::kF & F_GEOM_ANY ? (TR::kShare ? MTB_MIN_BLOCKS_GENERIC_SHARE : MTB_MIN_BLOCKS_GENERIC)
          : TR::kF & F_CLUSTERS ? (TR::kShare ? MTB_MIN_BLOCKS_CLUSTERS_SHARE : MTB_MIN_BLOCKS_CLUSTERS)
          : TR::kF & F_FOLLOW   ? (TR::kShare ? MTB_MIN_BLOCKS_LAYERS_SHARE : MTB_MIN_BLOCKS_CLUSTERS)
